@@ -1,0 +1,627 @@
+// Host side of the ResNet-50 trunk: tile planning + tensor maps for conv_gemm_kernel, BN folding,
+// max/avg pooling kernels, the irp_resnet50 handle and the single-conv parity hook.
+// Architecture follows torchvision/models/resnet.py:108-160 (Bottleneck, stride on the 3x3), :197-205 (stem),
+// :266-282 (_forward_impl) with the fc dropped as in functions/data_curation.py:658.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.h"
+#include "conv_gemm.cuh"
+
+namespace irp {
+
+// ------------------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------------------
+
+// Fold eval-mode BatchNorm into the conv: w'[co,r,s,ci] = w[co,ci,r,s] * g/sqrt(v+eps), b' = beta - mean*g/sqrt(v+eps).
+// Output layout [Cout][kh][kw_pad][cin_pad] (zero filled where s >= kw or ci >= cin): the K-major B operand.
+__global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, float eps, int cout, int cin, int kh, int kw,
+                               int kw_pad, int cin_pad, __nv_bfloat16* __restrict__ w_out,
+                               float* __restrict__ bias_out) {
+  const int k_pad = kh * kw_pad * cin_pad;
+  const long long total = static_cast<long long>(cout) * k_pad;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i / k_pad);
+    int rem = static_cast<int>(i % k_pad);
+    const int ci = rem % cin_pad;
+    rem /= cin_pad;
+    const int s = rem % kw_pad;
+    const int r = rem / kw_pad;
+    const float scale = gamma[co] / sqrtf(var[co] + eps);
+    float v = 0.f;
+    if (ci < cin && s < kw) v = w[((static_cast<size_t>(co) * cin + ci) * kh + r) * kw + s] * scale;
+    w_out[i] = __float2bfloat16_rn(v);
+    if (i % k_pad == 0) bias_out[co] = beta[co] - mean[co] * scale;
+  }
+}
+
+// 3x3 / stride 2 / pad 1 max pooling, NHWC bf16, 8 channels (16 bytes) per thread.
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
+                                    int W, int C, int Ho, int Wo) {
+  const int cg = C / 8;
+  const long long total = static_cast<long long>(B) * Ho * Wo * cg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    long long pix = i / cg;
+    const int wo = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int ho = static_cast<int>(pix % Ho);
+    const int n = static_cast<int>(pix / Ho);
+    __nv_bfloat162 m[4];
+    bool first = true;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = ho * 2 + r - 1;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = wo * 2 + s - 1;
+        if (w < 0 || w >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + h) * W + w) * C) + g);
+        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+        if (first) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m[j] = pv[j];
+          first = false;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], pv[j]);
+        }
+      }
+    }
+    uint4 o;
+    memcpy(&o, m, sizeof(o));
+    reinterpret_cast<uint4*>(y + ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C)[g] = o;
+  }
+}
+
+// Global average pool: NHWC bf16 [B, HW, C] -> fp32 [B, C]; one thread per (image, channel pair).
+__global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
+  const int c2 = C / 2;
+  const long long total = static_cast<long long>(B) * c2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c2);
+    const int n = static_cast<int>(i / c2);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(x + static_cast<size_t>(n) * HW * C) + c;
+    float s0 = 0.f, s1 = 0.f;
+    for (int j = 0; j < HW; ++j) {
+      const uint32_t v = __ldg(p + static_cast<size_t>(j) * c2);
+      s0 += bf16_lo(v);
+      s1 += bf16_hi(v);
+    }
+    const float inv = 1.0f / static_cast<float>(HW);
+    y[static_cast<size_t>(n) * C + 2 * c] = s0 * inv;
+    y[static_cast<size_t>(n) * C + 2 * c + 1] = s1 * inv;
+  }
+}
+
+// Fallback stem feed: explicit im2col of the padded NHWC4 input into [B*112*112, 192] bf16
+// (K index = (r*7+s)*3+c for the first 147 entries, zero after).
+__global__ void stem_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ a, int B) {
+  constexpr int kK = 192, kP = IRP_PAD_HW;
+  const long long total = static_cast<long long>(B) * 112 * 112 * (kK / 8);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % (kK / 8));
+    long long pix = i / (kK / 8);
+    const int wo = static_cast<int>(pix % 112);
+    pix /= 112;
+    const int ho = static_cast<int>(pix % 112);
+    const int n = static_cast<int>(pix / 112);
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      __nv_bfloat16 e = __float2bfloat16_rn(0.f);
+      if (k < 147) {
+        const int c = k % 3, s = (k / 3) % 7, r = k / 21;
+        e = x[((static_cast<size_t>(n) * kP + (2 * ho + r)) * kP + (2 * wo + s)) * 4 + c];
+      }
+      v[j] = e;
+    }
+    uint4 o;
+    memcpy(&o, v, sizeof(o));
+    reinterpret_cast<uint4*>(a)[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// conv planning
+// ------------------------------------------------------------------------------------------------------------
+enum ConvKind { kConvFlat = 0, kConvSpatial = 1, kConvStem = 2 };
+
+struct ConvPlan {
+  ConvParams p;
+  int bn_tile = 128;  // BN of the kernel instance
+  ConvKind kind = kConvFlat;
+  int H = 0, W = 0, cin = 0, ksize = 1, stride = 1;
+  int max_batch = 0;
+};
+
+// Choose the (bw,bh,bn) output box with bw*bh*bn <= 128 that minimises the number of M tiles.
+static void choose_box(int Wo, int Ho, int B, int* bw, int* bh, int* bn) {
+  long long best_tiles = -1;
+  int best[3] = {1, 1, 1};
+  for (int w = 1; w <= Wo && w <= kTileM; ++w) {
+    for (int h = 1; h <= Ho && w * h <= kTileM; ++h) {
+      int n = kTileM / (w * h);
+      if (n > B) n = B;
+      if (n < 1) continue;
+      const long long tiles = static_cast<long long>(ceil_div(Wo, w)) * ceil_div(Ho, h) * ceil_div(B, n);
+      const bool better = best_tiles < 0 || tiles < best_tiles ||
+                          (tiles == best_tiles && (w > best[0] || (w == best[0] && h > best[1])));
+      if (better) {
+        best_tiles = tiles;
+        best[0] = w;
+        best[1] = h;
+        best[2] = n;
+      }
+    }
+  }
+  *bw = best[0];
+  *bh = best[1];
+  *bn = best[2];
+}
+
+static inline int floor_div2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
+
+// Builds tensor maps + static fields. x/w/out pointers are baked into the maps / params.
+static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* bias, const void* residual,
+                     void* out, int max_batch, int H, int W, int Cin, int Cout, int ksize, int stride, int relu) {
+  IRP_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv: Cin (%d) and Cout (%d) must be multiples of 64", Cin, Cout);
+  IRP_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "conv: unsupported ksize %d stride %d",
+              ksize, stride);
+  const int pad = ksize == 3 ? 1 : 0;
+  const int Ho = (H + 2 * pad - ksize) / stride + 1;
+  const int Wo = (W + 2 * pad - ksize) / stride + 1;
+  ConvParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  plan->H = H;
+  plan->W = W;
+  plan->cin = Cin;
+  plan->ksize = ksize;
+  plan->stride = stride;
+  plan->max_batch = max_batch;
+  plan->bn_tile = (Cout % 128 == 0) ? 128 : 64;
+  constexpr int BK = 64;
+  p.Cout = Cout;
+  p.cin = Cin;
+  p.kc_blocks = Cin / BK;
+  p.ntaps = ksize * ksize;
+  p.bias = bias;
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.relu = relu;
+  p.n_tiles_n = Cout / plan->bn_tile;
+
+  char* xb = static_cast<char*>(const_cast<void*>(x));
+  if (ksize == 1 && stride == 1) {
+    // flattened: A is the plain [M, Cin] matrix, M = B*H*W
+    plan->kind = kConvFlat;
+    const uint64_t M = static_cast<uint64_t>(max_batch) * H * W;
+    uint64_t dims[4] = {static_cast<uint64_t>(Cin), M, 1, 1};
+    uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 2, M * Cin * 2, M * Cin * 2};
+    uint32_t box[4] = {BK, kTileM, 1, 1};
+    IRP_TRY(encode_bf16_map(&p.tmA[0], xb, 4, dims, strides, box, 128));
+    p.bw = kTileM;
+    p.bh = 1;
+    p.bn = 1;
+    p.tap_map[0] = 0;
+    p.tap_dw[0] = 0;
+    p.tap_dh[0] = 0;
+  } else {
+    plan->kind = kConvSpatial;
+    choose_box(Wo, Ho, max_batch, &p.bw, &p.bh, &p.bn);
+    uint32_t box[4] = {BK, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
+    if (stride == 1) {
+      uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                          static_cast<uint64_t>(max_batch)};
+      uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(W) * Cin * 2,
+                             static_cast<uint64_t>(H) * W * Cin * 2};
+      IRP_TRY(encode_bf16_map(&p.tmA[0], xb, 4, dims, strides, box, 128));
+      for (int r = 0; r < ksize; ++r)
+        for (int s = 0; s < ksize; ++s) {
+          const int t = r * ksize + s;
+          p.tap_map[t] = 0;
+          p.tap_dw[t] = static_cast<int8_t>(s - pad);
+          p.tap_dh[t] = static_cast<int8_t>(r - pad);
+        }
+    } else {
+      // four parity views: element (c, ww, hh, n) of view (ph,pw) is x[n, 2*hh+ph, 2*ww+pw, c]
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>((W - pw + 1) / 2),
+                              static_cast<uint64_t>((H - ph + 1) / 2), static_cast<uint64_t>(max_batch)};
+          uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 4, static_cast<uint64_t>(W) * Cin * 4,
+                                 static_cast<uint64_t>(H) * W * Cin * 2};
+          IRP_TRY(encode_bf16_map(&p.tmA[ph * 2 + pw], xb + (static_cast<size_t>(ph) * W + pw) * Cin * 2, 4, dims,
+                                  strides, box, 128));
+        }
+      for (int r = 0; r < ksize; ++r)
+        for (int s = 0; s < ksize; ++s) {
+          const int t = r * ksize + s;
+          const int dh = r - pad, dw = s - pad;
+          p.tap_map[t] = static_cast<int8_t>((dh & 1) * 2 + (dw & 1));
+          p.tap_dw[t] = static_cast<int8_t>(floor_div2(dw));
+          p.tap_dh[t] = static_cast<int8_t>(floor_div2(dh));
+        }
+    }
+  }
+  p.a_box_bytes = p.bw * p.bh * p.bn * BK * 2;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  // weights: [Cout][taps*Cin]
+  {
+    const uint64_t K = static_cast<uint64_t>(p.ntaps) * Cin;
+    uint64_t dims[2] = {K, static_cast<uint64_t>(Cout)};
+    uint64_t strides[1] = {K * 2};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(plan->bn_tile)};
+    IRP_TRY(encode_bf16_map(&p.tmB, const_cast<void*>(w), 2, dims, strides, box, 128));
+  }
+  return IRP_OK;
+}
+
+template <int BN, int BK, bool STEM>
+static int launch_instance(const ConvParams& p, cudaStream_t stream) {
+  using S = ConvSmem<BN, BK>;
+  static bool configured = false;
+  auto kernel = conv_gemm_kernel<BN, BK, STEM>;
+  if (!configured) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
+    configured = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (grid <= 0) return IRP_OK;
+  kernel<<<grid, kConvThreads, S::kTotalBytes, stream>>>(p);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+// Launch a planned conv on `batch` images (batch <= plan->max_batch).
+static int launch_conv(const ConvPlan& plan, int batch, cudaStream_t stream) {
+  ConvParams p = plan.p;
+  if (plan.kind == kConvFlat) {
+    const long long M = static_cast<long long>(batch) * plan.p.Ho * plan.p.Wo;
+    p.B = 1;
+    p.Ho = 1;
+    p.Wo = static_cast<int>(M);
+    p.tiles_w = static_cast<int>(ceil_div64(M, kTileM));
+    p.tiles_h = 1;
+    p.tiles_n = 1;
+  } else {
+    p.B = batch;
+    p.tiles_w = ceil_div(p.Wo, p.bw);
+    p.tiles_h = ceil_div(p.Ho, p.bh);
+    p.tiles_n = ceil_div(batch, p.bn);
+  }
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
+  if (plan.kind == kConvStem) return launch_instance<64, 32, true>(p, stream);
+  if (plan.bn_tile == 128) return launch_instance<128, 64, false>(p, stream);
+  return launch_instance<64, 64, false>(p, stream);
+}
+
+// Stem through the overlapping 5-D TMA view of the padded NHWC4 input (see conv_gemm.cuh, STEM path).
+static int plan_stem_tma(ConvPlan* plan, const void* x_nhwc4p, const void* w, const float* bias, void* out,
+                         int max_batch) {
+  ConvParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  plan->kind = kConvStem;
+  plan->bn_tile = 64;
+  plan->max_batch = max_batch;
+  constexpr int P = IRP_PAD_HW;
+  p.Cout = 64;
+  p.cin = 32;  // K per filter row: 8 pixels x 4 channels
+  p.kc_blocks = 1;
+  p.ntaps = 7;
+  p.bias = bias;
+  p.residual = nullptr;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.relu = 1;
+  p.n_tiles_n = 1;
+  p.Ho = 112;
+  p.Wo = 112;
+  p.bw = 16;
+  p.bh = 8;
+  p.bn = 1;
+  p.a_box_bytes = kTileM * 32 * 2;
+  uint64_t dims[5] = {32, 112, 2, P / 2, static_cast<uint64_t>(max_batch)};
+  uint64_t strides[4] = {16, static_cast<uint64_t>(P) * 8, static_cast<uint64_t>(P) * 16,
+                         static_cast<uint64_t>(P) * P * 8};
+  uint32_t box[5] = {32, 16, 1, 8, 1};
+  IRP_TRY(encode_bf16_map(&p.tmA[0], const_cast<void*>(x_nhwc4p), 5, dims, strides, box, 64));
+  uint64_t wd[2] = {7 * 32, 64};
+  uint64_t ws[1] = {7 * 32 * 2};
+  uint32_t wb[2] = {32, 64};
+  IRP_TRY(encode_bf16_map(&p.tmB, const_cast<void*>(w), 2, wd, ws, wb, 64));
+  return IRP_OK;
+}
+
+static int grid_for(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace irp
+
+// ------------------------------------------------------------------------------------------------------------
+// irp_resnet50 handle
+// ------------------------------------------------------------------------------------------------------------
+using namespace irp;
+
+namespace {
+
+struct ConvSpec {
+  int cin, cout, ksize, stride;
+  int H, W;        // input spatial size
+  int block;       // bottleneck index (-1 for the stem)
+  int role;        // 0 stem, 1 conv1, 2 conv2, 3 conv3, 4 downsample
+};
+
+// execution-independent index order: conv1, then per block conv1, conv2, conv3[, downsample]
+static std::vector<ConvSpec> build_specs() {
+  std::vector<ConvSpec> v;
+  v.push_back({3, 64, 7, 2, 224, 224, -1, 0});
+  const int planes[4] = {64, 128, 256, 512};
+  const int blocks[4] = {3, 4, 6, 3};
+  int inplanes = 64, hw = 56, blk = 0;
+  for (int l = 0; l < 4; ++l) {
+    for (int b = 0; b < blocks[l]; ++b, ++blk) {
+      const int stride = (b == 0 && l > 0) ? 2 : 1;
+      const int width = planes[l];
+      v.push_back({inplanes, width, 1, 1, hw, hw, blk, 1});
+      v.push_back({width, width, 3, stride, hw, hw, blk, 2});
+      const int hw_out = hw / stride;
+      v.push_back({width, width * 4, 1, 1, hw_out, hw_out, blk, 3});
+      if (b == 0) v.push_back({inplanes, width * 4, 1, stride, hw, hw, blk, 4});
+      inplanes = width * 4;
+      hw = hw_out;
+    }
+  }
+  return v;
+}
+
+static const std::vector<ConvSpec>& specs() {
+  static const std::vector<ConvSpec> s = build_specs();
+  return s;
+}
+
+}  // namespace
+
+struct irp_resnet50 {
+  int max_batch = 0;
+  int stem_mode = 0;  // 0: overlapping TMA view, 1: explicit im2col + flat GEMM
+  std::vector<ConvPlan> plans;
+  std::vector<__nv_bfloat16*> weights;
+  std::vector<float*> biases;
+  std::vector<int> out_buf;  // arena buffer id holding each conv's output
+  // arena
+  __nv_bfloat16* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // A, B, T1, T2, DS, STEM
+  __nv_bfloat16* im2col = nullptr;
+  const void* planned_input = nullptr;
+  ConvPlan stem_plan_tma;
+  bool planned = false;
+};
+
+static size_t weight_elems(const ConvSpec& s, int stem_mode) {
+  if (s.role == 0) return stem_mode == 0 ? 64 * 7 * 8 * 4 : 64 * 192;
+  return static_cast<size_t>(s.cout) * s.ksize * s.ksize * s.cin;
+}
+
+static int resnet50_plan(irp_resnet50* net, const void* d_x) {
+  const auto& sp = specs();
+  const int B = net->max_batch;
+  enum { A = 0, Bb = 1, T1 = 2, T2 = 3, DS = 4, STEM = 5 };
+  // stem
+  if (net->stem_mode == 0) {
+    IRP_TRY(plan_stem_tma(&net->plans[0], d_x, net->weights[0], net->biases[0], net->buf[STEM], B));
+  } else {
+    IRP_TRY(plan_conv(&net->plans[0], net->im2col, net->weights[0], net->biases[0], nullptr, net->buf[STEM], B, 112,
+                      112, 192, 64, 1, 1, 1));
+  }
+  net->out_buf[0] = STEM;
+  int cur = A, other = Bb;
+  size_t i = 1;
+  while (i < sp.size()) {
+    const bool has_ds = (i + 3 < sp.size()) && sp[i + 3].role == 4;
+    const ConvSpec &c1 = sp[i], &c2 = sp[i + 1], &c3 = sp[i + 2];
+    IRP_TRY(plan_conv(&net->plans[i], net->buf[cur], net->weights[i], net->biases[i], nullptr, net->buf[T1], B, c1.H,
+                      c1.W, c1.cin, c1.cout, 1, 1, 1));
+    net->out_buf[i] = T1;
+    IRP_TRY(plan_conv(&net->plans[i + 1], net->buf[T1], net->weights[i + 1], net->biases[i + 1], nullptr,
+                      net->buf[T2], B, c2.H, c2.W, c2.cin, c2.cout, 3, c2.stride, 1));
+    net->out_buf[i + 1] = T2;
+    const __nv_bfloat16* res = net->buf[cur];
+    if (has_ds) {
+      const ConvSpec& d = sp[i + 3];
+      IRP_TRY(plan_conv(&net->plans[i + 3], net->buf[cur], net->weights[i + 3], net->biases[i + 3], nullptr,
+                        net->buf[DS], B, d.H, d.W, d.cin, d.cout, 1, d.stride, 0));
+      net->out_buf[i + 3] = DS;
+      res = net->buf[DS];
+    }
+    IRP_TRY(plan_conv(&net->plans[i + 2], net->buf[T2], net->weights[i + 2], net->biases[i + 2], res,
+                      net->buf[other], B, c3.H, c3.W, c3.cin, c3.cout, 1, 1, 1));
+    net->out_buf[i + 2] = other;
+    const int t = cur;
+    cur = other;
+    other = t;
+    i += has_ds ? 4 : 3;
+  }
+  net->planned_input = d_x;
+  net->planned = true;
+  return IRP_OK;
+}
+
+extern "C" {
+
+int irp_resnet50_conv_shape(int index, int* cout, int* cin, int* kh, int* kw, int* stride) {
+  const auto& sp = specs();
+  IRP_REQUIRE(index >= 0 && index < static_cast<int>(sp.size()), "conv index %d out of range", index);
+  if (cout) *cout = sp[index].cout;
+  if (cin) *cin = sp[index].cin;
+  if (kh) *kh = sp[index].ksize;
+  if (kw) *kw = sp[index].ksize;
+  if (stride) *stride = sp[index].stride;
+  return IRP_OK;
+}
+
+int irp_resnet50_create(irp_resnet50** out, int max_batch) {
+  IRP_REQUIRE(out != nullptr && max_batch > 0, "irp_resnet50_create: bad arguments");
+  IRP_REQUIRE(max_batch <= 4096, "irp_resnet50_create: max_batch %d > 4096", max_batch);
+  irp_resnet50* net = new (std::nothrow) irp_resnet50();
+  if (!net) return IRP_ERR_NOMEM;
+  const auto& sp = specs();
+  net->max_batch = max_batch;
+  const char* mode = getenv("IRP_STEM_MODE");
+  net->stem_mode = (mode && mode[0] == '1') ? 1 : 0;
+  net->plans.resize(sp.size());
+  net->weights.assign(sp.size(), nullptr);
+  net->biases.assign(sp.size(), nullptr);
+  net->out_buf.assign(sp.size(), -1);
+  const size_t per_img[6] = {56 * 56 * 256, 56 * 56 * 256, 56 * 56 * 128, 56 * 56 * 64, 56 * 56 * 256,
+                             112 * 112 * 64};
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+    e = cudaMalloc(reinterpret_cast<void**>(&net->buf[i]), per_img[i] * max_batch * sizeof(__nv_bfloat16));
+  if (e == cudaSuccess && net->stem_mode == 1)
+    e = cudaMalloc(reinterpret_cast<void**>(&net->im2col),
+                   static_cast<size_t>(max_batch) * 112 * 112 * 192 * sizeof(__nv_bfloat16));
+  for (size_t i = 0; i < sp.size() && e == cudaSuccess; ++i) {
+    e = cudaMalloc(reinterpret_cast<void**>(&net->weights[i]),
+                   weight_elems(sp[i], net->stem_mode) * sizeof(__nv_bfloat16));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&net->biases[i]), sp[i].cout * sizeof(float));
+  }
+  if (e != cudaSuccess) {
+    set_last_error("irp_resnet50_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    irp_resnet50_destroy(net);
+    return IRP_ERR_NOMEM;
+  }
+  *out = net;
+  return IRP_OK;
+}
+
+void irp_resnet50_destroy(irp_resnet50* net) {
+  if (!net) return;
+  for (auto& b : net->buf) cudaFree(b);
+  cudaFree(net->im2col);
+  for (auto* w : net->weights) cudaFree(w);
+  for (auto* b : net->biases) cudaFree(b);
+  delete net;
+}
+
+int irp_resnet50_load_conv(irp_resnet50* net, int index, const float* d_weight_oihw, const float* d_gamma,
+                           const float* d_beta, const float* d_mean, const float* d_var, float eps, void* stream) {
+  const auto& sp = specs();
+  IRP_REQUIRE(net != nullptr && index >= 0 && index < static_cast<int>(sp.size()), "load_conv: bad index %d", index);
+  const ConvSpec& s = sp[index];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int kw_pad = s.ksize, cin_pad = s.cin;
+  if (s.role == 0 && net->stem_mode == 0) {
+    kw_pad = 8;
+    cin_pad = 4;
+  }
+  if (s.role == 0 && net->stem_mode == 1) {
+    // [64][192]: first 147 = (r,s,c) order, rest zero -> fold into [64][7][7][3] then pad on the device
+    IRP_CUDA_OK(cudaMemsetAsync(net->weights[0], 0, 64 * 192 * sizeof(__nv_bfloat16), st));
+    __nv_bfloat16* tmp = nullptr;
+    IRP_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&tmp), 64 * 147 * sizeof(__nv_bfloat16)));
+    fold_bn_kernel<<<grid_for(64 * 147, 256), 256, 0, st>>>(d_weight_oihw, d_gamma, d_beta, d_mean, d_var, eps, 64,
+                                                             3, 7, 7, 7, 3, tmp, net->biases[0]);
+    IRP_CUDA_OK(cudaGetLastError());
+    IRP_CUDA_OK(cudaMemcpy2DAsync(net->weights[0], 192 * sizeof(__nv_bfloat16), tmp, 147 * sizeof(__nv_bfloat16),
+                                  147 * sizeof(__nv_bfloat16), 64, cudaMemcpyDeviceToDevice, st));
+    IRP_CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+    return IRP_OK;
+  }
+  const long long total = static_cast<long long>(s.cout) * s.ksize * kw_pad * cin_pad;
+  fold_bn_kernel<<<grid_for(total, 256), 256, 0, st>>>(d_weight_oihw, d_gamma, d_beta, d_mean, d_var, eps, s.cout,
+                                                       s.cin, s.ksize, s.ksize, kw_pad, cin_pad, net->weights[index],
+                                                       net->biases[index]);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float* d_embed, int capture_index,
+                            void* d_capture, size_t capture_capacity, cudaStream_t st) {
+  IRP_REQUIRE(net != nullptr && d_x != nullptr && d_embed != nullptr, "embed: null argument");
+  IRP_REQUIRE(batch > 0 && batch <= net->max_batch, "embed: batch %d not in [1,%d]", batch, net->max_batch);
+  if (!net->planned || net->planned_input != d_x) IRP_TRY(resnet50_plan(net, d_x));
+  const auto& sp = specs();
+  enum { A = 0, STEM = 5 };
+  auto capture = [&](int idx) -> int {
+    if (idx != capture_index || d_capture == nullptr) return IRP_OK;
+    const ConvSpec& s = sp[idx];
+    const int ho = s.role == 0 ? 112 : s.H / s.stride, wo = s.role == 0 ? 112 : s.W / s.stride;
+    const size_t elems = static_cast<size_t>(batch) * ho * wo * s.cout;
+    IRP_REQUIRE(elems <= capture_capacity, "capture buffer too small: need %zu elements", elems);
+    IRP_CUDA_OK(cudaMemcpyAsync(d_capture, net->buf[net->out_buf[idx]], elems * sizeof(__nv_bfloat16),
+                                cudaMemcpyDeviceToDevice, st));
+    return IRP_OK;
+  };
+  if (net->stem_mode == 1) {
+    const long long total = static_cast<long long>(batch) * 112 * 112 * (192 / 8);
+    stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(d_x), net->im2col,
+                                                             batch);
+    IRP_CUDA_OK(cudaGetLastError());
+  }
+  IRP_TRY(launch_conv(net->plans[0], batch, st));
+  IRP_TRY(capture(0));
+  {
+    const long long total = static_cast<long long>(batch) * 56 * 56 * (64 / 8);
+    maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(net->buf[STEM], net->buf[A], batch, 112, 112, 64, 56,
+                                                              56);
+    IRP_CUDA_OK(cudaGetLastError());
+  }
+  size_t i = 1;
+  int last = 0;
+  while (i < sp.size()) {
+    const bool has_ds = (i + 3 < sp.size()) && sp[i + 3].role == 4;
+    IRP_TRY(launch_conv(net->plans[i], batch, st));
+    IRP_TRY(capture(static_cast<int>(i)));
+    IRP_TRY(launch_conv(net->plans[i + 1], batch, st));
+    IRP_TRY(capture(static_cast<int>(i + 1)));
+    if (has_ds) {
+      IRP_TRY(launch_conv(net->plans[i + 3], batch, st));
+      IRP_TRY(capture(static_cast<int>(i + 3)));
+    }
+    IRP_TRY(launch_conv(net->plans[i + 2], batch, st));
+    IRP_TRY(capture(static_cast<int>(i + 2)));
+    last = static_cast<int>(i + 2);
+    i += has_ds ? 4 : 3;
+  }
+  {
+    const long long total = static_cast<long long>(batch) * (2048 / 2);
+    avgpool_kernel<<<grid_for(total, 128), 128, 0, st>>>(net->buf[net->out_buf[last]], d_embed, batch, 49, 2048);
+    IRP_CUDA_OK(cudaGetLastError());
+  }
+  return IRP_OK;
+}
+
+int irp_resnet50_embed(irp_resnet50* net, const void* d_x_nhwc4p, int batch, float* d_embed, void* stream) {
+  return resnet50_forward(net, d_x_nhwc4p, batch, d_embed, -1, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int irp_resnet50_embed_capture(irp_resnet50* net, const void* d_x_nhwc4p, int batch, float* d_embed,
+                               int capture_index, void* d_capture_bf16, size_t capacity_elems, void* stream) {
+  return resnet50_forward(net, d_x_nhwc4p, batch, d_embed, capture_index, d_capture_bf16, capacity_elems,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int irp_conv2d_nhwc(const void* d_x, const void* d_w, const float* d_bias, const void* d_residual, void* d_out,
+                    int B, int H, int W, int Cin, int Cout, int ksize, int stride, int relu, void* stream) {
+  IRP_REQUIRE(d_x && d_w && d_bias && d_out && B > 0 && H > 0 && W > 0, "conv2d: bad arguments");
+  ConvPlan plan;
+  IRP_TRY(plan_conv(&plan, d_x, d_w, d_bias, d_residual, d_out, B, H, W, Cin, Cout, ksize, stride, relu));
+  return launch_conv(plan, B, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

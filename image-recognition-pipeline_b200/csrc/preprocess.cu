@@ -1,0 +1,359 @@
+// A1 preprocessing: ragged uint8 HWC batch -> resize(232, Pillow antialiased bilinear) -> center crop 224 ->
+// /255 -> (x-mean)/std -> bf16, in one pass over the pixels.
+//
+// Replaces `transform(img)` at functions/data_curation.py:675 (ResNet50_Weights.DEFAULT.transforms(),
+// torchvision/transforms/_presets.py ImageClassification.forward; output size per
+// torchvision/transforms/functional.py:359-384, crop offsets per :592-593).  The resample arithmetic restates
+// Pillow's ImagingResample for 8-bit images (src/libImaging/Resample.c in Pillow 11/12: precompute_coeffs,
+// normalize_coeffs_8bpc with PRECISION_BITS = 22, horizontal pass then vertical pass, each rounded and clipped
+// to uint8).  oracle/pil_resample.py is the numpy restatement checked bit-for-bit against Pillow itself.
+//
+// Two kernels:
+//   resample_plan_kernel : per image, per axis, for the 224 output indices inside the crop window: first source
+//                          index, tap count and the 22-bit fixed-point tap weights (fp64 maths, like Pillow).
+//   resample_kernel      : one CTA per (image, band of 8 output rows): horizontal pass of the source rows the
+//                          band needs into shared memory (uint8, rounded like Pillow), vertical pass into
+//                          registers, LUT normalise, staged in shared memory and written with 16-byte stores.
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace irp {
+
+constexpr int kCrop = IRP_CROP;      // 224
+constexpr int kResize = IRP_RESIZE;  // 232
+constexpr int kPad = IRP_PAD_HW;     // 230
+constexpr int kPrecisionBits = 22;   // Pillow: 32 - 8 - 2
+constexpr int kBandRows = 8;         // output rows per CTA
+constexpr int kChunkRows = 24;       // source rows horizontally filtered per pass
+constexpr int kRowElems = kCrop * 3; // 672 (x, c) elements per filtered row
+constexpr int kThreads = 256;
+constexpr int kElemsPerThread = 3;   // ceil(672 / 256)
+
+// plan layout per image (int32): [axis 0 | axis 1], each axis: first[224], count[224], coef[224][max_taps]
+__host__ __device__ inline size_t plan_ints_per_axis(int max_taps) { return static_cast<size_t>(kCrop) * (2 + max_taps); }
+
+struct Geometry {
+  int out_h, out_w;  // resized size
+  int top, left;     // crop offsets
+};
+
+// torchvision _compute_resized_output_size (short side -> 232, long = int(232*long/short)) + center_crop offsets
+// (Python round = half to even).
+__host__ __device__ inline int round_half_even_div2(int d) {
+  // round(d / 2.0) with ties to even, d >= 0
+  const int q = d >> 1;
+  if ((d & 1) == 0) return q;
+  return (q & 1) ? q + 1 : q;
+}
+__host__ __device__ inline Geometry compute_geometry(int h, int w) {
+  Geometry g;
+  if (w <= h) {
+    g.out_w = kResize;
+    g.out_h = static_cast<int>(static_cast<double>(static_cast<long long>(kResize) * h) / static_cast<double>(w));
+  } else {
+    g.out_h = kResize;
+    g.out_w = static_cast<int>(static_cast<double>(static_cast<long long>(kResize) * w) / static_cast<double>(h));
+  }
+  g.top = round_half_even_div2(g.out_h - kCrop);
+  g.left = round_half_even_div2(g.out_w - kCrop);
+  return g;
+}
+
+__global__ void resample_plan_kernel(const int32_t* __restrict__ hw, int n_images, int max_taps,
+                                     int32_t* __restrict__ plan, int32_t* __restrict__ status) {
+  const int img = blockIdx.x;
+  const int j = threadIdx.x;
+  if (img >= n_images || j >= 2 * kCrop) return;
+  const int axis = j / kCrop;  // 0: horizontal (x), 1: vertical (y)
+  const int o = j % kCrop;
+  const int h = hw[2 * img], w = hw[2 * img + 1];
+  const Geometry g = compute_geometry(h, w);
+  const int in_size = axis == 0 ? w : h;
+  const int out_size = axis == 0 ? g.out_w : g.out_h;
+  const int xx = o + (axis == 0 ? g.left : g.top);
+
+  int32_t* base = plan + (static_cast<size_t>(img) * 2 + axis) * plan_ints_per_axis(max_taps);
+  int32_t* first = base;
+  int32_t* count = base + kCrop;
+  int32_t* coef = base + 2 * kCrop + static_cast<size_t>(o) * max_taps;
+
+  if (in_size == out_size) {  // Pillow skips the pass: identity tap
+    first[o] = xx;
+    count[o] = 1;
+    coef[0] = 1 << kPrecisionBits;
+    return;
+  }
+  // Pillow precompute_coeffs (bilinear: support 1.0), evaluated in fp64 without FMA contraction.
+  const double scale = __ddiv_rn(static_cast<double>(in_size), static_cast<double>(out_size));
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = filterscale;  // 1.0 * filterscale
+  const double center = __dmul_rn(__dadd_rn(static_cast<double>(xx), 0.5), scale);
+  const double ss = __ddiv_rn(1.0, filterscale);
+  int xmin = static_cast<int>(__dadd_rn(__dsub_rn(center, support), 0.5));
+  if (xmin < 0) xmin = 0;
+  int xmax = static_cast<int>(__dadd_rn(__dadd_rn(center, support), 0.5));
+  if (xmax > in_size) xmax = in_size;
+  int n = xmax - xmin;
+  if (n > max_taps) {
+    atomicExch(status, 1);
+    n = max_taps;
+  }
+  double ww = 0.0;
+  for (int x = 0; x < n; ++x) {
+    double a = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
+    if (a < 0.0) a = -a;
+    const double wgt = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+    ww = __dadd_rn(ww, wgt);
+  }
+  for (int x = 0; x < n; ++x) {
+    double a = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
+    if (a < 0.0) a = -a;
+    double wgt = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+    if (ww != 0.0) wgt = __ddiv_rn(wgt, ww);
+    // normalize_coeffs_8bpc: round half away from zero into 22-bit fixed point
+    const double scaled = __dmul_rn(wgt, static_cast<double>(1 << kPrecisionBits));
+    coef[x] = wgt < 0.0 ? static_cast<int>(__dadd_rn(-0.5, scaled)) : static_cast<int>(__dadd_rn(0.5, scaled));
+  }
+  first[o] = xmin;
+  count[o] = n;
+}
+
+__device__ __forceinline__ int clip8_fixed(int acc) {
+  const int v = acc >> kPrecisionBits;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// dynamic smem: int32 hfirst[224], hcount[224], hcoef[224*T], vfirst[8], vcount[8], vcoef[8*T];
+//               bf16 lut[768]; uint8 hbuf[kChunkRows*672]; bf16 obuf[...]
+template <int LAYOUT>
+__global__ void __launch_bounds__(kThreads) resample_kernel(const uint8_t* __restrict__ pixels,
+                                                            const int64_t* __restrict__ offsets,
+                                                            const int32_t* __restrict__ hw, int max_taps,
+                                                            const int32_t* __restrict__ plan,
+                                                            __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int T = max_taps;
+  int32_t* hfirst = reinterpret_cast<int32_t*>(smem);
+  int32_t* hcount = hfirst + kCrop;
+  int32_t* hcoef = hcount + kCrop;
+  int32_t* vfirst = hcoef + kCrop * T;
+  int32_t* vcount = vfirst + kBandRows;
+  int32_t* vcoef = vcount + kBandRows;
+  __nv_bfloat16* lut = reinterpret_cast<__nv_bfloat16*>(vcoef + kBandRows * T);
+  // keep 16-byte alignment for the staged output
+  size_t used = reinterpret_cast<uint8_t*>(lut + 768) - smem;
+  used = (used + 15) & ~static_cast<size_t>(15);
+  uint8_t* hbuf = smem + used;
+  used += static_cast<size_t>(kChunkRows) * kRowElems;
+  used = (used + 15) & ~static_cast<size_t>(15);
+  __nv_bfloat16* obuf = reinterpret_cast<__nv_bfloat16*>(smem + used);
+
+  const int img = blockIdx.y;
+  const int band = blockIdx.x;
+  const int y0 = band * kBandRows;
+  const int tid = threadIdx.x;
+  const int w = hw[2 * img + 1];
+  const uint8_t* src = pixels + offsets[img];
+  const size_t row_bytes = static_cast<size_t>(w) * 3;
+
+  // ---- load plan tables + build the normalisation LUT ----
+  const int32_t* plan_h = plan + (static_cast<size_t>(img) * 2 + 0) * plan_ints_per_axis(T);
+  const int32_t* plan_v = plan + (static_cast<size_t>(img) * 2 + 1) * plan_ints_per_axis(T);
+  for (int i = tid; i < kCrop * (2 + T); i += kThreads) hfirst[i] = plan_h[i];
+  if (tid < kBandRows) {
+    vfirst[tid] = plan_v[y0 + tid];
+    vcount[tid] = plan_v[kCrop + y0 + tid];
+  }
+  for (int i = tid; i < kBandRows * T; i += kThreads) vcoef[i] = plan_v[2 * kCrop + static_cast<size_t>(y0) * T + i];
+  for (int i = tid; i < 768; i += kThreads) {
+    const int c = i >> 8, v = i & 255;
+    const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+    const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+    const float f = __fdiv_rn(static_cast<float>(v), 255.0f);  // to_tensor: u8 -> float / 255
+    lut[i] = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(f, mean), stdv));
+  }
+  __syncthreads();
+
+  // source rows this band needs: [row_lo, row_hi)
+  int row_lo = vfirst[0], row_hi = vfirst[0] + vcount[0];
+#pragma unroll
+  for (int y = 1; y < kBandRows; ++y) {
+    row_lo = min(row_lo, vfirst[y]);
+    row_hi = max(row_hi, vfirst[y] + vcount[y]);
+  }
+
+  int acc[kBandRows][kElemsPerThread];
+#pragma unroll
+  for (int y = 0; y < kBandRows; ++y)
+#pragma unroll
+    for (int k = 0; k < kElemsPerThread; ++k) acc[y][k] = 1 << (kPrecisionBits - 1);
+
+  for (int chunk = row_lo; chunk < row_hi; chunk += kChunkRows) {
+    const int rows = min(kChunkRows, row_hi - chunk);
+    // ---- horizontal pass: rows x 672 elements, rounded to uint8 like Pillow ----
+    for (int idx = tid; idx < rows * kRowElems; idx += kThreads) {
+      const int r = idx / kRowElems;
+      const int e = idx - r * kRowElems;
+      const int x = e / 3;
+      const int c = e - x * 3;
+      const int first = hfirst[x], n = hcount[x];
+      const uint8_t* sp = src + static_cast<size_t>(chunk + r) * row_bytes + static_cast<size_t>(first) * 3 + c;
+      const int32_t* cf = hcoef + x * T;
+      int a = 1 << (kPrecisionBits - 1);
+      for (int t = 0; t < n; ++t) a += static_cast<int>(__ldg(sp + 3 * t)) * cf[t];
+      hbuf[idx] = static_cast<uint8_t>(clip8_fixed(a));
+    }
+    __syncthreads();
+    // ---- vertical pass: accumulate the taps that fall in this chunk ----
+#pragma unroll
+    for (int y = 0; y < kBandRows; ++y) {
+      const int vf = vfirst[y], vn = vcount[y];
+      const int t_lo = max(0, chunk - vf), t_hi = min(vn, chunk + rows - vf);
+      for (int t = t_lo; t < t_hi; ++t) {
+        const int cf = vcoef[y * T + t];
+        const uint8_t* hp = hbuf + (vf + t - chunk) * kRowElems;
+#pragma unroll
+        for (int k = 0; k < kElemsPerThread; ++k) {
+          const int e = tid + k * kThreads;
+          if (e < kRowElems) acc[y][k] += static_cast<int>(hp[e]) * cf;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- normalise + stage ----
+  if (LAYOUT == IRP_LAYOUT_NHWC4P) {
+    // obuf[8][230][4]; zero everything first (borders + pad channel)
+    uint32_t* z = reinterpret_cast<uint32_t*>(obuf);
+    for (int i = tid; i < kBandRows * kPad * 2; i += kThreads) z[i] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int y = 0; y < kBandRows; ++y)
+#pragma unroll
+      for (int k = 0; k < kElemsPerThread; ++k) {
+        const int e = tid + k * kThreads;
+        if (e < kRowElems) {
+          const int x = e / 3, c = e - x * 3;
+          obuf[(y * kPad + 3 + x) * 4 + c] = lut[c * 256 + clip8_fixed(acc[y][k])];
+        }
+      }
+    __syncthreads();
+    // rows y0..y0+7 of image -> padded rows 3+y0.. ; each padded row is 230*8 = 1840 bytes = 115 uint4
+    constexpr int kVecPerRow = kPad * 8 / 16;
+    uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * kPad + 3 + y0) * kPad * 4);
+    const uint4* sv = reinterpret_cast<const uint4*>(obuf);
+    for (int i = tid; i < kBandRows * kVecPerRow; i += kThreads) dst[i] = sv[i];
+    // top / bottom zero borders
+    if (band == 0) {
+      uint4* top = reinterpret_cast<uint4*>(out + static_cast<size_t>(img) * kPad * kPad * 4);
+      for (int i = tid; i < 3 * kVecPerRow; i += kThreads) top[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (band == gridDim.x - 1) {
+      uint4* bot = reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * kPad + 3 + kCrop) * kPad * 4);
+      for (int i = tid; i < 3 * kVecPerRow; i += kThreads) bot[i] = make_uint4(0, 0, 0, 0);
+    }
+  } else {
+    // obuf[3][8][224]
+#pragma unroll
+    for (int y = 0; y < kBandRows; ++y)
+#pragma unroll
+      for (int k = 0; k < kElemsPerThread; ++k) {
+        const int e = tid + k * kThreads;
+        if (e < kRowElems) {
+          const int x = e / 3, c = e - x * 3;
+          obuf[(c * kBandRows + y) * kCrop + x] = lut[c * 256 + clip8_fixed(acc[y][k])];
+        }
+      }
+    __syncthreads();
+    constexpr int kVecPerRow = kCrop * 2 / 16;  // 28
+    const uint4* sv = reinterpret_cast<const uint4*>(obuf);
+    for (int i = tid; i < 3 * kBandRows * kVecPerRow; i += kThreads) {
+      const int v = i % kVecPerRow;
+      const int y = (i / kVecPerRow) % kBandRows;
+      const int c = i / (kVecPerRow * kBandRows);
+      uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * 3 + c) * kCrop + y0 + y) * kCrop);
+      dst[v] = sv[i];
+    }
+  }
+}
+
+static size_t resample_smem_bytes(int max_taps, int layout) {
+  size_t b = static_cast<size_t>(kCrop) * (2 + max_taps) * 4 + static_cast<size_t>(kBandRows) * (2 + max_taps) * 4 +
+             768 * 2;
+  b = (b + 15) & ~static_cast<size_t>(15);
+  b += static_cast<size_t>(kChunkRows) * kRowElems;
+  b = (b + 15) & ~static_cast<size_t>(15);
+  b += layout == IRP_LAYOUT_NHWC4P ? static_cast<size_t>(kBandRows) * kPad * 4 * 2
+                                   : static_cast<size_t>(3) * kBandRows * kCrop * 2;
+  return b;
+}
+
+}  // namespace irp
+
+using namespace irp;
+
+extern "C" {
+
+size_t irp_preprocess_workspace_bytes(int n_images, int max_taps) {
+  if (n_images <= 0 || max_taps <= 0) return 0;
+  return static_cast<size_t>(n_images) * 2 * plan_ints_per_axis(max_taps) * sizeof(int32_t) + 16;
+}
+
+int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
+                   int max_taps, void* d_workspace, size_t workspace_bytes, void* d_out, int out_layout,
+                   void* stream) {
+  IRP_REQUIRE(d_pixels && d_offsets && d_hw && d_workspace && d_out, "preprocess: null argument");
+  IRP_REQUIRE(n_images > 0, "preprocess: n_images %d", n_images);
+  IRP_REQUIRE(max_taps >= 3 && max_taps <= 513, "preprocess: max_taps %d out of range", max_taps);
+  IRP_REQUIRE(out_layout == IRP_LAYOUT_NCHW || out_layout == IRP_LAYOUT_NHWC4P, "preprocess: bad layout %d",
+              out_layout);
+  IRP_REQUIRE(workspace_bytes >= irp_preprocess_workspace_bytes(n_images, max_taps),
+              "preprocess: workspace %zu < %zu bytes", workspace_bytes,
+              irp_preprocess_workspace_bytes(n_images, max_taps));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // status word lives in the last 16 bytes of the workspace
+  int32_t* plan = static_cast<int32_t*>(d_workspace);
+  int32_t* status =
+      reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_workspace) +
+                                 static_cast<size_t>(n_images) * 2 * plan_ints_per_axis(max_taps) * sizeof(int32_t));
+  IRP_CUDA_OK(cudaMemsetAsync(status, 0, 16, st));
+  resample_plan_kernel<<<n_images, 2 * kCrop, 0, st>>>(d_hw, n_images, max_taps, plan, status);
+  IRP_CUDA_OK(cudaGetLastError());
+  const size_t smem = resample_smem_bytes(max_taps, out_layout);
+  IRP_REQUIRE(smem <= 227 * 1024, "preprocess: max_taps %d needs %zu bytes of shared memory", max_taps, smem);
+  dim3 grid(kCrop / kBandRows, n_images);
+  if (out_layout == IRP_LAYOUT_NHWC4P) {
+    auto k = resample_kernel<IRP_LAYOUT_NHWC4P>;
+    if (smem > 48 * 1024) IRP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, static_cast<__nv_bfloat16*>(d_out));
+  } else {
+    auto k = resample_kernel<IRP_LAYOUT_NCHW>;
+    if (smem > 48 * 1024) IRP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, static_cast<__nv_bfloat16*>(d_out));
+  }
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+/* Host-side view of the resize/crop geometry (used by the Python mirror to size max_taps and by tests). */
+int irp_preprocess_geometry(int h, int w, int* out_h, int* out_w, int* top, int* left, int* taps) {
+  IRP_REQUIRE(h > 0 && w > 0, "geometry: bad size %dx%d", h, w);
+  const Geometry g = compute_geometry(h, w);
+  if (out_h) *out_h = g.out_h;
+  if (out_w) *out_w = g.out_w;
+  if (top) *top = g.top;
+  if (left) *left = g.left;
+  if (taps) {
+    const double sx = static_cast<double>(w) / g.out_w, sy = static_cast<double>(h) / g.out_h;
+    double s = sx > sy ? sx : sy;
+    if (s < 1.0) s = 1.0;
+    int c = static_cast<int>(s);
+    if (static_cast<double>(c) < s) ++c;
+    *taps = 2 * c + 1;
+  }
+  return IRP_OK;
+}
+
+}  // extern "C"

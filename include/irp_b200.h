@@ -1,0 +1,156 @@
+/*
+ * irp_b200.h -- C ABI of libirp_b200.so: the B200 (sm_100a) implementation of the embedding-based
+ * outlier-detection stage of Eaglewing89/image-recognition-pipeline (functions/data_curation.py:654-728).
+ *
+ * The reference has no FFI of its own: its boundary is four Python functions.  The host-side mirror
+ * (image-recognition-pipeline_b200/functions/data_curation.py) keeps those signatures and calls the entry
+ * points below through ctypes, registered as torch custom ops (namespace irp_b200).  INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns an irp_status (0 = ok) and never throws; irp_last_error() gives the message of the
+ *     most recent failure on the calling thread;
+ *   - pointers named d_* are DEVICE pointers owned by the caller, h_* are host pointers; nothing returned
+ *     aliases library-owned device memory except through the opaque handles;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is enqueued on it and the
+ *     calls do not synchronise unless stated;
+ *   - one handle must not be used from two threads at once (the reference is single-threaded,
+ *     functions/data_curation.py:661-684).
+ */
+#ifndef IRP_B200_H_
+#define IRP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum irp_status {
+  IRP_OK = 0,
+  IRP_ERR_INVALID = 1, /* bad argument / unsupported shape */
+  IRP_ERR_CUDA = 2,    /* a CUDA runtime or driver call failed */
+  IRP_ERR_NOMEM = 3,
+  IRP_ERR_DEVICE = 4 /* not an sm_100 device */
+} irp_status;
+
+#define IRP_B200_ABI_VERSION 1
+
+/* ABI version of the loaded library (IRP_B200_ABI_VERSION at build time). */
+int irp_abi_version(void);
+/* Message of the last failure on this thread ("" if none). The pointer stays valid until the next failure. */
+const char* irp_last_error(void);
+/* Checks that `device` is a compute-capability 10.x GPU and resolves the driver entry points. */
+int irp_init(int device);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * A1  preprocessing  --  replaces `transform(img)` at functions/data_curation.py:675, i.e.
+ * ResNet50_Weights.DEFAULT.transforms() (torchvision/transforms/_presets.py ImageClassification.forward):
+ * resize shorter side -> 232 with Pillow's antialiased bilinear filter (8-bit fixed point, horizontal then
+ * vertical pass, each rounded to uint8), center crop 224, /255, (x-mean)/std.  Bit-exact with Pillow before the
+ * final bf16 rounding.
+ *
+ * Input: a ragged batch of decoded RGB images, HWC uint8, packed back to back in d_pixels; image i starts at
+ * byte d_offsets[i] and has d_hw[2*i] rows and d_hw[2*i+1] columns.
+ * Output layout:
+ *   IRP_LAYOUT_NCHW    bf16 [n,3,224,224]            (what the reference transform returns, as bf16)
+ *   IRP_LAYOUT_NHWC4P  bf16 [n,230,230,4]            (3-pixel zero border, 4th channel zero: the layout the
+ *                                                     stem convolution's TMA view reads; border and pad
+ *                                                     channel are (re)written by this call)
+ * max_taps bounds the per-output filter taps: 2*ceil(max(1, max_i short_side_i/232))+1 for the batch.
+ * ---------------------------------------------------------------------------------------------------------- */
+enum { IRP_LAYOUT_NCHW = 0, IRP_LAYOUT_NHWC4P = 1 };
+enum { IRP_CROP = 224, IRP_RESIZE = 232, IRP_PAD_HW = 230 };
+
+/* Host-only helper: resized size, crop offsets and the tap bound (2*ceil(max(scale,1))+1) for one h x w image. */
+int irp_preprocess_geometry(int h, int w, int* out_h, int* out_w, int* top, int* left, int* taps);
+size_t irp_preprocess_workspace_bytes(int n_images, int max_taps);
+int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
+                   int max_taps, void* d_workspace, size_t workspace_bytes, void* d_out, int out_layout,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * A0/A2  ResNet-50 trunk  --  replaces initialize_model (functions/data_curation.py:654-659) and the per-image
+ * `model(img_tensor)` at :677 (torchvision/models/resnet.py:108-160,266-282 minus fc).  Eval-mode BatchNorm is
+ * folded into bf16 weights + fp32 bias; ReLU / residual add run in the conv epilogues.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct irp_resnet50 irp_resnet50;
+
+enum { IRP_RESNET50_NUM_CONVS = 53, IRP_EMBED_DIM = 2048 };
+
+/* Creates the trunk for up to max_batch images per call (activation arena + tensor maps). */
+int irp_resnet50_create(irp_resnet50** out, int max_batch);
+void irp_resnet50_destroy(irp_resnet50* net);
+/* Shape of conv `index` in execution order (conv1, then per block conv1,conv2,conv3[,downsample]). */
+int irp_resnet50_conv_shape(int index, int* cout, int* cin, int* kh, int* kw, int* stride);
+/* Loads conv `index`: fp32 OIHW weight plus its BatchNorm (gamma, beta, running_mean, running_var, eps), all
+ * device pointers; folds and re-lays them out on the device. */
+int irp_resnet50_load_conv(irp_resnet50* net, int index, const float* d_weight_oihw, const float* d_gamma,
+                           const float* d_beta, const float* d_mean, const float* d_var, float eps, void* stream);
+/* d_x: IRP_LAYOUT_NHWC4P bf16 batch; d_embed: fp32 [batch,2048] pooled embeddings (the `.squeeze()` of :677). */
+int irp_resnet50_embed(irp_resnet50* net, const void* d_x_nhwc4p, int batch, float* d_embed, void* stream);
+/* Same as irp_resnet50_embed, and additionally copies the NHWC bf16 output of conv `capture_index` (after its
+ * fused epilogue) into d_capture_bf16 (parity hook for the per-layer tests). */
+int irp_resnet50_embed_capture(irp_resnet50* net, const void* d_x_nhwc4p, int batch, float* d_embed,
+                               int capture_index, void* d_capture_bf16, size_t capacity_elems, void* stream);
+
+/* One fused convolution (the building block of the trunk), exposed for parity tests:
+ * x NHWC bf16 [B,H,W,Cin], w bf16 [Cout,kh,kw,Cin], bias fp32 [Cout], residual NHWC bf16 or NULL.
+ * Supported: (kh,kw,stride,pad) in {(1,1,1,0),(1,1,2,0),(3,3,1,1),(3,3,2,1)}, Cin % 64 == 0, Cout % 64 == 0. */
+int irp_conv2d_nhwc(const void* d_x, const void* d_w, const float* d_bias, const void* d_residual, void* d_out,
+                    int B, int H, int W, int Cin, int Cout, int ksize, int stride, int relu, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * A3  PCA  --  replaces PCA(n_components).fit_transform at functions/data_curation.py:700-701 with the exact
+ * covariance route (sklearn/decomposition/_pca.py:587-640 covariance_eigh, _base.py:151-159 transform,
+ * utils/extmath.py:973-981 sign convention).
+ *
+ *   irp_cov_accumulate : adds this shard's  n, sum(x - s), sum (x-s)(x-s)^T  into fp64 accumulators
+ *                        (split-bf16 tensor-core GEMM, fp32 per-chunk accumulate, fp64 combine).  Multi-GPU:
+ *                        all-reduce the three accumulators (that is the stage's only collective), then
+ *   irp_pca_fit        : mean, covariance, fp64 symmetric eigensolve (Householder tridiagonalisation, bisection,
+ *                        inverse iteration), top-k components with sklearn's sign convention;
+ *   irp_pca_transform  : Z = (X - mean) V^T.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t irp_cov_workspace_bytes(int64_t n_rows, int dim);
+int irp_cov_accumulate(const float* d_x, int64_t n_rows, int dim, const float* d_shift, double* d_count,
+                       double* d_sum, double* d_scatter, void* d_workspace, size_t workspace_bytes, void* stream);
+
+size_t irp_pca_fit_workspace_bytes(int dim, int k);
+/* Outputs (device): mean fp64[dim], components fp64[k,dim] (row-major), eigenvalues fp64[dim] descending
+ * (all of them; explained_variance_ = first k, total variance = their sum). Synchronises `stream`. */
+int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scatter, const float* d_shift,
+                int dim, int k, double* d_mean, double* d_components, double* d_eigenvalues, void* d_workspace,
+                size_t workspace_bytes, void* stream);
+int irp_pca_transform(const float* d_x, int64_t n_rows, int dim, const double* d_mean, const double* d_components,
+                      int k, float* d_z, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * A4  outlier scoring  --  replaces detect_outliers (functions/data_curation.py:709-728):
+ * LocalOutlierFactor(n_neighbors, contamination).fit_predict(...) == -1, per class and globally
+ * (sklearn/neighbors/_lof.py:286-332,498-523).  Brute-force fp64 Euclidean k-NN restricted to rows of the same
+ * group, reachability / LRD / LOF, np.percentile threshold, strict `<` flag.
+ *
+ *   d_group[i] in [0, n_groups): rows are scored only against rows of their own group (per-class pass);
+ *   pass d_group = NULL and n_groups = 1 for the global pass.
+ *   d_scores: negative_outlier_factor_ per row (fp64); d_offsets: threshold per group (fp64 [n_groups]);
+ *   d_flags: 1 where score < threshold of the row's group.
+ *
+ * irp_centroid_zscore is the north_star's distance-to-centroid scorer (no reference counterpart): per group
+ * centroid, Euclidean distance, z-score of the distance, flag = distance above the (1-contamination) percentile.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t irp_lof_workspace_bytes(int64_t n_rows, int dim, int k);
+int irp_lof(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, int n_groups, int k,
+            double contamination, double* d_scores, double* d_offsets, uint8_t* d_flags, void* d_workspace,
+            size_t workspace_bytes, void* stream);
+
+size_t irp_centroid_workspace_bytes(int64_t n_rows, int dim, int n_groups);
+int irp_centroid_zscore(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, int n_groups,
+                        double contamination, double* d_dist, double* d_zscore, double* d_thresholds,
+                        uint8_t* d_flags, void* d_workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRP_B200_H_ */
