@@ -1,0 +1,652 @@
+// A4 outlier scoring: Local Outlier Factor (per group and global) and the distance-to-centroid z-score scorer.
+//
+// Replaces detect_outliers (functions/data_curation.py:709-728).  LOF arithmetic follows scikit-learn
+// (sklearn/neighbors/_lof.py:286-323 fit, :498-523 local reachability density): k = max(1, min(n_neighbors, n-1)),
+// neighbours exclude the sample itself, reach = max(d, k-distance(neighbour)), lrd = 1/(mean reach + 1e-10),
+// score = -mean(lrd[nbr]/lrd[i]), offset = np.percentile(score, 100*contamination) (linear interpolation),
+// outlier iff score < offset.  Everything is evaluated in fp64; oracle/lof_ref.py is the numpy restatement.
+//
+// Pipeline: stable counting sort of the rows by group -> squared norms -> tiled brute-force k-NN (64x64 distance
+// tiles in registers, per-query sorted candidate lists in shared memory) -> lrd -> lof -> per-group radix select
+// of the two order statistics around the percentile -> flags.
+#include <cfloat>
+#include <cstring>
+
+#include "common.h"
+
+namespace irp {
+
+constexpr int kSortThreads = 1024;
+constexpr int kKnnThreads = 256;
+constexpr int kKnnTile = 64;   // queries per CTA, candidates per step
+constexpr int kKnnDChunk = 32; // feature chunk staged in shared memory
+constexpr int kMaxK = 128;
+
+// ------------------------------------------------------------------------------------------------------------
+// stable counting sort by group: thread t owns the contiguous row range [t*L, (t+1)*L)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads) group_count_kernel(const int32_t* __restrict__ group, long long n,
+                                                                   int n_groups, int32_t* __restrict__ counts) {
+  // counts: [n_groups][kSortThreads]
+  const long long L = (n + kSortThreads - 1) / kSortThreads;
+  const int t = threadIdx.x;
+  for (int g = 0; g < n_groups; ++g) counts[static_cast<size_t>(g) * kSortThreads + t] = 0;
+  const long long lo = t * L, hi = min(n, lo + L);
+  for (long long i = lo; i < hi; ++i) {
+    const int g = group ? group[i] : 0;
+    if (g >= 0 && g < n_groups) counts[static_cast<size_t>(g) * kSortThreads + t] += 1;
+  }
+}
+
+// exclusive scan over counts in (group, thread) order; gstart[g] = first sorted position of group g
+__global__ void __launch_bounds__(kSortThreads) group_scan_kernel(int32_t* __restrict__ counts, int n_groups,
+                                                                  int32_t* __restrict__ gstart) {
+  __shared__ int32_t warp_tot[kSortThreads / 32];
+  __shared__ int32_t carry;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) carry = 0;
+  __syncthreads();
+  for (int g = 0; g < n_groups; ++g) {
+    const int32_t v = counts[static_cast<size_t>(g) * kSortThreads + t];
+    int32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    int32_t base = carry;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    counts[static_cast<size_t>(g) * kSortThreads + t] = base + x - v;  // exclusive
+    __syncthreads();
+    if (t == kSortThreads - 1) {
+      gstart[g] = carry;
+      carry = base + x;
+    }
+    __syncthreads();
+  }
+  if (t == 0) gstart[n_groups] = carry;
+}
+
+__global__ void __launch_bounds__(kSortThreads) group_scatter_kernel(const int32_t* __restrict__ group, long long n,
+                                                                     int n_groups, int32_t* __restrict__ counts,
+                                                                     int32_t* __restrict__ order) {
+  const long long L = (n + kSortThreads - 1) / kSortThreads;
+  const int t = threadIdx.x;
+  const long long lo = t * L, hi = min(n, lo + L);
+  for (long long i = lo; i < hi; ++i) {
+    const int g = group ? group[i] : 0;
+    if (g >= 0 && g < n_groups) {
+      const int32_t pos = counts[static_cast<size_t>(g) * kSortThreads + t]++;
+      order[pos] = static_cast<int32_t>(i);
+    }
+  }
+}
+
+__global__ void iota_kernel(int32_t* order, long long n, int32_t* gstart) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) order[i] = static_cast<int32_t>(i);
+  if (i == 0) {
+    gstart[0] = 0;
+    gstart[1] = static_cast<int32_t>(n);
+  }
+}
+
+// squared norms in sorted order (fp64)
+__global__ void sqnorm_kernel(const float* __restrict__ z, const int32_t* __restrict__ order, long long n, int dim,
+                              double* __restrict__ sq) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float* r = z + static_cast<size_t>(order[i]) * dim;
+  double s = 0.0;
+  for (int j = 0; j < dim; ++j) {
+    const double v = r[j];
+    s += v * v;
+  }
+  sq[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// brute-force k-NN inside each group
+// ------------------------------------------------------------------------------------------------------------
+// warp-cooperative insertion of (dc, jc) into the ascending list (ld, li) of length K held in shared memory
+__device__ __forceinline__ void list_insert(double* ld, int32_t* li, int K, double dc, int32_t jc, int lane) {
+  int pos = 0;
+  for (int s0 = 0; s0 < K; s0 += 32) {
+    const int s = s0 + lane;
+    const bool le = (s < K) && (ld[s] <= dc);
+    pos += __popc(__ballot_sync(0xffffffffu, le));
+  }
+  // shift [pos, K-2] -> [pos+1, K-1]
+  double vd[kMaxK / 32];
+  int32_t vi[kMaxK / 32];
+#pragma unroll
+  for (int m = 0; m < kMaxK / 32; ++m) {
+    const int s = m * 32 + lane;
+    if (s >= pos && s < K - 1) {
+      vd[m] = ld[s];
+      vi[m] = li[s];
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int m = 0; m < kMaxK / 32; ++m) {
+    const int s = m * 32 + lane;
+    if (s >= pos && s < K - 1) {
+      ld[s + 1] = vd[m];
+      li[s + 1] = vi[m];
+    }
+  }
+  if (lane == 0) {
+    ld[pos] = dc;
+    li[pos] = jc;
+  }
+  __syncwarp();
+}
+
+// dynamic smem: Qs[kKnnDChunk][64], Cs[kKnnDChunk][64], Dt[64][65], ld[64][K], li[64][K]
+__global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restrict__ z,
+                                                          const int32_t* __restrict__ order,
+                                                          const int32_t* __restrict__ gstart, int n_groups, int dim,
+                                                          int k, const double* __restrict__ sq,
+                                                          double* __restrict__ knn_d, int32_t* __restrict__ knn_i) {
+  extern __shared__ double shk[];
+  double* Qs = shk;
+  double* Cs = Qs + kKnnDChunk * kKnnTile;
+  double* Dt = Cs + kKnnDChunk * kKnnTile;
+  double* ld = Dt + kKnnTile * (kKnnTile + 1);
+  int32_t* li = reinterpret_cast<int32_t*>(ld + kKnnTile * k);
+
+  // locate this CTA's (group, query tile)
+  int tile = blockIdx.x;
+  int g = 0, g0 = 0, g1 = 0;
+  for (; g < n_groups; ++g) {
+    g0 = gstart[g];
+    g1 = gstart[g + 1];
+    const int tiles = (g1 - g0 + kKnnTile - 1) / kKnnTile;
+    if (tile < tiles) break;
+    tile -= tiles;
+  }
+  if (g >= n_groups) return;
+  const int ng = g1 - g0;
+  const int q0 = g0 + tile * kKnnTile;
+  const int K = max(1, min(k, ng - 1));  // _lof.py:293
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kKnnTile * k; i += kKnnThreads) {
+    ld[i] = INFINITY;
+    li[i] = -1;
+  }
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int c0 = g0; c0 < g1; c0 += kKnnTile) {
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int j0 = 0; j0 < dim; j0 += kKnnDChunk) {
+      __syncthreads();
+      for (int i = tid; i < kKnnTile * kKnnDChunk; i += kKnnThreads) {
+        const int r = i / kKnnDChunk, jj = i % kKnnDChunk;
+        const int j = j0 + jj;
+        double qv = 0.0, cv = 0.0;
+        if (j < dim) {
+          if (q0 + r < g1) qv = z[static_cast<size_t>(order[q0 + r]) * dim + j];
+          if (c0 + r < g1) cv = z[static_cast<size_t>(order[c0 + r]) * dim + j];
+        }
+        Qs[jj * kKnnTile + r] = qv;
+        Cs[jj * kKnnTile + r] = cv;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int jj = 0; jj < kKnnDChunk; ++jj) {
+        const double2 qa = *reinterpret_cast<const double2*>(&Qs[jj * kKnnTile + ty * 4]);
+        const double2 qb = *reinterpret_cast<const double2*>(&Qs[jj * kKnnTile + ty * 4 + 2]);
+        const double2 ca = *reinterpret_cast<const double2*>(&Cs[jj * kKnnTile + tx * 4]);
+        const double2 cb = *reinterpret_cast<const double2*>(&Cs[jj * kKnnTile + tx * 4 + 2]);
+        const double q[4] = {qa.x, qa.y, qb.x, qb.y};
+        const double c[4] = {ca.x, ca.y, cb.x, cb.y};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fma(q[a], c[b], acc[a][b]);
+      }
+    }
+    // squared distances -> Dt
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int qi = q0 + ty * 4 + a;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int ci = c0 + tx * 4 + b;
+        double d2 = INFINITY;
+        if (qi < g1 && ci < g1 && ci != qi) d2 = fmax(sq[qi] + sq[ci] - 2.0 * acc[a][b], 0.0);
+        Dt[(ty * 4 + a) * (kKnnTile + 1) + tx * 4 + b] = d2;
+      }
+    }
+    __syncthreads();
+    // selection: warp w owns queries w*8 .. w*8+7
+    for (int qq = 0; qq < 8; ++qq) {
+      const int ql = warp * 8 + qq;
+      if (q0 + ql >= g1) break;
+      double* qld = ld + ql * k;
+      int32_t* qli = li + ql * k;
+      double tau = qld[K - 1];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const double dc = Dt[ql * (kKnnTile + 1) + half * 32 + lane];
+        unsigned pending = __ballot_sync(0xffffffffu, dc < tau);
+        while (pending) {
+          const int src = __ffs(pending) - 1;
+          pending &= pending - 1;
+          const double dv = __shfl_sync(0xffffffffu, dc, src);
+          if (dv < tau) {
+            list_insert(qld, qli, K, dv, c0 + half * 32 + src, lane);
+            tau = qld[K - 1];
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // write out: distances (sqrt) + neighbour positions (sorted-order indices)
+  for (int i = tid; i < kKnnTile * k; i += kKnnThreads) {
+    const int ql = i / k, s = i % k;
+    if (q0 + ql < g1) {
+      knn_d[static_cast<size_t>(q0 + ql) * k + s] = s < K ? sqrt(ld[ql * k + s]) : INFINITY;
+      knn_i[static_cast<size_t>(q0 + ql) * k + s] = s < K ? li[ql * k + s] : -1;
+    }
+  }
+}
+
+// per-row group lookup in sorted order (binary search over gstart) -> K for that row
+__device__ __forceinline__ int row_group(const int32_t* gstart, int n_groups, int i) {
+  int lo = 0, hi = n_groups;  // gstart[lo] <= i < gstart[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (gstart[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void lrd_kernel(const double* __restrict__ knn_d, const int32_t* __restrict__ knn_i,
+                           const int32_t* __restrict__ gstart, int n_groups, long long n, int k,
+                           double* __restrict__ lrd) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int g = row_group(gstart, n_groups, static_cast<int>(i));
+  const int ng = gstart[g + 1] - gstart[g];
+  if (ng < 2) {
+    lrd[i] = 1.0;
+    return;
+  }
+  const int K = max(1, min(k, ng - 1));
+  double s = 0.0;
+  for (int t = 0; t < K; ++t) {
+    const int nb = knn_i[i * k + t];
+    const double dk = knn_d[static_cast<size_t>(nb) * k + (K - 1)];
+    s += fmax(knn_d[i * k + t], dk);
+  }
+  lrd[i] = 1.0 / (s / K + 1e-10);
+}
+
+__global__ void lof_score_kernel(const double* __restrict__ lrd, const int32_t* __restrict__ knn_i,
+                                 const int32_t* __restrict__ gstart, int n_groups, const int32_t* __restrict__ order,
+                                 long long n, int k, double* __restrict__ score_sorted,
+                                 double* __restrict__ score_out) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int g = row_group(gstart, n_groups, static_cast<int>(i));
+  const int ng = gstart[g + 1] - gstart[g];
+  double sc = -1.0;
+  if (ng >= 2) {
+    const int K = max(1, min(k, ng - 1));
+    const double li = lrd[i];
+    double s = 0.0;
+    for (int t = 0; t < K; ++t) s += lrd[knn_i[i * k + t]] / li;
+    sc = -(s / K);
+  }
+  score_sorted[i] = sc;
+  score_out[order[i]] = sc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// np.percentile (method="linear") per group via MSB-first radix select on order-preserving 64-bit keys
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f64_key(double v) {
+  const unsigned long long u = static_cast<unsigned long long>(__double_as_longlong(v));
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+  const unsigned long long u = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+  return __longlong_as_double(static_cast<long long>(u));
+}
+
+// rank-th smallest (0-based) of v[0..n); whole block participates
+__device__ double block_select(const double* __restrict__ v, int n, int rank, int* hist) {
+  unsigned long long prefix = 0, mask = 0;
+  int r = rank;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long key = f64_key(v[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
+    }
+    __syncthreads();
+    // every thread walks the 256 bins (cheap, keeps control flow uniform)
+    int cum = 0, bin = 0;
+    for (; bin < 256; ++bin) {
+      const int h = hist[bin];
+      if (cum + h > r) break;
+      cum += h;
+    }
+    r -= cum;
+    prefix |= static_cast<unsigned long long>(bin) << shift;
+    mask |= 0xFFull << shift;
+    __syncthreads();
+  }
+  return key_f64(prefix);
+}
+
+// q in [0,1]; returns numpy's linear-interpolated quantile of v[0..n)
+__device__ double block_percentile(const double* __restrict__ v, int n, double q, int* hist, double* red) {
+  // numpy/lib/_function_base_impl.py _compute_virtual_index(n, q, alpha=1, beta=1), _get_gamma, _lerp
+  const double vi = (static_cast<double>(n) * q + (1.0 + q * (1.0 - 1.0 - 1.0))) - 1.0;
+  double prev = floor(vi);
+  double gamma = vi - prev;
+  int lo = static_cast<int>(prev);
+  if (lo < 0) lo = 0;
+  if (lo > n - 1) lo = n - 1;
+  int hi = lo + 1;
+  if (hi > n - 1) hi = n - 1;
+  const double a = block_select(v, n, lo, hi == lo ? hist : hist);
+  double b = a;
+  if (hi != lo) {
+    // b = next order statistic: a again if it has duplicates beyond rank lo, else the smallest value > a
+    int cnt_le = 0;
+    double mn = INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double x = v[i];
+      if (x <= a) ++cnt_le;
+      else mn = fmin(mn, x);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt_le += __shfl_xor_sync(0xffffffffu, cnt_le, o);
+      mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    __shared__ int s_cnt[32];
+    __shared__ double s_mn[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) {
+      s_cnt[warp] = cnt_le;
+      s_mn[warp] = mn;
+    }
+    __syncthreads();
+    int tc = 0;
+    double tm = INFINITY;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) {
+      tc += s_cnt[w];
+      tm = fmin(tm, s_mn[w]);
+    }
+    b = (tc >= lo + 2) ? a : tm;
+  }
+  (void)red;
+  const double diff = b - a;
+  double res = a + diff * gamma;
+  if (gamma >= 0.5) res = b - diff * (1.0 - gamma);
+  return res;
+}
+
+__global__ void __launch_bounds__(1024) group_percentile_kernel(const double* __restrict__ values_sorted,
+                                                                const int32_t* __restrict__ gstart, double q,
+                                                                double* __restrict__ out) {
+  __shared__ int hist[256];
+  __shared__ double red[32];
+  const int g = blockIdx.x;
+  const int g0 = gstart[g], n = gstart[g + 1] - g0;
+  if (n <= 0) {
+    if (threadIdx.x == 0) out[g] = nan("");
+    return;
+  }
+  const double r = block_percentile(values_sorted + g0, n, q, hist, red);
+  if (threadIdx.x == 0) out[g] = r;
+}
+
+__global__ void flag_kernel(const double* __restrict__ value_sorted, const int32_t* __restrict__ gstart, int n_groups,
+                            const int32_t* __restrict__ order, long long n, const double* __restrict__ thr,
+                            int greater, uint8_t* __restrict__ flags) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int g = row_group(gstart, n_groups, static_cast<int>(i));
+  const double v = value_sorted[i], t = thr[g];
+  flags[order[i]] = greater ? (v > t) : (v < t);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// centroid / z-score scorer
+// ------------------------------------------------------------------------------------------------------------
+// one CTA per (group, feature chunk): centroid[g][j] = mean over the group's rows (fixed summation order)
+__global__ void __launch_bounds__(256) centroid_kernel(const float* __restrict__ z, const int32_t* __restrict__ order,
+                                                       const int32_t* __restrict__ gstart, int dim,
+                                                       double* __restrict__ centroid) {
+  const int g = blockIdx.x;
+  const int g0 = gstart[g], g1 = gstart[g + 1];
+  __shared__ double part[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j0 = blockIdx.y * 32; j0 < dim; j0 += gridDim.y * 32) {
+    const int j = j0 + lane;
+    double s = 0.0;
+    if (j < dim)
+      for (int i = g0 + warp; i < g1; i += 8) s += static_cast<double>(z[static_cast<size_t>(order[i]) * dim + j]);
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && j < dim) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += part[w][lane];
+      centroid[static_cast<size_t>(g) * dim + j] = g1 > g0 ? t / (g1 - g0) : 0.0;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void centroid_dist_kernel(const float* __restrict__ z, const int32_t* __restrict__ order,
+                                     const int32_t* __restrict__ gstart, int n_groups, long long n, int dim,
+                                     const double* __restrict__ centroid, double* __restrict__ dist_sorted,
+                                     double* __restrict__ dist_out) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int g = row_group(gstart, n_groups, static_cast<int>(i));
+  const float* r = z + static_cast<size_t>(order[i]) * dim;
+  const double* c = centroid + static_cast<size_t>(g) * dim;
+  double s = 0.0;
+  for (int j = 0; j < dim; ++j) {
+    const double d = static_cast<double>(r[j]) - c[j];
+    s += d * d;
+  }
+  s = sqrt(s);
+  dist_sorted[i] = s;
+  dist_out[order[i]] = s;
+}
+
+// per group: mean / population std of the distances (two-pass, fixed order), then z-scores
+__global__ void __launch_bounds__(1024) group_zscore_kernel(const double* __restrict__ dist_sorted,
+                                                            const int32_t* __restrict__ gstart,
+                                                            const int32_t* __restrict__ order,
+                                                            double* __restrict__ zscore_out) {
+  __shared__ double red[32];
+  __shared__ double s_mean, s_std;
+  const int g = blockIdx.x;
+  const int g0 = gstart[g], n = gstart[g + 1] - g0;
+  if (n <= 0) return;
+  const double* v = dist_sorted + g0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += red[w];
+    s_mean = t / n;
+  }
+  __syncthreads();
+  const double mean = s_mean;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = v[i] - mean;
+    q += d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = q;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += red[w];
+    s_std = sqrt(t / n);
+  }
+  __syncthreads();
+  const double sd = s_std;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    zscore_out[order[g0 + i]] = sd > 0.0 ? (v[i] - mean) / sd : 0.0;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct SortedRows {
+  int32_t* order;
+  int32_t* gstart;
+  int32_t* counts;
+};
+
+static size_t sort_bytes(long long n, int n_groups) {
+  return align_up(static_cast<size_t>(n) * 4, 256) + align_up(static_cast<size_t>(n_groups + 1) * 4, 256) +
+         align_up(static_cast<size_t>(n_groups) * kSortThreads * 4, 256);
+}
+
+static int sort_rows(const int32_t* d_group, long long n, int n_groups, uint8_t*& ws, SortedRows* out,
+                     cudaStream_t st) {
+  out->order = reinterpret_cast<int32_t*>(ws);
+  ws += align_up(static_cast<size_t>(n) * 4, 256);
+  out->gstart = reinterpret_cast<int32_t*>(ws);
+  ws += align_up(static_cast<size_t>(n_groups + 1) * 4, 256);
+  out->counts = reinterpret_cast<int32_t*>(ws);
+  ws += align_up(static_cast<size_t>(n_groups) * kSortThreads * 4, 256);
+  if (d_group == nullptr || n_groups == 1) {
+    iota_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(out->order, n, out->gstart);
+  } else {
+    group_count_kernel<<<1, kSortThreads, 0, st>>>(d_group, n, n_groups, out->counts);
+    group_scan_kernel<<<1, kSortThreads, 0, st>>>(out->counts, n_groups, out->gstart);
+    group_scatter_kernel<<<1, kSortThreads, 0, st>>>(d_group, n, n_groups, out->counts, out->order);
+  }
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+}  // namespace irp
+
+using namespace irp;
+
+extern "C" {
+
+size_t irp_lof_workspace_bytes(int64_t n_rows, int dim, int k) {
+  if (n_rows <= 0 || dim <= 0 || k <= 0) return 0;
+  const size_t n = static_cast<size_t>(n_rows);
+  size_t b = sort_bytes(n_rows, 1024);
+  b += align_up(n * 8, 256);          // sq
+  b += align_up(n * k * 8, 256);      // knn_d
+  b += align_up(n * k * 4, 256);      // knn_i
+  b += align_up(n * 8, 256);          // lrd
+  b += align_up(n * 8, 256);          // score_sorted
+  return b + 1024;
+}
+
+int irp_lof(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, int n_groups, int k,
+            double contamination, double* d_scores, double* d_offsets, uint8_t* d_flags, void* d_workspace,
+            size_t workspace_bytes, void* stream) {
+  IRP_REQUIRE(d_z && d_scores && d_offsets && d_flags && d_workspace, "lof: null argument");
+  IRP_REQUIRE(n_rows >= 2 && n_rows < (1ll << 31) && dim >= 1, "lof: n_rows %lld dim %d",
+              static_cast<long long>(n_rows), dim);
+  IRP_REQUIRE(k >= 1 && k <= kMaxK, "lof: n_neighbors %d not in [1,%d]", k, kMaxK);
+  IRP_REQUIRE(n_groups >= 1 && n_groups <= 1024, "lof: n_groups %d not in [1,1024]", n_groups);
+  IRP_REQUIRE(contamination > 0.0 && contamination <= 0.5, "lof: contamination %g not in (0,0.5]", contamination);
+  IRP_REQUIRE(workspace_bytes >= irp_lof_workspace_bytes(n_rows, dim, k), "lof: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(n_rows);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(d_workspace), 256));
+  SortedRows sr;
+  IRP_TRY(sort_rows(d_group, n_rows, n_groups, ws, &sr, st));
+  double* sq = reinterpret_cast<double*>(ws);
+  ws += align_up(n * 8, 256);
+  double* knn_d = reinterpret_cast<double*>(ws);
+  ws += align_up(n * k * 8, 256);
+  int32_t* knn_i = reinterpret_cast<int32_t*>(ws);
+  ws += align_up(n * k * 4, 256);
+  double* lrd = reinterpret_cast<double*>(ws);
+  ws += align_up(n * 8, 256);
+  double* score_sorted = reinterpret_cast<double*>(ws);
+
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  sqnorm_kernel<<<blocks, 256, 0, st>>>(d_z, sr.order, n_rows, dim, sq);
+  const size_t smem = (2 * kKnnDChunk * kKnnTile + kKnnTile * (kKnnTile + 1) + static_cast<size_t>(kKnnTile) * k) * 8 +
+                      static_cast<size_t>(kKnnTile) * k * 4;
+  static size_t cfg = 0;
+  if (smem > cfg) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cfg = smem;
+  }
+  const unsigned knn_grid = static_cast<unsigned>((n + kKnnTile - 1) / kKnnTile + n_groups);
+  knn_kernel<<<knn_grid, kKnnThreads, smem, st>>>(d_z, sr.order, sr.gstart, n_groups, dim, k, sq, knn_d, knn_i);
+  lrd_kernel<<<blocks, 256, 0, st>>>(knn_d, knn_i, sr.gstart, n_groups, n_rows, k, lrd);
+  lof_score_kernel<<<blocks, 256, 0, st>>>(lrd, knn_i, sr.gstart, n_groups, sr.order, n_rows, k, score_sorted,
+                                           d_scores);
+  // sklearn passes 100*contamination to np.percentile, which divides by 100 again
+  const double q = (100.0 * contamination) / 100.0;
+  group_percentile_kernel<<<n_groups, 1024, 0, st>>>(score_sorted, sr.gstart, q, d_offsets);
+  flag_kernel<<<blocks, 256, 0, st>>>(score_sorted, sr.gstart, n_groups, sr.order, n_rows, d_offsets, 0, d_flags);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+size_t irp_centroid_workspace_bytes(int64_t n_rows, int dim, int n_groups) {
+  if (n_rows <= 0 || dim <= 0 || n_groups <= 0) return 0;
+  const size_t n = static_cast<size_t>(n_rows);
+  return sort_bytes(n_rows, n_groups) + align_up(static_cast<size_t>(n_groups) * dim * 8, 256) +
+         align_up(n * 8, 256) + 1024;
+}
+
+int irp_centroid_zscore(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, int n_groups,
+                        double contamination, double* d_dist, double* d_zscore, double* d_thresholds,
+                        uint8_t* d_flags, void* d_workspace, size_t workspace_bytes, void* stream) {
+  IRP_REQUIRE(d_z && d_dist && d_zscore && d_thresholds && d_flags && d_workspace, "centroid: null argument");
+  IRP_REQUIRE(n_rows >= 1 && n_rows < (1ll << 31) && dim >= 1, "centroid: n_rows %lld dim %d",
+              static_cast<long long>(n_rows), dim);
+  IRP_REQUIRE(n_groups >= 1 && n_groups <= 1024, "centroid: n_groups %d not in [1,1024]", n_groups);
+  IRP_REQUIRE(contamination > 0.0 && contamination < 1.0, "centroid: contamination %g", contamination);
+  IRP_REQUIRE(workspace_bytes >= irp_centroid_workspace_bytes(n_rows, dim, n_groups), "centroid: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(n_rows);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(d_workspace), 256));
+  SortedRows sr;
+  IRP_TRY(sort_rows(d_group, n_rows, n_groups, ws, &sr, st));
+  double* centroid = reinterpret_cast<double*>(ws);
+  ws += align_up(static_cast<size_t>(n_groups) * dim * 8, 256);
+  double* dist_sorted = reinterpret_cast<double*>(ws);
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  dim3 cgrid(n_groups, (dim + 31) / 32 < 64 ? (dim + 31) / 32 : 64);
+  centroid_kernel<<<cgrid, 256, 0, st>>>(d_z, sr.order, sr.gstart, dim, centroid);
+  centroid_dist_kernel<<<blocks, 256, 0, st>>>(d_z, sr.order, sr.gstart, n_groups, n_rows, dim, centroid, dist_sorted,
+                                               d_dist);
+  group_zscore_kernel<<<n_groups, 1024, 0, st>>>(dist_sorted, sr.gstart, sr.order, d_zscore);
+  const double q = (100.0 * (1.0 - contamination)) / 100.0;
+  group_percentile_kernel<<<n_groups, 1024, 0, st>>>(dist_sorted, sr.gstart, q, d_thresholds);
+  flag_kernel<<<blocks, 256, 0, st>>>(dist_sorted, sr.gstart, n_groups, sr.order, n_rows, d_thresholds, 1, d_flags);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+}  // extern "C"

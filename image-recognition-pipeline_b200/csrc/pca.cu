@@ -1,0 +1,863 @@
+// A3 PCA: shifted scatter matrix on tensor cores (split-bf16 x3, fp32 TMEM accumulate per K chunk, fp64 combine),
+// fp64 symmetric eigensolver for the top-k pairs (Householder tridiagonalisation with the matrix resident in L2,
+// multisection Sturm bisection, inverse iteration, reflector back-transform), sklearn's sign convention, and the
+// fp64-accumulated projection.
+//
+// Replaces PCA(n_components).fit_transform at functions/data_curation.py:700-701; mirrors the exact solver
+// sklearn offers for the same class: sklearn/decomposition/_pca.py:587-640 (covariance_eigh), _base.py:151-159
+// (transform), utils/extmath.py:973-981 (svd_flip, u_based_decision=False).  oracle/pca_ref.py is the fp64 numpy
+// restatement the parity tests compare against.
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace irp {
+
+// ============================================================================================================
+// 1. split + transpose pre-pass:  y = x - shift;  y = a + b + c with a,b,c bf16 (8 mantissa bits each);
+//    writes A^T, B^T, C^T as [dim][n_pad] (K-major: samples contiguous) and accumulates column sums.
+// ============================================================================================================
+constexpr int kSplitTile = 64;
+
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ x, long long n_rows, int dim,
+                                                              const float* __restrict__ shift, long long n_pad,
+                                                              __nv_bfloat16* __restrict__ at,
+                                                              __nv_bfloat16* __restrict__ bt,
+                                                              __nv_bfloat16* __restrict__ ct,
+                                                              double* __restrict__ col_sum) {
+  __shared__ float tile[kSplitTile][kSplitTile + 1];
+  const long long r0 = static_cast<long long>(blockIdx.x) * kSplitTile;
+  const int c0 = blockIdx.y * kSplitTile;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  for (int i = ty; i < kSplitTile; i += 4) {
+    const long long r = r0 + i;
+    float v = 0.f;
+    if (r < n_rows) v = x[r * dim + c0 + tx] - shift[c0 + tx];
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  // column sums of this tile (fp32 over 64 rows, fp64 across tiles)
+  if (ty == 0) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < kSplitTile; ++i) s += tile[i][tx];
+    atomicAdd(&col_sum[c0 + tx], static_cast<double>(s));
+  }
+  // transposed write: thread tx walks samples (contiguous in the output), ty strides features
+  for (int j = ty; j < kSplitTile; j += 4) {
+    const float v = tile[tx][j];
+    const __nv_bfloat16 a = __float2bfloat16_rn(v);
+    const float ra = v - __bfloat162float(a);
+    const __nv_bfloat16 b = __float2bfloat16_rn(ra);
+    const float rb = ra - __bfloat162float(b);
+    const __nv_bfloat16 c = __float2bfloat16_rn(rb);
+    const size_t o = static_cast<size_t>(c0 + j) * n_pad + r0 + tx;
+    at[o] = a;
+    bt[o] = b;
+    ct[o] = c;
+  }
+}
+
+// ============================================================================================================
+// 2. scatter GEMM on tcgen05:  S[i,j] += sum_k (a_i a_j + a_i b_j + b_i a_j + b_i b_j + a_i c_j + c_i a_j)[k]
+//    over one K chunk per work unit; upper-triangular 128x128 tiles only; fp64 atomics into S.
+// ============================================================================================================
+constexpr int kCovBN = 128, kCovBK = 64, kCovStages = 6, kCovThreads = 192;
+constexpr int kCovABytes = 128 * kCovBK * 2, kCovBBytes = kCovBN * kCovBK * 2;
+constexpr int kCovSmem = kCovStages * (kCovABytes + kCovBBytes) + 256 + 1024;
+constexpr int kCovPasses = 6;
+
+struct alignas(64) CovParams {
+  CUtensorMap tm[3];  // A^T, B^T, C^T: [dim][n_pad] bf16
+  int tiles_1d;       // dim / 128
+  int n_tri;          // tiles_1d*(tiles_1d+1)/2
+  int k_blocks_total; // n_pad / 64
+  int k_blocks_per_chunk;
+  int n_chunks;
+  int num_units;      // n_tri * n_chunks
+  int dim;
+  double* scatter;    // [dim][dim] fp64, upper-triangular tiles accumulate here
+};
+
+__device__ __forceinline__ void tri_decode(int t, int nt, int* ti, int* tj) {
+  // row-major enumeration of the upper triangle (ti <= tj)
+  int i = 0;
+  int rem = t;
+  while (rem >= nt - i) {
+    rem -= nt - i;
+    ++i;
+  }
+  *ti = i;
+  *tj = i + rem;
+}
+
+__global__ void __launch_bounds__(kCovThreads, 1) cov_gemm_kernel(const __grid_constant__ CovParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kCovStages * kCovABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCovStages * (kCovABytes + kCovBBytes));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kCovStages;
+  uint64_t* tfull_bar = bars + 2 * kCovStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // two accumulators per buffer: [hi*hi] and [all correction products] -- the small terms must not be
+  // rounded against the large hi*hi partial sums (the tensor core truncates when it aligns addends)
+  constexpr uint32_t kTmemCols = 4 * kCovBN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.tm[i]);
+    for (int i = 0; i < kCovStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pass -> (A-side array, B-side array)
+  const int pa[kCovPasses] = {0, 0, 1, 1, 0, 2};
+  const int pb[kCovPasses] = {0, 1, 0, 1, 2, 0};
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        const int chunk = u % p.n_chunks;
+        int ti, tj;
+        tri_decode(u / p.n_chunks, p.tiles_1d, &ti, &tj);
+        const int kb0 = chunk * p.k_blocks_per_chunk;
+        const int kb1 = min(p.k_blocks_total, kb0 + p.k_blocks_per_chunk);
+        for (int pass = 0; pass < kCovPasses; ++pass) {
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], kCovABytes + kCovBBytes);
+            tma_load_2d(smem_a + stage * kCovABytes, &p.tm[pa[pass]], &full_bar[stage], kb * kCovBK, ti * 128);
+            tma_load_2d(smem_b + stage * kCovBBytes, &p.tm[pb[pass]], &full_bar[stage], kb * kCovBK, tj * 128);
+            if (++stage == kCovStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, kCovBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        const int chunk = u % p.n_chunks;
+        const int kb0 = chunk * p.k_blocks_per_chunk;
+        const int kb1 = min(p.k_blocks_total, kb0 + p.k_blocks_per_chunk);
+        const int per_pass = kb1 - kb0;
+        const int total = kCovPasses * per_pass;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_big = tmem_base + acc * 2 * kCovBN;
+        const uint32_t tmem_small = tmem_big + kCovBN;
+        for (int it = 0; it < total; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * kCovABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * kCovBBytes);
+          const bool big = it < per_pass;  // pass 0 = hi*hi
+          const uint32_t tmem_d = big ? tmem_big : tmem_small;
+          const int first = big ? 0 : per_pass;
+#pragma unroll
+          for (int k = 0; k < kCovBK / 16; ++k)
+            umma_bf16(tmem_d, umma_smem_desc<128>(a_addr + k * 32), umma_smem_desc<128>(b_addr + k * 32), idesc,
+                      (it != first || k != 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kCovStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      int ti, tj;
+      tri_decode(u / p.n_chunks, p.tiles_1d, &ti, &tj);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 2 * kCovBN + (static_cast<uint32_t>(quarter * 32) << 16);
+      double* dst = p.scatter + static_cast<size_t>(ti * 128 + row) * p.dim + tj * 128;
+#pragma unroll 1
+      for (int c = 0; c < kCovBN; c += 32) {
+        uint32_t v[32], s[32];
+        __syncwarp();
+        tmem_ld_32x32b_x32(taddr + c, v);
+        tmem_ld_32x32b_x32(taddr + kCovBN + c, s);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          atomicAdd(dst + c + i,
+                    static_cast<double>(__uint_as_float(v[i])) + static_cast<double>(__uint_as_float(s[i])));
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ============================================================================================================
+// 3. covariance assembly:  mean = shift + sum/n;  C = (S - n * delta delta^T) / (n-1), delta = sum/n; symmetric.
+// ============================================================================================================
+__global__ void assemble_cov_kernel(const double* __restrict__ count, const double* __restrict__ sum,
+                                    const double* __restrict__ scatter, const float* __restrict__ shift, int dim,
+                                    double* __restrict__ mean, double* __restrict__ cov, double* __restrict__ trace) {
+  const double n = count[0];
+  const long long total = static_cast<long long>(dim) * dim;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx / dim), j = static_cast<int>(idx % dim);
+    const int a = i < j ? i : j, b = i < j ? j : i;
+    // tiles are stored for tile_row <= tile_col; inside a diagonal tile both triangles are valid
+    const double s = scatter[static_cast<size_t>(a) * dim + b];
+    const double di = sum[i] / n, dj = sum[j] / n;
+    const double c = (s - n * di * dj) / (n - 1.0);
+    cov[idx] = c;
+    if (i == j) {
+      mean[i] = static_cast<double>(shift[i]) + di;
+      atomicAdd(trace, c);
+    }
+  }
+}
+
+// ============================================================================================================
+// 4. Householder tridiagonalisation (fp64, matrix [n][n] symmetric, both triangles kept).
+//    tridiag_step(j) applies reflector j (rank-2 update of the trailing block) and, fused in the same pass over
+//    the matrix, forms reflector j+1 and p_{j+1} = tau A v.  One launch per column; the 33 MB matrix stays in L2.
+//      V    [n][n]: row t holds reflector t (entries t+1..n-1; v[t+1] = 1)
+//      tau  [n], diag [n], off [n] (off[t] = sub-diagonal between t and t+1)
+//      pbuf [2][n]: p vectors, ping-pong
+// ============================================================================================================
+constexpr int kTriThreads = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) s += red[i];
+  return s;
+}
+
+__global__ void __launch_bounds__(kTriThreads) tridiag_step_kernel(double* __restrict__ A, int n, int j,
+                                                                    double* __restrict__ V, double* __restrict__ tau,
+                                                                    double* __restrict__ diag,
+                                                                    double* __restrict__ off,
+                                                                    double* __restrict__ pbuf) {
+  extern __shared__ double sh[];
+  double* w = sh;           // [n] w_j           (indices j+1..n-1 valid)
+  double* v = sh + n;       // [n] v_j
+  double* vn = sh + 2 * n;  // [n] v_{j+1}       (indices t+1..n-1 valid)
+  __shared__ double red[kTriThreads / 32];
+  __shared__ double s_tau_next, s_scale, s_beta;
+
+  const int tid = threadIdx.x;
+  const int t = j + 1;  // row whose reflector is formed in this launch
+  const double* p_cur = pbuf + static_cast<size_t>((j & 1)) * n;
+  double* p_next = pbuf + static_cast<size_t>((t & 1)) * n;
+
+  // ---- w_j = p_j - (tau_j/2 * p_j.v_j) v_j ----
+  if (j >= 0) {
+    const double tj = tau[j];
+    double part = 0.0;
+    for (int c = t + tid; c < n; c += kTriThreads) {
+      const double vv = V[static_cast<size_t>(j) * n + c];
+      const double pp = p_cur[c];
+      v[c] = vv;
+      w[c] = pp;
+      part += vv * pp;
+    }
+    const double alpha = 0.5 * tj * block_sum(part, red);
+    for (int c = t + tid; c < n; c += kTriThreads) w[c] -= alpha * v[c];
+  } else {
+    for (int c = t + tid; c < n; c += kTriThreads) {
+      v[c] = 0.0;
+      w[c] = 0.0;
+    }
+  }
+  __syncthreads();
+
+  // ---- updated row t -> d[t], x = A_new[t][t+1:] -> reflector t ----
+  const double vt = v[t], wt = w[t];
+  double norm2 = 0.0;
+  for (int c = t + 1 + tid; c < n; c += kTriThreads) {
+    const double a = A[static_cast<size_t>(t) * n + c] - vt * w[c] - wt * v[c];
+    vn[c] = a;
+    if (c > t + 1) norm2 += a * a;
+  }
+  norm2 = block_sum(norm2, red);
+  if (tid == 0) {
+    const double alpha = vn[t + 1];
+    double beta, tn, scale;
+    if (norm2 == 0.0) {
+      beta = alpha;
+      tn = 0.0;
+      scale = 0.0;
+    } else {
+      beta = -copysign(sqrt(alpha * alpha + norm2), alpha);
+      tn = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
+    }
+    s_tau_next = tn;
+    s_scale = scale;
+    s_beta = beta;
+    if (blockIdx.x == 0) {
+      diag[t] = A[static_cast<size_t>(t) * n + t] - 2.0 * vt * wt;
+      off[t] = beta;
+      tau[t] = tn;
+    }
+  }
+  __syncthreads();
+  const double tn = s_tau_next, scale = s_scale;
+  for (int c = t + 1 + tid; c < n; c += kTriThreads) {
+    const double val = (c == t + 1) ? 1.0 : vn[c] * scale;
+    vn[c] = val;
+    if (blockIdx.x == 0) V[static_cast<size_t>(t) * n + c] = val;
+  }
+  __syncthreads();
+
+  // ---- trailing block rows i >= t+1: rank-2 update fused with p_{t} = tau_t * A_new[i, t+1:] . v_t ----
+  const int warp = tid >> 5, lane = tid & 31;
+  const int warps_total = gridDim.x * (kTriThreads / 32);
+  for (int i = t + 1 + blockIdx.x * (kTriThreads / 32) + warp; i < n; i += warps_total) {
+    double* row = A + static_cast<size_t>(i) * n;
+    const double vi = v[i], wi = w[i];
+    double acc = 0.0;
+    for (int c = t + 1 + lane; c < n; c += 32) {
+      const double a = row[c] - vi * w[c] - wi * v[c];
+      row[c] = a;
+      acc += a * vn[c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) p_next[i] = tn * acc;
+  }
+}
+
+// ============================================================================================================
+// 5. top-k eigenvalues of the tridiagonal by multisection (one warp per eigenvalue, 32 shifts per round).
+//    Sturm count with LAPACK's pivmin safeguard (dlaebz).
+// ============================================================================================================
+__global__ void __launch_bounds__(128) bisect_topk_kernel(const double* __restrict__ diag,
+                                                          const double* __restrict__ off, int n, int k,
+                                                          double* __restrict__ evals, double* __restrict__ tnorm) {
+  extern __shared__ double sh[];
+  double* d = sh;
+  double* e2 = sh + n;  // e2[i] = off[i-1]^2 for i>=1
+  __shared__ double red[4];
+  double gl = INFINITY, gu = -INFINITY, emax = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double di = diag[i];
+    const double el = i > 0 ? off[i - 1] : 0.0, er = i < n - 1 ? off[i] : 0.0;
+    d[i] = di;
+    e2[i] = el * el;
+    gl = fmin(gl, di - fabs(el) - fabs(er));
+    gu = fmax(gu, di + fabs(el) + fabs(er));
+    emax = fmax(emax, fabs(el));
+  }
+  // block min/max
+  for (int o = 16; o > 0; o >>= 1) {
+    gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
+    gu = fmax(gu, __shfl_xor_sync(0xffffffffu, gu, o));
+    emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+  }
+  __shared__ double s_gl[4], s_gu[4], s_em[4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_gl[warp] = gl;
+    s_gu[warp] = gu;
+    s_em[warp] = emax;
+  }
+  __syncthreads();
+  gl = fmin(fmin(s_gl[0], s_gl[1]), fmin(s_gl[2], s_gl[3]));
+  gu = fmax(fmax(s_gu[0], s_gu[1]), fmax(s_gu[2], s_gu[3]));
+  emax = fmax(fmax(s_em[0], s_em[1]), fmax(s_em[2], s_em[3]));
+  (void)red;
+  const double tn = fmax(fabs(gl), fabs(gu));
+  const double pivmin = fmax(2.2250738585072014e-308 * fmax(1.0, emax * emax), 1e-300);
+  if (blockIdx.x == 0 && threadIdx.x == 0) tnorm[0] = tn;
+  const int which = blockIdx.x * 4 + warp;  // which-th largest
+  if (which >= k) return;
+  const int idx = n - 1 - which;  // ascending 0-based index
+  double lo = gl - 2.0 * tn * 2.220446049250313e-16 * n - 2.0 * pivmin;
+  double hi = gu + 2.0 * tn * 2.220446049250313e-16 * n + 2.0 * pivmin;
+  for (int round = 0; round < 13; ++round) {
+    const double x = lo + (hi - lo) * (static_cast<double>(lane + 1) / 33.0);
+    double q = d[0] - x;
+    int cnt = q < 0.0;
+    for (int i = 1; i < n; ++i) {
+      if (fabs(q) < pivmin) q = -pivmin;
+      q = d[i] - x - e2[i] / q;
+      cnt += q < 0.0;
+    }
+    // lanes with cnt <= idx lie at or below the eigenvalue
+    const unsigned below = __ballot_sync(0xffffffffu, cnt <= idx);
+    const int nb = __popc(below);  // monotone: lanes 0..nb-1
+    const double new_lo = nb > 0 ? __shfl_sync(0xffffffffu, x, nb - 1) : lo;
+    const double new_hi = nb < 32 ? __shfl_sync(0xffffffffu, x, nb < 32 ? nb : 31) : hi;
+    lo = new_lo;
+    hi = new_hi;
+  }
+  if (lane == 0) evals[which] = 0.5 * (lo + hi);
+}
+
+// ============================================================================================================
+// 6. inverse iteration on the tridiagonal (one thread per eigenvector; Gaussian elimination with partial pivoting
+//    as in LAPACK dgtsv), pseudo-random start, 3 solves.  work: [k][5][n] doubles.
+// ============================================================================================================
+__device__ __forceinline__ double hash_unit(uint32_t a, uint32_t b) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u;
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  h *= 0x297A2D39u;
+  h ^= h >> 15;
+  return (static_cast<double>(h) / 4294967296.0) - 0.5;
+}
+
+__global__ void inverse_iteration_kernel(const double* __restrict__ diag, const double* __restrict__ off, int n, int k,
+                                         const double* __restrict__ evals, const double* __restrict__ tnorm,
+                                         double* __restrict__ work, double* __restrict__ Z) {
+  const int which = blockIdx.x * blockDim.x + threadIdx.x;
+  if (which >= k) return;
+  double* dl = work + static_cast<size_t>(which) * 5 * n;
+  double* dd = dl + n;
+  double* du = dd + n;
+  double* du2 = du + n;
+  double* b = du2 + n;
+  const double lam = evals[which];
+  const double pivmin = fmax(tnorm[0], 1e-300) * 2.220446049250313e-16;
+  for (int i = 0; i < n; ++i) b[i] = hash_unit(static_cast<uint32_t>(which), static_cast<uint32_t>(i));
+  for (int iter = 0; iter < 3; ++iter) {
+    for (int i = 0; i < n; ++i) {
+      dd[i] = diag[i] - lam;
+      if (i < n - 1) {
+        dl[i] = off[i];
+        du[i] = off[i];
+      }
+      du2[i] = 0.0;
+    }
+    // forward elimination with partial pivoting
+    for (int i = 0; i < n - 1; ++i) {
+      if (fabs(dd[i]) >= fabs(dl[i])) {
+        if (fabs(dd[i]) < pivmin) dd[i] = copysign(pivmin, dd[i] == 0.0 ? 1.0 : dd[i]);
+        const double f = dl[i] / dd[i];
+        dd[i + 1] -= f * du[i];
+        b[i + 1] -= f * b[i];
+        du2[i] = 0.0;
+      } else {
+        const double f = dd[i] / dl[i];
+        dd[i] = dl[i];
+        const double tmp = dd[i + 1];
+        dd[i + 1] = du[i] - f * tmp;
+        if (i < n - 2) {
+          du2[i] = du[i + 1];
+          du[i + 1] = -f * du2[i];
+        }
+        du[i] = tmp;
+        const double tb = b[i];
+        b[i] = b[i + 1];
+        b[i + 1] = tb - f * b[i + 1];
+      }
+    }
+    if (fabs(dd[n - 1]) < pivmin) dd[n - 1] = copysign(pivmin, dd[n - 1] == 0.0 ? 1.0 : dd[n - 1]);
+    // back substitution
+    b[n - 1] /= dd[n - 1];
+    if (n > 1) b[n - 2] = (b[n - 2] - du[n - 2] * b[n - 1]) / dd[n - 2];
+    for (int i = n - 3; i >= 0; --i) b[i] = (b[i] - du[i] * b[i + 1] - du2[i] * b[i + 2]) / dd[i];
+    // normalise (max-abs first to stay in range)
+    double mx = 0.0;
+    for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(b[i]));
+    const double inv = mx > 0.0 ? 1.0 / mx : 1.0;
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+      b[i] *= inv;
+      s += b[i] * b[i];
+    }
+    const double rn = 1.0 / sqrt(s);
+    for (int i = 0; i < n; ++i) b[i] *= rn;
+  }
+  for (int i = 0; i < n; ++i) Z[static_cast<size_t>(which) * n + i] = b[i];
+}
+
+// Re-orthogonalise eigenvectors whose eigenvalues are numerically degenerate (|gap| < 1e-8 ||T||); single CTA.
+__global__ void __launch_bounds__(256) cluster_mgs_kernel(double* __restrict__ Z, int n, int k,
+                                                          const double* __restrict__ evals,
+                                                          const double* __restrict__ tnorm) {
+  __shared__ double red[8];
+  const double tol = 1e-8 * tnorm[0];
+  int cluster_start = 0;
+  for (int i = 1; i < k; ++i) {
+    if (fabs(evals[i - 1] - evals[i]) >= tol) {
+      cluster_start = i;
+      continue;
+    }
+    double* zi = Z + static_cast<size_t>(i) * n;
+    for (int j = cluster_start; j < i; ++j) {
+      const double* zj = Z + static_cast<size_t>(j) * n;
+      double part = 0.0;
+      for (int c = threadIdx.x; c < n; c += blockDim.x) part += zi[c] * zj[c];
+      const double dot = block_sum(part, red);
+      for (int c = threadIdx.x; c < n; c += blockDim.x) zi[c] -= dot * zj[c];
+      __syncthreads();
+    }
+    double part = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) part += zi[c] * zi[c];
+    const double nn = block_sum(part, red);
+    const double rn = nn > 0.0 ? 1.0 / sqrt(nn) : 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) zi[c] *= rn;
+    __syncthreads();
+  }
+}
+
+// ============================================================================================================
+// 7. back-transform y = H_0 H_1 ... H_{n-2} z (one CTA per eigenvector), then sklearn's sign convention:
+//    the entry of largest magnitude (first on ties) is made positive.
+// ============================================================================================================
+__global__ void __launch_bounds__(256) back_transform_kernel(const double* __restrict__ V,
+                                                             const double* __restrict__ tau, int n,
+                                                             const double* __restrict__ Z,
+                                                             double* __restrict__ comps) {
+  extern __shared__ double z[];
+  __shared__ double red[8];
+  __shared__ double s_best;
+  __shared__ int s_idx;
+  const int which = blockIdx.x;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) z[c] = Z[static_cast<size_t>(which) * n + c];
+  __syncthreads();
+  for (int t = n - 2; t >= 0; --t) {
+    const double tt = tau[t];
+    if (tt == 0.0) continue;  // uniform across the block
+    const double* vt = V + static_cast<size_t>(t) * n;
+    double part = 0.0;
+    for (int c = t + 1 + threadIdx.x; c < n; c += blockDim.x) part += vt[c] * z[c];
+    const double s = tt * block_sum(part, red);
+    for (int c = t + 1 + threadIdx.x; c < n; c += blockDim.x) z[c] -= s * vt[c];
+    __syncthreads();
+  }
+  __syncthreads();
+  // argmax |z| (first occurrence)
+  double best = -1.0;
+  int bidx = n;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    const double a = fabs(z[c]);
+    if (a > best) {
+      best = a;
+      bidx = c;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ob > best || (ob == best && oi < bidx)) {
+      best = ob;
+      bidx = oi;
+    }
+  }
+  __shared__ double wb[8];
+  __shared__ int wi[8];
+  if ((threadIdx.x & 31) == 0) {
+    wb[threadIdx.x >> 5] = best;
+    wi[threadIdx.x >> 5] = bidx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = wb[0];
+    int bi = wi[0];
+    for (int i = 1; i < 8; ++i)
+      if (wb[i] > b || (wb[i] == b && wi[i] < bi)) {
+        b = wb[i];
+        bi = wi[i];
+      }
+    s_best = b;
+    s_idx = bi;
+  }
+  __syncthreads();
+  (void)s_best;
+  const double sign = z[s_idx] < 0.0 ? -1.0 : 1.0;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) comps[static_cast<size_t>(which) * n + c] = sign * z[c];
+}
+
+// clip negative eigenvalues to zero (sklearn _pca.py:626)
+__global__ void clip_evals_kernel(double* evals, int k) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k && evals[i] < 0.0) evals[i] = 0.0;
+}
+
+// ============================================================================================================
+// 8. projection  Z[r][c] = sum_j (x[r][j] - mean[j]) * comps[c][j]   (fp64 accumulate, fp32 out)
+// ============================================================================================================
+constexpr int kProjRows = 32, kProjChunk = 64, kProjThreads = 256;
+
+__global__ void __launch_bounds__(kProjThreads) project_kernel(const float* __restrict__ x, long long n_rows, int dim,
+                                                               const double* __restrict__ mean,
+                                                               const double* __restrict__ comps, int k,
+                                                               float* __restrict__ z) {
+  extern __shared__ double shp[];
+  double* xs = shp;                            // [kProjRows][kProjChunk+1]
+  double* vs = shp + kProjRows * (kProjChunk + 1);  // [k][kProjChunk+1]
+  const long long r0 = static_cast<long long>(blockIdx.x) * kProjRows;
+  const int r = threadIdx.x >> 3;   // 0..31
+  const int cg = threadIdx.x & 7;   // component group
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  for (int j0 = 0; j0 < dim; j0 += kProjChunk) {
+    for (int i = threadIdx.x; i < kProjRows * kProjChunk; i += kProjThreads) {
+      const int rr = i / kProjChunk, jj = i % kProjChunk;
+      const long long row = r0 + rr;
+      xs[rr * (kProjChunk + 1) + jj] =
+          row < n_rows ? static_cast<double>(x[row * dim + j0 + jj]) - mean[j0 + jj] : 0.0;
+    }
+    for (int i = threadIdx.x; i < k * kProjChunk; i += kProjThreads) {
+      const int cc = i / kProjChunk, jj = i % kProjChunk;
+      vs[cc * (kProjChunk + 1) + jj] = comps[static_cast<size_t>(cc) * dim + j0 + jj];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int jj = 0; jj < kProjChunk; ++jj) {
+      const double xv = xs[r * (kProjChunk + 1) + jj];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = cg + 8 * i;
+        if (c < k) acc[i] += xv * vs[c * (kProjChunk + 1) + jj];
+      }
+    }
+    __syncthreads();
+  }
+  const long long row = r0 + r;
+  if (row < n_rows) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = cg + 8 * i;
+      if (c < k) z[row * k + c] = static_cast<float>(acc[i]);
+    }
+  }
+}
+
+__global__ void add_count_kernel(double* count, double v) { count[0] += v; }
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace irp
+
+using namespace irp;
+
+extern "C" {
+
+size_t irp_cov_workspace_bytes(int64_t n_rows, int dim) {
+  if (n_rows <= 0 || dim <= 0) return 0;
+  const size_t n_pad = align_up(static_cast<size_t>(n_rows), 64);
+  return 3 * align_up(static_cast<size_t>(dim) * n_pad * sizeof(__nv_bfloat16), 1024) + 1024;
+}
+
+int irp_cov_accumulate(const float* d_x, int64_t n_rows, int dim, const float* d_shift, double* d_count,
+                       double* d_sum, double* d_scatter, void* d_workspace, size_t workspace_bytes, void* stream) {
+  IRP_REQUIRE(d_x && d_shift && d_count && d_sum && d_scatter && d_workspace, "cov_accumulate: null argument");
+  IRP_REQUIRE(n_rows > 0 && dim > 0 && dim % 128 == 0, "cov_accumulate: n_rows %lld, dim %d (dim must be a multiple of 128)",
+              static_cast<long long>(n_rows), dim);
+  IRP_REQUIRE(workspace_bytes >= irp_cov_workspace_bytes(n_rows, dim), "cov_accumulate: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n_pad = align_up(static_cast<size_t>(n_rows), 64);
+  const size_t arr = align_up(static_cast<size_t>(dim) * n_pad * sizeof(__nv_bfloat16), 1024);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(d_workspace), 1024));
+  __nv_bfloat16* at = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(ws + arr);
+  __nv_bfloat16* ct = reinterpret_cast<__nv_bfloat16*>(ws + 2 * arr);
+  dim3 grid(static_cast<unsigned>(n_pad / kSplitTile), dim / kSplitTile);
+  split_transpose_kernel<<<grid, 256, 0, st>>>(d_x, n_rows, dim, d_shift, static_cast<long long>(n_pad), at, bt, ct,
+                                               d_sum);
+  IRP_CUDA_OK(cudaGetLastError());
+  add_count_kernel<<<1, 1, 0, st>>>(d_count, static_cast<double>(n_rows));
+  IRP_CUDA_OK(cudaGetLastError());
+
+  CovParams p;
+  memset(&p, 0, sizeof(p));
+  uint64_t dims[2] = {n_pad, static_cast<uint64_t>(dim)};
+  uint64_t strides[1] = {n_pad * 2};
+  uint32_t box[2] = {kCovBK, 128};
+  IRP_TRY(encode_bf16_map(&p.tm[0], at, 2, dims, strides, box, 128));
+  IRP_TRY(encode_bf16_map(&p.tm[1], bt, 2, dims, strides, box, 128));
+  IRP_TRY(encode_bf16_map(&p.tm[2], ct, 2, dims, strides, box, 128));
+  p.tiles_1d = dim / 128;
+  p.n_tri = p.tiles_1d * (p.tiles_1d + 1) / 2;
+  p.k_blocks_total = static_cast<int>(n_pad / kCovBK);
+  // 512 samples per fp32 accumulation chain: measured 9e-5 rad subspace error at k=50 (32 blocks: 5e-4)
+  p.k_blocks_per_chunk = 8;
+  if (const char* e = getenv("IRP_COV_CHUNK")) p.k_blocks_per_chunk = atoi(e) > 0 ? atoi(e) : 8;
+  p.n_chunks = ceil_div(p.k_blocks_total, p.k_blocks_per_chunk);
+  p.num_units = p.n_tri * p.n_chunks;
+  p.dim = dim;
+  p.scatter = d_scatter;
+  static bool configured = false;
+  if (!configured) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(cov_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCovSmem));
+    configured = true;
+  }
+  const int grid_g = p.num_units < num_sms() ? p.num_units : num_sms();
+  cov_gemm_kernel<<<grid_g, kCovThreads, kCovSmem, st>>>(p);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+size_t irp_pca_fit_workspace_bytes(int dim, int k) {
+  if (dim <= 0 || k <= 0) return 0;
+  const size_t n = static_cast<size_t>(dim);
+  size_t b = 0;
+  b += n * n * 8;                             // covariance / working matrix
+  b += n * n * 8;                             // reflectors V
+  b += 8 * n * 8;                             // tau, diag, off, pbuf[2], spare
+  b += static_cast<size_t>(k) * 5 * n * 8;    // inverse-iteration scratch
+  b += static_cast<size_t>(k) * n * 8;        // Z (tridiagonal eigenvectors)
+  b += 1024;
+  return b;
+}
+
+int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scatter, const float* d_shift, int dim,
+                int k, double* d_mean, double* d_components, double* d_eigenvalues, void* d_workspace,
+                size_t workspace_bytes, void* stream) {
+  IRP_REQUIRE(d_count && d_sum && d_scatter && d_shift && d_mean && d_components && d_eigenvalues && d_workspace,
+              "pca_fit: null argument");
+  IRP_REQUIRE(dim >= 4 && dim <= 4096 && k >= 1 && k <= dim && k <= 512, "pca_fit: dim %d / k %d unsupported", dim, k);
+  IRP_REQUIRE(workspace_bytes >= irp_pca_fit_workspace_bytes(dim, k), "pca_fit: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = dim;
+  double* ws = reinterpret_cast<double*>(align_up(reinterpret_cast<size_t>(d_workspace), 256));
+  double* A = ws;
+  double* V = A + static_cast<size_t>(n) * n;
+  double* tau = V + static_cast<size_t>(n) * n;
+  double* diag = tau + n;
+  double* off = diag + n;
+  double* pbuf = off + n;       // [2][n]
+  double* scal = pbuf + 2 * n;  // [n]: scal[0] = trace, scal[1] = ||T||
+  double* work = scal + 3 * n;
+  double* Z = work + static_cast<size_t>(k) * 5 * n;
+
+  IRP_CUDA_OK(cudaMemsetAsync(tau, 0, 8 * static_cast<size_t>(n) * sizeof(double), st));
+  assemble_cov_kernel<<<num_sms() * 4, 256, 0, st>>>(d_count, d_sum, d_scatter, d_shift, n, d_mean, A, scal);
+  IRP_CUDA_OK(cudaGetLastError());
+
+  // ---- tridiagonalisation: launches j = -1 .. n-3 ----
+  const size_t tri_smem = 3 * static_cast<size_t>(n) * sizeof(double);
+  static size_t tri_cfg = 0;
+  if (tri_smem > 32 * 1024 && tri_smem > tri_cfg) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(tridiag_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(tri_smem)));
+    tri_cfg = tri_smem;
+  }
+  const int rows_per_cta = kTriThreads / 32;
+  for (int j = -1; j <= n - 3; ++j) {
+    const int rows = n - (j + 2);
+    int grid = ceil_div(rows > 0 ? rows : 1, rows_per_cta);
+    const int cap = num_sms() * 2;
+    if (grid > cap) grid = cap;
+    tridiag_step_kernel<<<grid, kTriThreads, tri_smem, st>>>(A, n, j, V, tau, diag, off, pbuf);
+  }
+  IRP_CUDA_OK(cudaGetLastError());
+  // last diagonal entry: after launch j = n-3 the (n-1,n-1) element is final
+  IRP_CUDA_OK(cudaMemcpyAsync(diag + (n - 1), A + static_cast<size_t>(n - 1) * n + (n - 1), sizeof(double),
+                              cudaMemcpyDeviceToDevice, st));
+  // d[0] is produced by launch j=-1 (t=0) as A[0][0] ✓
+
+  // ---- eigenvalues (top-k) ----
+  const size_t bis_smem = 2 * static_cast<size_t>(n) * sizeof(double);
+  static size_t bis_cfg = 0;
+  if (bis_smem > 32 * 1024 && bis_smem > bis_cfg) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(bisect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(bis_smem)));
+    bis_cfg = bis_smem;
+  }
+  bisect_topk_kernel<<<ceil_div(k, 4), 128, bis_smem, st>>>(diag, off, n, k, d_eigenvalues, scal + 1);
+  IRP_CUDA_OK(cudaGetLastError());
+  // ---- eigenvectors of T ----
+  inverse_iteration_kernel<<<ceil_div(k, 32), 32, 0, st>>>(diag, off, n, k, d_eigenvalues, scal + 1, work, Z);
+  IRP_CUDA_OK(cudaGetLastError());
+  cluster_mgs_kernel<<<1, 256, 0, st>>>(Z, n, k, d_eigenvalues, scal + 1);
+  IRP_CUDA_OK(cudaGetLastError());
+  // ---- back-transform + sign ----
+  const size_t bt_smem = static_cast<size_t>(n) * sizeof(double);
+  static size_t bt_cfg = 0;
+  if (bt_smem > 32 * 1024 && bt_smem > bt_cfg) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(back_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(bt_smem)));
+    bt_cfg = bt_smem;
+  }
+  back_transform_kernel<<<k, 256, bt_smem, st>>>(V, tau, n, Z, d_components);
+  IRP_CUDA_OK(cudaGetLastError());
+  clip_evals_kernel<<<ceil_div(k, 128), 128, 0, st>>>(d_eigenvalues, k);
+  IRP_CUDA_OK(cudaGetLastError());
+  // total variance (trace of C) is returned right after the k eigenvalues
+  IRP_CUDA_OK(cudaMemcpyAsync(d_eigenvalues + k, scal, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return IRP_OK;
+}
+
+int irp_pca_transform(const float* d_x, int64_t n_rows, int dim, const double* d_mean, const double* d_components,
+                      int k, float* d_z, void* stream) {
+  IRP_REQUIRE(d_x && d_mean && d_components && d_z, "pca_transform: null argument");
+  IRP_REQUIRE(n_rows > 0 && dim > 0 && dim % kProjChunk == 0 && k >= 1 && k <= 128,
+              "pca_transform: n_rows %lld dim %d k %d unsupported (k <= 128, dim %% 64 == 0)",
+              static_cast<long long>(n_rows), dim, k);
+  const size_t smem = (static_cast<size_t>(kProjRows) + k) * (kProjChunk + 1) * sizeof(double);
+  static size_t cfg = 0;
+  if (smem > 32 * 1024 && smem > cfg) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cfg = smem;
+  }
+  const unsigned grid = static_cast<unsigned>(ceil_div64(n_rows, kProjRows));
+  project_kernel<<<grid, kProjThreads, smem, static_cast<cudaStream_t>(stream)>>>(d_x, n_rows, dim, d_mean,
+                                                                                  d_components, k, d_z);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+}  // extern "C"

@@ -118,8 +118,9 @@ int irp_cov_accumulate(const float* d_x, int64_t n_rows, int dim, const float* d
                        double* d_sum, double* d_scatter, void* d_workspace, size_t workspace_bytes, void* stream);
 
 size_t irp_pca_fit_workspace_bytes(int dim, int k);
-/* Outputs (device): mean fp64[dim], components fp64[k,dim] (row-major), eigenvalues fp64[dim] descending
- * (all of them; explained_variance_ = first k, total variance = their sum). Synchronises `stream`. */
+/* Outputs (device): mean fp64[dim]; components fp64[k,dim] (row-major, sklearn sign convention); eigenvalues
+ * fp64[k+1]: the k largest eigenvalues of the covariance in descending order (explained_variance_) followed by
+ * the total variance trace(C) (denominator of explained_variance_ratio_). Work is enqueued on `stream`. */
 int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scatter, const float* d_shift,
                 int dim, int k, double* d_mean, double* d_components, double* d_eigenvalues, void* d_workspace,
                 size_t workspace_bytes, void* stream);

@@ -314,8 +314,212 @@ def t_preprocess(lib):
     return ok
 
 
+def synth_features(n, d=2048, seed=0):
+    """Embedding-like matrix: a few dominant directions, a slowly decaying tail, positive mean."""
+    rng = np.random.default_rng(seed)
+    r = 256
+    basis = np.linalg.qr(rng.standard_normal((d, r)))[0]
+    sv = np.concatenate([[150.0, 60.0, 30.0], 12.0 * np.arange(1, r - 2) ** -0.6])
+    x = (rng.standard_normal((n, r)) * sv) @ basis.T + 0.05 * rng.standard_normal((n, d)) + 3.0
+    return np.maximum(x, 0).astype(np.float32)  # relu-like, many exact zeros
+
+
+def gpu_pca(lib, x_t, k, shift_t):
+    n, d = x_t.shape
+    cnt = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ssum = torch.zeros(d, dtype=torch.float64, device="cuda")
+    scat = torch.zeros(d, d, dtype=torch.float64, device="cuda")
+    wsb = lib.irp_cov_workspace_bytes(n, d)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.irp_cov_accumulate(ptr(x_t), n, d, ptr(shift_t), ptr(cnt), ptr(ssum), ptr(scat), ptr(ws), wsb,
+                                      stream()), "cov_accumulate")
+    mean = torch.empty(d, dtype=torch.float64, device="cuda")
+    comps = torch.empty(k, d, dtype=torch.float64, device="cuda")
+    ev = torch.empty(k + 1, dtype=torch.float64, device="cuda")
+    wsb2 = lib.irp_pca_fit_workspace_bytes(d, k)
+    ws2 = torch.empty(wsb2, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.irp_pca_fit(ptr(cnt), ptr(ssum), ptr(scat), ptr(shift_t), d, k, ptr(mean), ptr(comps), ptr(ev),
+                               ptr(ws2), wsb2, stream()), "pca_fit")
+    z = torch.empty(n, k, dtype=torch.float32, device="cuda")
+    _lib.check(lib.irp_pca_transform(ptr(x_t), n, d, ptr(mean), ptr(comps), k, ptr(z), stream()), "pca_transform")
+    torch.cuda.synchronize()
+    return mean, comps, ev, z, (cnt, ssum, scat)
+
+
+def t_pca(lib):
+    from oracle import pca_ref
+    ok = True
+    for (n, k) in [(1500, 50), (700, 20)]:
+        x = synth_features(n, seed=n)
+        x_t = torch.from_numpy(x).cuda()
+        shift_t = x_t[:256].mean(0).contiguous()
+        mean, comps, ev, z, (cnt, ssum, scat) = gpu_pca(lib, x_t, k, shift_t)
+        ref = pca_ref.pca_fit(x, k)
+        xs = x.astype(np.float64) - shift_t.cpu().numpy().astype(np.float64)
+        s_ref = xs.T @ xs
+        s_gpu = np.triu(scat.cpu().numpy())
+        s_gpu = s_gpu + np.triu(s_gpu, 1).T
+        ds = s_gpu - s_ref
+        print(f"[pca] scatter: max|dS|/max|S|={np.abs(ds).max() / np.abs(s_ref).max():.2e}, ||dS||_2/(n-1)="
+              f"{np.linalg.norm(ds, 2) / (n - 1):.2e}, gap(k)={ref.eigenvalues[k - 1] - ref.eigenvalues[k]:.3e}, "
+              f"mean signed rel err={np.mean(ds / (np.abs(s_ref) + 1e-30)):.2e}", flush=True)
+        ang = pca_ref.subspace_angle(comps.cpu().numpy(), ref.components)
+        ev_rel = np.abs(ev[:k].cpu().numpy() - ref.explained_variance).max() / ref.explained_variance[0]
+        ev_rel_each = (np.abs(ev[:k].cpu().numpy() - ref.explained_variance) / ref.explained_variance).max()
+        tv_rel = abs(ev[k].item() - ref.eigenvalues.sum()) / ref.eigenvalues.sum()
+        mean_err = np.abs(mean.cpu().numpy() - ref.mean).max()
+        cosv = np.abs((comps.cpu().numpy() * ref.components).sum(1))
+        sign_ok = bool(((comps.cpu().numpy() * ref.components).sum(1) > 0).all())
+        zref = pca_ref.pca_transform(x, ref.mean, ref.components)
+        zerr = np.abs(z.cpu().numpy() - zref).max() / np.abs(zref).max()
+        orth = np.abs(comps.cpu().numpy() @ comps.cpu().numpy().T - np.eye(k)).max()
+        good = ang < 1e-3 and ev_rel_each < 1e-4 and sign_ok and zerr < 1e-3
+        print(f"[pca] n={n} k={k}: subspace angle={ang:.3e} rad, eval rel err(max)={ev_rel_each:.2e} "
+              f"(vs top {ev_rel:.2e}), total var rel={tv_rel:.2e}, mean err={mean_err:.2e}, min|cos|={cosv.min():.6f}, "
+              f"signs {'ok' if sign_ok else 'BAD'}, orth err={orth:.2e}, Z rel err={zerr:.2e} "
+              f"{'OK' if good else 'FAIL'}", flush=True)
+        ok &= good
+    # timing at 27k rows
+    n, k = 27000, 50
+    x_t = torch.from_numpy(synth_features(4096, seed=7)).cuda().repeat(7, 1)[:n].contiguous()
+    x_t += 0.01 * torch.randn_like(x_t)
+    shift_t = x_t[:256].mean(0).contiguous()
+    d = 2048
+    cnt = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ssum = torch.zeros(d, dtype=torch.float64, device="cuda")
+    scat = torch.zeros(d, d, dtype=torch.float64, device="cuda")
+    wsb = lib.irp_cov_workspace_bytes(n, d)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    mean = torch.empty(d, dtype=torch.float64, device="cuda")
+    comps = torch.empty(k, d, dtype=torch.float64, device="cuda")
+    ev = torch.empty(k + 1, dtype=torch.float64, device="cuda")
+    wsb2 = lib.irp_pca_fit_workspace_bytes(d, k)
+    ws2 = torch.empty(wsb2, dtype=torch.uint8, device="cuda")
+    z = torch.empty(n, k, dtype=torch.float32, device="cuda")
+    ev_t = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for it in range(2):
+        cnt.zero_(); ssum.zero_(); scat.zero_()
+        ev_t[0].record()
+        lib.irp_cov_accumulate(ptr(x_t), n, d, ptr(shift_t), ptr(cnt), ptr(ssum), ptr(scat), ptr(ws), wsb, stream())
+        ev_t[1].record()
+        lib.irp_pca_fit(ptr(cnt), ptr(ssum), ptr(scat), ptr(shift_t), d, k, ptr(mean), ptr(comps), ptr(ev), ptr(ws2),
+                        wsb2, stream())
+        ev_t[2].record()
+        lib.irp_pca_transform(ptr(x_t), n, d, ptr(mean), ptr(comps), k, ptr(z), stream())
+        ev_t[3].record()
+        torch.cuda.synchronize()
+    print(f"[pca] n={n}: cov {ev_t[0].elapsed_time(ev_t[1]):.2f} ms, fit(eig) {ev_t[1].elapsed_time(ev_t[2]):.2f} ms, "
+          f"transform {ev_t[2].elapsed_time(ev_t[3]):.2f} ms", flush=True)
+    return ok
+
+
+def gpu_lof(lib, z_t, groups_t, n_groups, k, cont):
+    n, d = z_t.shape
+    scores = torch.empty(n, dtype=torch.float64, device="cuda")
+    offs = torch.empty(n_groups, dtype=torch.float64, device="cuda")
+    flags = torch.empty(n, dtype=torch.uint8, device="cuda")
+    wsb = lib.irp_lof_workspace_bytes(n, d, k)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.irp_lof(ptr(z_t), n, d, ptr(groups_t), n_groups, k, C.c_double(cont), ptr(scores), ptr(offs),
+                           ptr(flags), ptr(ws), wsb, stream()), "lof")
+    torch.cuda.synchronize()
+    return scores, offs, flags
+
+
+def t_lof(lib):
+    from oracle import lof_ref
+    from sklearn.neighbors import LocalOutlierFactor
+    ok = True
+    rng = np.random.default_rng(3)
+    n, d, G = 3000, 50, 10
+    y = rng.integers(0, G, n)
+    centers = rng.standard_normal((G, d)) * 4
+    z = (centers[y] + rng.standard_normal((n, d)) * rng.uniform(0.5, 2.0, (n, 1))).astype(np.float32)
+    z[:12] = z[20]  # duplicates
+    z_t = torch.from_numpy(z).cuda()
+    # global
+    sc, off, fl = gpu_lof(lib, z_t, None, 1, 75, 0.03)
+    lof = LocalOutlierFactor(n_neighbors=75, contamination=0.03)
+    pred = lof.fit_predict(z) == -1
+    s_ref = lof.negative_outlier_factor_.astype(np.float64)
+    rel = np.abs(sc.cpu().numpy() - s_ref).max() / np.abs(s_ref).max()
+    band = np.abs(s_ref - lof.offset_) < 1e-3 * abs(lof.offset_)
+    mism = ((fl.cpu().numpy() != 0) != pred) & ~band
+    o_ref = lof_ref.lof_scores(z, 75)
+    print(f"[lof global] score max rel err vs sklearn={rel:.2e}, vs oracle={np.abs(sc.cpu().numpy()-o_ref).max():.2e}, "
+          f"offset {off[0].item():.8f} vs {lof.offset_:.8f}, flagged {int(fl.sum())} vs {int(pred.sum())}, "
+          f"mismatches outside band={int(mism.sum())} {'OK' if mism.sum() == 0 and rel < 1e-5 else 'FAIL'}", flush=True)
+    ok &= mism.sum() == 0 and rel < 1e-5
+    # per class
+    g_t = torch.from_numpy(y.astype(np.int32)).cuda()
+    sc, off, fl = gpu_lof(lib, z_t, g_t, G, 30, 0.05)
+    bad = 0
+    worst = 0.0
+    for c in range(G):
+        m = y == c
+        lof = LocalOutlierFactor(n_neighbors=30, contamination=0.05)
+        pred = lof.fit_predict(z[m]) == -1
+        s_ref = lof.negative_outlier_factor_.astype(np.float64)
+        worst = max(worst, np.abs(sc.cpu().numpy()[m] - s_ref).max() / np.abs(s_ref).max())
+        band = np.abs(s_ref - lof.offset_) < 1e-3 * abs(lof.offset_)
+        bad += int((((fl.cpu().numpy()[m] != 0) != pred) & ~band).sum())
+    print(f"[lof per-class] worst score rel err={worst:.2e}, mismatches outside band={bad} "
+          f"{'OK' if bad == 0 and worst < 1e-5 else 'FAIL'}", flush=True)
+    ok &= bad == 0 and worst < 1e-5
+    # small groups (k clipped) + centroid scorer
+    n2 = 400
+    y2 = np.concatenate([np.zeros(20, np.int64), np.ones(31, np.int64), rng.integers(2, 5, n2 - 51)])
+    z2 = rng.standard_normal((n2, 16)).astype(np.float32)
+    sc, off, fl = gpu_lof(lib, torch.from_numpy(z2).cuda(), torch.from_numpy(y2.astype(np.int32)).cuda(), 5, 30, 0.05)
+    import warnings
+    bad = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for c in range(5):
+            m = y2 == c
+            lof = LocalOutlierFactor(n_neighbors=30, contamination=0.05)
+            pred = lof.fit_predict(z2[m]) == -1
+            band = np.abs(lof.negative_outlier_factor_ - lof.offset_) < 1e-3 * abs(lof.offset_)
+            bad += int((((fl.cpu().numpy()[m] != 0) != pred) & ~band).sum())
+    print(f"[lof small groups] mismatches outside band={bad} {'OK' if bad == 0 else 'FAIL'}", flush=True)
+    ok &= bad == 0
+    dist = torch.empty(n, dtype=torch.float64, device="cuda")
+    zs = torch.empty(n, dtype=torch.float64, device="cuda")
+    thr = torch.empty(G, dtype=torch.float64, device="cuda")
+    fl2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    wsb = lib.irp_centroid_workspace_bytes(n, d, G)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.irp_centroid_zscore(ptr(z_t), n, d, ptr(g_t), G, C.c_double(0.05), ptr(dist), ptr(zs), ptr(thr),
+                                       ptr(fl2), ptr(ws), wsb, stream()), "centroid")
+    torch.cuda.synchronize()
+    rd, rz, rt, rf = lof_ref.centroid_zscore(z, y, G, 0.05)
+    e1 = np.abs(dist.cpu().numpy() - rd).max()
+    e2 = np.abs(zs.cpu().numpy() - rz).max()
+    e3 = np.abs(thr.cpu().numpy() - rt).max()
+    fm = int(((fl2.cpu().numpy() != 0) != rf).sum())
+    print(f"[centroid] dist err={e1:.2e} zscore err={e2:.2e} thr err={e3:.2e} flag mismatches={fm} "
+          f"{'OK' if fm == 0 and e1 < 1e-9 else 'FAIL'}", flush=True)
+    ok &= fm == 0 and e1 < 1e-9
+    # timing 27k x 50
+    n = 27000
+    y = rng.integers(0, G, n)
+    z = (centers[y] + rng.standard_normal((n, d))).astype(np.float32)
+    z_t = torch.from_numpy(z).cuda()
+    g_t = torch.from_numpy(y.astype(np.int32)).cuda()
+    e0, e1_, e2_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    for _ in range(2):
+        e0.record()
+        gpu_lof(lib, z_t, g_t, G, 30, 0.05)
+        e1_.record()
+        gpu_lof(lib, z_t, None, 1, 75, 0.03)
+        e2_.record()
+        torch.cuda.synchronize()
+    print(f"[lof] n={n} d={d}: per-class {e0.elapsed_time(e1_):.2f} ms, global {e1_.elapsed_time(e2_):.2f} ms", flush=True)
+    return ok
+
+
 TESTS = {"conv_flat": t_conv_flat, "conv_3x3": t_conv_3x3, "conv_s2": t_conv_s2, "stem": t_stem, "resnet": t_resnet,
-         "preprocess": t_preprocess}
+         "preprocess": t_preprocess, "pca": t_pca, "lof": t_lof}
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
