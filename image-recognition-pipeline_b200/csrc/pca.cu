@@ -42,12 +42,12 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
     tile[i][tx] = v;
   }
   __syncthreads();
-  // column sums of this tile (fp32 over 64 rows, fp64 across tiles)
+  // column sums of this tile in fp64 (independent of how the rows are split into tiles / shards)
   if (ty == 0) {
-    float s = 0.f;
+    double s = 0.0;
 #pragma unroll 8
-    for (int i = 0; i < kSplitTile; ++i) s += tile[i][tx];
-    atomicAdd(&col_sum[c0 + tx], static_cast<double>(s));
+    for (int i = 0; i < kSplitTile; ++i) s += static_cast<double>(tile[i][tx]);
+    atomicAdd(&col_sum[c0 + tx], s);
   }
   // transposed write: thread tx walks samples (contiguous in the output), ty strides features
   for (int j = ty; j < kSplitTile; j += 4) {

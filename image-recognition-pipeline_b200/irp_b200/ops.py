@@ -1,0 +1,184 @@
+"""torch custom ops (namespace ``irp_b200``) over the C ABI of libirp_b200.so.
+
+Each op takes CUDA tensors, enqueues the library call on the current torch stream and returns torch tensors;
+torch is plumbing here (device memory, streams), every kernel is the library's own sm_100a code.  There is no
+CPU implementation behind these ops: they raise on non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _lib_for(t: torch.Tensor):
+    if not t.is_cuda:
+        raise RuntimeError("irp_b200 ops run on CUDA tensors only (no CPU fallback on the outlier-stage hot path)")
+    return _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# A1 preprocess
+# ---------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("irp_b200::preprocess", mutates_args=())
+def preprocess(pixels: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor, max_taps: int,
+               layout: int) -> torch.Tensor:
+    """Ragged uint8 HWC batch -> bf16 [n,3,224,224] (layout 0) or padded NHWC4 [n,230,230,4] (layout 1)."""
+    lib = _lib_for(pixels)
+    assert pixels.dtype == torch.uint8 and offsets.dtype == torch.int64 and hw.dtype == torch.int32
+    n = hw.shape[0]
+    shape = (n, 3, _lib.CROP, _lib.CROP) if layout == _lib.LAYOUT_NCHW else (n, _lib.PAD_HW, _lib.PAD_HW, 4)
+    out = torch.empty(shape, dtype=torch.bfloat16, device=pixels.device)
+    ws_bytes = lib.irp_preprocess_workspace_bytes(n, max_taps)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pixels.device)
+    _lib.check(lib.irp_preprocess(_ptr(pixels), _ptr(offsets), _ptr(hw), n, max_taps, _ptr(ws), ws_bytes, _ptr(out),
+                                  layout, _stream()), "irp_preprocess")
+    return out
+
+
+@preprocess.register_fake
+def _(pixels, offsets, hw, max_taps, layout):
+    n = hw.shape[0]
+    shape = (n, 3, _lib.CROP, _lib.CROP) if layout == _lib.LAYOUT_NCHW else (n, _lib.PAD_HW, _lib.PAD_HW, 4)
+    return pixels.new_empty(shape, dtype=torch.bfloat16)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# A2 ResNet-50 trunk (handle passed as an integer address)
+# ---------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("irp_b200::resnet50_embed", mutates_args=())
+def resnet50_embed(handle: int, x_nhwc4p: torch.Tensor) -> torch.Tensor:
+    """bf16 [B,230,230,4] -> fp32 [B,2048] pooled embeddings."""
+    lib = _lib_for(x_nhwc4p)
+    assert x_nhwc4p.dtype == torch.bfloat16 and x_nhwc4p.is_contiguous()
+    b = x_nhwc4p.shape[0]
+    out = torch.empty((b, _lib.EMBED_DIM), dtype=torch.float32, device=x_nhwc4p.device)
+    _lib.check(lib.irp_resnet50_embed(C.c_void_p(handle), _ptr(x_nhwc4p), b, _ptr(out), _stream()),
+               "irp_resnet50_embed")
+    return out
+
+
+@resnet50_embed.register_fake
+def _(handle, x_nhwc4p):
+    return x_nhwc4p.new_empty((x_nhwc4p.shape[0], _lib.EMBED_DIM), dtype=torch.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# A3 PCA
+# ---------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("irp_b200::cov_accumulate", mutates_args=("count", "total", "scatter"))
+def cov_accumulate(x: torch.Tensor, shift: torch.Tensor, count: torch.Tensor, total: torch.Tensor,
+                   scatter: torch.Tensor) -> None:
+    """count += n; total += sum(x - shift); scatter += (x - shift)^T (x - shift)  (fp64 accumulators)."""
+    lib = _lib_for(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and shift.dtype == torch.float32
+    assert count.dtype == total.dtype == scatter.dtype == torch.float64
+    n, d = x.shape
+    ws_bytes = lib.irp_cov_workspace_bytes(n, d)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    _lib.check(lib.irp_cov_accumulate(_ptr(x), n, d, _ptr(shift), _ptr(count), _ptr(total), _ptr(scatter), _ptr(ws),
+                                      ws_bytes, _stream()), "irp_cov_accumulate")
+
+
+@torch.library.custom_op("irp_b200::pca_fit", mutates_args=())
+def pca_fit(count: torch.Tensor, total: torch.Tensor, scatter: torch.Tensor, shift: torch.Tensor,
+            k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (mean fp64[d], components fp64[k,d], eigenvalues fp64[k+1] = top-k then total variance)."""
+    lib = _lib_for(scatter)
+    d = scatter.shape[0]
+    mean = torch.empty(d, dtype=torch.float64, device=scatter.device)
+    comps = torch.empty((k, d), dtype=torch.float64, device=scatter.device)
+    evals = torch.empty(k + 1, dtype=torch.float64, device=scatter.device)
+    ws_bytes = lib.irp_pca_fit_workspace_bytes(d, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=scatter.device)
+    _lib.check(lib.irp_pca_fit(_ptr(count), _ptr(total), _ptr(scatter), _ptr(shift), d, k, _ptr(mean), _ptr(comps),
+                               _ptr(evals), _ptr(ws), ws_bytes, _stream()), "irp_pca_fit")
+    return mean, comps, evals
+
+
+@pca_fit.register_fake
+def _(count, total, scatter, shift, k):
+    d = scatter.shape[0]
+    return (scatter.new_empty(d), scatter.new_empty((k, d)), scatter.new_empty(k + 1))
+
+
+@torch.library.custom_op("irp_b200::pca_transform", mutates_args=())
+def pca_transform(x: torch.Tensor, mean: torch.Tensor, components: torch.Tensor) -> torch.Tensor:
+    """(x - mean) @ components^T with fp64 accumulation -> fp32 [n,k]."""
+    lib = _lib_for(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n, d = x.shape
+    k = components.shape[0]
+    z = torch.empty((n, k), dtype=torch.float32, device=x.device)
+    _lib.check(lib.irp_pca_transform(_ptr(x), n, d, _ptr(mean), _ptr(components), k, _ptr(z), _stream()),
+               "irp_pca_transform")
+    return z
+
+
+@pca_transform.register_fake
+def _(x, mean, components):
+    return x.new_empty((x.shape[0], components.shape[0]), dtype=torch.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# A4 scoring
+# ---------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("irp_b200::lof", mutates_args=())
+def lof(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: int, n_neighbors: int,
+        contamination: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (negative_outlier_factor fp64[n], offset fp64[n_groups], flags uint8[n])."""
+    lib = _lib_for(z)
+    assert z.dtype == torch.float32 and z.is_contiguous()
+    n, d = z.shape
+    scores = torch.empty(n, dtype=torch.float64, device=z.device)
+    offsets = torch.empty(n_groups, dtype=torch.float64, device=z.device)
+    flags = torch.empty(n, dtype=torch.uint8, device=z.device)
+    ws_bytes = lib.irp_lof_workspace_bytes(n, d, n_neighbors)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    _lib.check(lib.irp_lof(_ptr(z), n, d, _ptr(group), n_groups, n_neighbors, C.c_double(contamination), _ptr(scores),
+                           _ptr(offsets), _ptr(flags), _ptr(ws), ws_bytes, _stream()), "irp_lof")
+    return scores, offsets, flags
+
+
+@lof.register_fake
+def _(z, group, n_groups, n_neighbors, contamination):
+    n = z.shape[0]
+    return (z.new_empty(n, dtype=torch.float64), z.new_empty(n_groups, dtype=torch.float64),
+            z.new_empty(n, dtype=torch.uint8))
+
+
+@torch.library.custom_op("irp_b200::centroid_zscore", mutates_args=())
+def centroid_zscore(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: int,
+                    contamination: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (distance fp64[n], zscore fp64[n], threshold fp64[n_groups], flags uint8[n])."""
+    lib = _lib_for(z)
+    assert z.dtype == torch.float32 and z.is_contiguous()
+    n, d = z.shape
+    dist = torch.empty(n, dtype=torch.float64, device=z.device)
+    zs = torch.empty(n, dtype=torch.float64, device=z.device)
+    thr = torch.empty(n_groups, dtype=torch.float64, device=z.device)
+    flags = torch.empty(n, dtype=torch.uint8, device=z.device)
+    ws_bytes = lib.irp_centroid_workspace_bytes(n, d, n_groups)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    _lib.check(lib.irp_centroid_zscore(_ptr(z), n, d, _ptr(group), n_groups, C.c_double(contamination), _ptr(dist),
+                                       _ptr(zs), _ptr(thr), _ptr(flags), _ptr(ws), ws_bytes, _stream()),
+               "irp_centroid_zscore")
+    return dist, zs, thr, flags
+
+
+@centroid_zscore.register_fake
+def _(z, group, n_groups, contamination):
+    n = z.shape[0]
+    return (z.new_empty(n, dtype=torch.float64), z.new_empty(n, dtype=torch.float64),
+            z.new_empty(n_groups, dtype=torch.float64), z.new_empty(n, dtype=torch.uint8))

@@ -1,0 +1,352 @@
+"""Host-side engine of the B200 outlier-detection stage.
+
+``ResNet50Trunk``   owns an ``irp_resnet50`` handle: loads a torchvision ResNet-50 state (BN folded on the device)
+                    and embeds padded NHWC4 bf16 batches.
+``OutlierStage``    runs the whole hot path on one rank's shard of a packed uint8 image batch:
+                    preprocess -> embed -> (all-reduce of the PCA partial sums) -> PCA fit -> project ->
+                    LOF per class + global, mirroring functions/data_curation.py:661-728 of the reference.
+
+Multi-GPU (one process per GPU, torch.distributed/NCCL): images shard across ranks with no data-path collective;
+the PCA needs ONE all-reduce of [count, sum, scatter] (plus an 8 KB broadcast of the shift vector so every rank
+accumulates about the same origin); scoring needs the projected rows of all ranks (one all-gather of N x k
+floats).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+
+def conv_bn_pairs(model: torch.nn.Module):
+    """(conv, bn) pairs of a torchvision ResNet-50 in the library's index order:
+    conv1, then per bottleneck conv1, conv2, conv3[, downsample] (irp_resnet50_conv_shape)."""
+    pairs = [(model.conv1, model.bn1)]
+    for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
+        for blk in layer:
+            pairs += [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2), (blk.conv3, blk.bn3)]
+            if blk.downsample is not None:
+                pairs.append((blk.downsample[0], blk.downsample[1]))
+    if len(pairs) != _lib.NUM_CONVS:
+        raise ValueError(f"expected a ResNet-50 ({_lib.NUM_CONVS} convolutions), found {len(pairs)}")
+    return pairs
+
+
+class ResNet50Trunk:
+    """ResNet-50 minus fc on the library's tcgen05 kernels (functions/data_curation.py:654-659, :677)."""
+
+    def __init__(self, torch_model: torch.nn.Module, device: torch.device, max_batch: int = 256):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ResNet50Trunk needs a CUDA (sm_100) device; there is no CPU path")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.lib = _lib.init(idx)
+        self.max_batch = int(max_batch)
+        self._handle = C.c_void_p()
+        with torch.cuda.device(idx):
+            _lib.check(self.lib.irp_resnet50_create(C.byref(self._handle), self.max_batch), "irp_resnet50_create")
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            for i, (conv, bn) in enumerate(conv_bn_pairs(torch_model)):
+                shape = [C.c_int() for _ in range(5)]
+                _lib.check(self.lib.irp_resnet50_conv_shape(i, *[C.byref(s) for s in shape]), "conv_shape")
+                cout, cin, kh, kw, _ = (s.value for s in shape)
+                w = conv.weight.detach().to(self.device, torch.float32).contiguous()
+                if tuple(w.shape) != (cout, cin, kh, kw):
+                    raise ValueError(f"conv {i}: weight shape {tuple(w.shape)} != {(cout, cin, kh, kw)}")
+                if conv.bias is not None:
+                    raise ValueError("ResNet-50 convolutions are bias-free (torchvision/models/resnet.py)")
+                t = [p.detach().to(self.device, torch.float32).contiguous()
+                     for p in (bn.weight, bn.bias, bn.running_mean, bn.running_var)]
+                _lib.check(self.lib.irp_resnet50_load_conv(self._handle, i, C.c_void_p(w.data_ptr()),
+                                                           *[C.c_void_p(p.data_ptr()) for p in t],
+                                                           C.c_float(bn.eps), stream), f"load_conv[{i}]")
+            torch.cuda.synchronize(idx)
+
+    @property
+    def handle(self) -> int:
+        return int(self._handle.value)
+
+    def embed(self, x_nhwc4p: torch.Tensor) -> torch.Tensor:
+        """bf16 [B,230,230,4] -> fp32 [B,2048]; B <= max_batch."""
+        if x_nhwc4p.shape[0] > self.max_batch:
+            raise ValueError(f"batch {x_nhwc4p.shape[0]} > max_batch {self.max_batch}")
+        return ops.resnet50_embed(self.handle, x_nhwc4p)
+
+    def embed_nchw(self, x: torch.Tensor) -> torch.Tensor:
+        """Normalised [B,3,224,224] tensor (what the reference feeds `model`) -> fp32 [B,2048]."""
+        b = x.shape[0]
+        xp = torch.zeros((b, _lib.PAD_HW, _lib.PAD_HW, 4), dtype=torch.bfloat16, device=self.device)
+        xp[:, 3:3 + _lib.CROP, 3:3 + _lib.CROP, :3] = x.to(self.device).permute(0, 2, 3, 1).to(torch.bfloat16)
+        out = []
+        for s in range(0, b, self.max_batch):
+            out.append(self.embed(xp[s:s + self.max_batch].contiguous()))
+        return torch.cat(out, 0)
+
+    def close(self):
+        if self._handle:
+            self.lib.irp_resnet50_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# packing a ragged batch of decoded images
+# -----------------------------------------------------------------------------------------------------------------
+ALIGN = 128  # every image starts on a 128-byte boundary of the packed buffer
+
+
+@dataclass
+class PackedImages:
+    """A ragged uint8 HWC batch packed back to back.  `pixels/offsets/hw` are torch tensors (host or device);
+    `offsets_np/hw_np` are always-host copies used for slicing without a device round trip."""
+    pixels: torch.Tensor   # uint8 [total_bytes]
+    offsets: torch.Tensor  # int64 [n]
+    hw: torch.Tensor       # int32 [n,2]
+    max_taps: int
+    offsets_np: np.ndarray = None
+    hw_np: np.ndarray = None
+
+    def __post_init__(self):
+        if self.offsets_np is None:
+            self.offsets_np = self.offsets.cpu().numpy()
+        if self.hw_np is None:
+            self.hw_np = self.hw.cpu().numpy()
+
+    def __len__(self):
+        return int(self.hw_np.shape[0])
+
+    def to(self, device, non_blocking=True):
+        return PackedImages(self.pixels.to(device, non_blocking=non_blocking),
+                            self.offsets.to(device, non_blocking=non_blocking),
+                            self.hw.to(device, non_blocking=non_blocking), self.max_taps, self.offsets_np, self.hw_np)
+
+    def slice(self, lo: int, hi: int) -> "PackedImages":
+        """Images [lo, hi) as a view (offsets rebased)."""
+        start = int(self.offsets_np[lo])
+        h, w = int(self.hw_np[hi - 1, 0]), int(self.hw_np[hi - 1, 1])
+        end = int(self.offsets_np[hi - 1]) + h * w * 3
+        return PackedImages(self.pixels[start:end], self.offsets[lo:hi] - start, self.hw[lo:hi], self.max_taps,
+                            self.offsets_np[lo:hi] - start, self.hw_np[lo:hi])
+
+    def nbytes(self) -> int:
+        return int((self.hw_np[:, 0].astype(np.int64) * self.hw_np[:, 1] * 3).sum())
+
+
+def taps_for(h: int, w: int) -> int:
+    """2*ceil(max(scale,1))+1 for the resize-232 transform of an h x w image (matches irp_preprocess_geometry)."""
+    if w <= h:
+        out_w, out_h = 232, int(232 * h / w)
+    else:
+        out_h, out_w = 232, int(232 * w / h)
+    s = max(h / out_h, w / out_w, 1.0)
+    return 2 * int(math.ceil(s)) + 1
+
+
+def pack_images(images: Sequence[np.ndarray], pin: bool = True) -> PackedImages:
+    """Pack HWC uint8 RGB arrays into one (pinned) host buffer."""
+    sizes = np.array([[im.shape[0], im.shape[1]] for im in images], np.int32).reshape(-1, 2)
+    nbytes = sizes[:, 0].astype(np.int64) * sizes[:, 1] * 3
+    padded = (nbytes + ALIGN - 1) // ALIGN * ALIGN
+    offsets = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
+    total = int(padded.sum())
+    buf = torch.empty(max(total, ALIGN), dtype=torch.uint8, pin_memory=pin and torch.cuda.is_available())
+    view = buf.numpy()
+    for im, o, nb in zip(images, offsets, nbytes):
+        if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+            raise ValueError(f"expected HWC uint8 RGB, got {im.dtype} {im.shape}")
+        view[o:o + nb] = np.ascontiguousarray(im).reshape(-1)
+    taps = max((taps_for(int(h), int(w)) for h, w in sizes), default=3)
+    return PackedImages(buf[:max(total, 1)], torch.from_numpy(offsets), torch.from_numpy(sizes), taps, offsets, sizes)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# the stage
+# -----------------------------------------------------------------------------------------------------------------
+@dataclass
+class PCAState:
+    mean: torch.Tensor         # fp64 [d]
+    components: torch.Tensor   # fp64 [k,d]
+    explained_variance: torch.Tensor  # fp64 [k]
+    total_variance: float
+    n_samples: int
+
+
+@dataclass
+class StageResult:
+    features: torch.Tensor      # fp32 [n_local, 2048]
+    z: torch.Tensor             # fp32 [n_total, k] (all ranks' rows, rank order)
+    pca: PCAState
+    class_outliers: torch.Tensor   # bool [n_total]
+    global_outliers: torch.Tensor  # bool [n_total]
+    class_scores: torch.Tensor     # fp64 [n_total]
+    global_scores: torch.Tensor    # fp64 [n_total]
+
+
+class CudaBackend:
+    """The product backend: every step is a libirp_b200 kernel (through the irp_b200 custom ops)."""
+
+    def __init__(self, trunk: ResNet50Trunk):
+        self.trunk = trunk
+        self.device = trunk.device
+
+    def embed(self, part: PackedImages, max_taps: int) -> torch.Tensor:
+        x = ops.preprocess(part.pixels, part.offsets, part.hw, max_taps, _lib.LAYOUT_NHWC4P)
+        return self.trunk.embed(x)
+
+    cov_accumulate = staticmethod(ops.cov_accumulate)
+    pca_fit = staticmethod(ops.pca_fit)
+    pca_transform = staticmethod(ops.pca_transform)
+    lof = staticmethod(ops.lof)
+
+
+class OutlierStage:
+    """embed + PCA + outlier scoring for one rank's shard (see module docstring).
+
+    `backend` supplies the compute steps (CudaBackend in the product; the CPU test-suite injects an oracle-backed
+    one to exercise the sharding / all-reduce / gather logic under gloo)."""
+
+    def __init__(self, backend, batch_size: int = 256, pca_components: int = 50, class_n_neighbors: int = 30,
+                 class_contamination: float = 0.05, global_n_neighbors: int = 75,
+                 global_contamination: float = 0.03, process_group=None, embed_dim: int = _lib.EMBED_DIM):
+        if isinstance(backend, ResNet50Trunk):
+            backend = CudaBackend(backend)
+        self.backend = backend
+        self.device = torch.device(backend.device)
+        self.batch_size = int(batch_size)
+        if hasattr(backend, "trunk"):
+            self.batch_size = min(self.batch_size, backend.trunk.max_batch)
+        self.k = int(pca_components)
+        self.embed_dim = int(embed_dim)
+        self.class_nn, self.class_cont = int(class_n_neighbors), float(class_contamination)
+        self.global_nn, self.global_cont = int(global_n_neighbors), float(global_contamination)
+        self.pg = process_group
+        self.copy_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+
+    # ---- distributed helpers ----
+    def _dist(self):
+        import torch.distributed as dist
+        return dist if (dist.is_available() and dist.is_initialized()) else None
+
+    @property
+    def world_size(self) -> int:
+        d = self._dist()
+        return d.get_world_size(self.pg) if d else 1
+
+    # ---- embed ----
+    def embed_packed(self, packed: PackedImages, from_host: bool = False) -> torch.Tensor:
+        """Preprocess + embed every image of `packed`; fp32 [n,2048] on the device.
+
+        With from_host=True the packed tensors live in (pinned) host memory and every batch's bytes are copied
+        on a side stream while the previous batch computes."""
+        n = len(packed)
+        feats = torch.empty((n, self.embed_dim), dtype=torch.float32, device=self.device)
+        if n == 0:
+            return feats
+        bs = self.batch_size
+        overlap = from_host and self.copy_stream is not None
+        cur = torch.cuda.current_stream(self.device) if overlap else None
+
+        def stage(lo):
+            part = packed.slice(lo, min(n, lo + bs))
+            if not from_host:
+                return part, None
+            if not overlap:
+                return part.to(self.device, non_blocking=False), None
+            with torch.cuda.stream(self.copy_stream):
+                dev = part.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            return dev, ev
+
+        nxt = stage(0)
+        for lo in range(0, n, bs):
+            part, ev = nxt
+            if lo + bs < n:
+                nxt = stage(lo + bs)
+            if ev is not None:
+                cur.wait_event(ev)
+                for t in (part.pixels, part.offsets, part.hw):
+                    t.record_stream(cur)
+            feats[lo:lo + len(part)] = self.backend.embed(part, packed.max_taps)
+        return feats
+
+    # ---- PCA ----
+    def fit_pca(self, feats: torch.Tensor) -> PCAState:
+        d = feats.shape[1]
+        dist = self._dist()
+        multi = dist is not None and self.world_size > 1
+        # common origin for every rank: the mean of rank 0's first rows
+        shift = feats[: min(256, feats.shape[0])].mean(0).contiguous() if feats.shape[0] > 0 else \
+            torch.zeros(d, dtype=torch.float32, device=self.device)
+        if multi:
+            src = dist.get_global_rank(self.pg, 0) if self.pg is not None else 0
+            dist.broadcast(shift, src=src, group=self.pg)
+        # one flat fp64 buffer [count | sum | scatter] so the reduction is a single all-reduce
+        acc = torch.zeros(1 + d + d * d, dtype=torch.float64, device=self.device)
+        count, total, scatter = acc[:1], acc[1:1 + d], acc[1 + d:].view(d, d)
+        if feats.shape[0] > 0:
+            self.backend.cov_accumulate(feats, shift, count, total, scatter)
+        if multi:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.pg)
+        mean, comps, evals = self.backend.pca_fit(count, total, scatter, shift, self.k)
+        n_total = int(round(float(count.item())))
+        return PCAState(mean, comps, evals[: self.k].clone(), float(evals[self.k].item()), n_total)
+
+    def transform(self, feats: torch.Tensor, pca: PCAState) -> torch.Tensor:
+        if feats.shape[0] == 0:
+            return torch.empty((0, self.k), dtype=torch.float32, device=self.device)
+        return self.backend.pca_transform(feats, pca.mean, pca.components)
+
+    # ---- scoring ----
+    def gather_rows(self, local: torch.Tensor) -> torch.Tensor:
+        """All ranks' rows concatenated in rank order (identity on one rank)."""
+        dist = self._dist()
+        if not dist or self.world_size == 1:
+            return local
+        ws = self.world_size
+        n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros_like(n_local) for _ in range(ws)]
+        dist.all_gather(sizes, n_local, group=self.pg)
+        sizes = [int(s.item()) for s in sizes]
+        mx = max(sizes)
+        pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=self.device)
+        pad[: local.shape[0]] = local
+        outs = [torch.empty_like(pad) for _ in range(ws)]
+        dist.all_gather(outs, pad, group=self.pg)
+        return torch.cat([o[:s] for o, s in zip(outs, sizes)], 0)
+
+    def detect(self, z_all: torch.Tensor, class_ids_all: torch.Tensor, n_classes: int):
+        cs, _, cf = self.backend.lof(z_all, class_ids_all, n_classes, self.class_nn, self.class_cont)
+        gs, _, gf = self.backend.lof(z_all, None, 1, self.global_nn, self.global_cont)
+        return cf.bool(), gf.bool(), cs, gs
+
+    # ---- whole stage ----
+    def run(self, packed: PackedImages, class_ids: torch.Tensor, n_classes: int,
+            from_host: bool = False) -> StageResult:
+        """`packed` / `class_ids` are THIS rank's shard; returned flags cover all ranks' rows in rank order."""
+        feats = self.embed_packed(packed, from_host=from_host)
+        pca = self.fit_pca(feats)
+        z_local = self.transform(feats, pca)
+        ids_local = class_ids.to(self.device, non_blocking=True).to(torch.int32)
+        z_all = self.gather_rows(z_local)
+        ids_all = self.gather_rows(ids_local)
+        cf, gf, cs, gs = self.detect(z_all.contiguous(), ids_all.contiguous(), n_classes)
+        return StageResult(feats, z_all, pca, cf, gf, cs, gs)
+
+
+def shard_range(n: int, rank: int, world_size: int):
+    """Contiguous [lo, hi) image range of `rank` (contiguous N/G shards)."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

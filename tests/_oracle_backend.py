@@ -1,0 +1,70 @@
+"""Test-only backend for OutlierStage: every compute step is the numpy oracle, on CPU tensors.
+
+Lets the CPU suite exercise the host-side logic of the stage (batching, sharding, the single all-reduce of the
+PCA partial sums, the gather of projected rows) under gloo without a GPU.  Never imported by the product."""
+import numpy as np
+import torch
+
+from oracle import lof_ref, pil_resample
+
+
+class OracleBackend:
+    device = torch.device("cpu")
+
+    def __init__(self, embed_dim=64, seed=0):
+        rng = np.random.default_rng(seed)
+        # stand-in for the trunk: fixed random projection of a 16x16 average-pooled preprocessed image
+        self.proj = rng.standard_normal((3 * 16 * 16, embed_dim)).astype(np.float32) / 10.0
+        self.embed_calls = 0
+
+    def embed(self, part, max_taps):
+        self.embed_calls += 1
+        feats = []
+        pix = part.pixels.numpy()
+        for (h, w), off in zip(part.hw_np, part.offsets_np):
+            img = pix[off:off + h * w * 3].reshape(h, w, 3)
+            x = pil_resample.transform(img)  # [3,224,224]
+            pooled = x.reshape(3, 16, 14, 16, 14).mean(axis=(2, 4)).reshape(-1)
+            feats.append(np.maximum(pooled @ self.proj + 1.0, 0))
+        return torch.from_numpy(np.stack(feats).astype(np.float32))
+
+    @staticmethod
+    def cov_accumulate(x, shift, count, total, scatter):
+        y = x.numpy().astype(np.float64) - shift.numpy().astype(np.float64)
+        count += y.shape[0]
+        total += torch.from_numpy(y.sum(0))
+        scatter += torch.from_numpy(y.T @ y)
+
+    @staticmethod
+    def pca_fit(count, total, scatter, shift, k):
+        n = float(count.item())
+        delta = total.numpy() / n
+        cov = (scatter.numpy() - n * np.outer(delta, delta)) / (n - 1)
+        evals, evecs = np.linalg.eigh(cov)
+        evals, evecs = evals[::-1], evecs[:, ::-1]
+        comps = evecs[:, :k].T.copy()
+        idx = np.argmax(np.abs(comps), axis=1)
+        comps *= np.sign(comps[np.arange(k), idx])[:, None]
+        out = np.concatenate([np.maximum(evals[:k], 0), [np.trace(cov)]])
+        return (torch.from_numpy(shift.numpy().astype(np.float64) + delta), torch.from_numpy(comps),
+                torch.from_numpy(out))
+
+    @staticmethod
+    def pca_transform(x, mean, comps):
+        z = (x.numpy().astype(np.float64) - mean.numpy()) @ comps.numpy().T
+        return torch.from_numpy(z.astype(np.float32))
+
+    @staticmethod
+    def lof(z, group, n_groups, k, contamination):
+        zn = z.numpy()
+        g = np.zeros(len(zn), np.int64) if group is None else group.numpy().astype(np.int64)
+        scores = np.zeros(len(zn))
+        offsets = np.zeros(n_groups)
+        flags = np.zeros(len(zn), np.uint8)
+        for c in range(n_groups):
+            m = g == c
+            if m.sum() < 2:
+                continue
+            f, s, o = lof_ref.lof_fit_predict(zn[m], k, contamination)
+            scores[m], offsets[c], flags[m] = s, o, f
+        return torch.from_numpy(scores), torch.from_numpy(offsets), torch.from_numpy(flags)

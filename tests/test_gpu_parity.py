@@ -1,0 +1,544 @@
+"""GPU parity: the CUDA path (through the C ABI / irp_b200 custom ops / drop-in functions) against the oracle,
+the committed golden fixtures, and size-independent properties at the BASELINE sizes.
+
+Tolerances (BASELINE.json north_star):
+  preprocess   bit-exact with the reference transform after its float32 result is rounded to bf16
+  embeddings   cosine >= 0.999 per image and max|a-b|/max|b| <= 2e-2 (bf16 operands, fp32 accumulate)
+  PCA          top-k subspace angle <= 1e-3 rad vs the exact fp64 solver, same component signs
+  LOF flags    identical except rows whose score is within 1e-3 (relative) of the threshold
+"""
+import ctypes as C
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+from oracle import lof_ref, pca_ref, pil_resample, stage_ref, synth
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+COS_MIN = 0.999
+LINF_REL_MAX = 2e-2
+ANGLE_MAX = 1e-3
+BAND = 1e-3
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.fixture(scope="module")
+def ops_mod(lib):
+    from irp_b200 import ops
+    return ops
+
+
+@pytest.fixture(scope="module")
+def trunk(lib):
+    from irp_b200.stage import ResNet50Trunk
+    return ResNet50Trunk(stage_ref.full_resnet50(seed=1234), torch.device("cuda:0"), max_batch=64)
+
+
+# =============================================================================================== A1 preprocess
+def _preprocess(ops_mod, images, layout):
+    from irp_b200.stage import pack_images
+    p = pack_images(images).to("cuda:0")
+    return ops_mod.preprocess(p.pixels, p.offsets, p.hw, p.max_taps, layout)
+
+
+def _expected_bf16(images):
+    return torch.from_numpy(np.stack([pil_resample.transform(im) for im in images])).bfloat16()
+
+
+def test_preprocess_golden_bit_exact(ops_mod):
+    g = load_golden("preprocess.npz")
+    images = [np.random.default_rng(int(s)).integers(0, 256, (int(h), int(w), 3), dtype=np.uint8)
+              for (h, w), s in zip(g["sizes"], g["seeds"])]
+    out = _preprocess(ops_mod, images, 0).cpu()
+    exp = torch.from_numpy(np.stack([pil_resample.normalize(c) for c in g["crops"]])).bfloat16()
+    assert torch.equal(out.view(torch.int16), exp.view(torch.int16))
+
+
+@pytest.mark.parametrize("sizes", [
+    [(224, 224), (232, 232), (233, 232), (232, 640)],          # no resize / pure crop / one-axis resize
+    [(57, 60), (120, 500), (500, 120), (150, 200)],             # upscales, extreme aspect ratios
+    [(1000, 700), (2400, 1800), (231, 500), (3000, 2900)],      # many-tap downscales
+])
+def test_preprocess_matches_oracle_ragged_batches(ops_mod, sizes):
+    rng = np.random.default_rng(len(sizes) + sizes[0][0])
+    images = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    exp = _expected_bf16(images)
+    out = _preprocess(ops_mod, images, 0).cpu()
+    assert torch.equal(out.view(torch.int16), exp.view(torch.int16))
+    padded = _preprocess(ops_mod, images, 1).cpu()
+    want = torch.zeros(len(images), 230, 230, 4, dtype=torch.bfloat16)
+    want[:, 3:227, 3:227, :3] = exp.permute(0, 2, 3, 1)
+    assert torch.equal(padded.view(torch.int16), want.view(torch.int16))
+
+
+def test_preprocess_single_image_and_transform_callable(lib):
+    from PIL import Image
+    from functions import data_curation as dc
+    img = np.random.default_rng(5).integers(0, 256, (310, 415, 3), dtype=np.uint8)
+    t = dc.B200Transform("cuda:0")(Image.fromarray(img))
+    assert t.shape == (3, 224, 224) and t.dtype == torch.float32
+    exp = torch.from_numpy(pil_resample.transform(img)).bfloat16().float()
+    assert torch.equal(t.cpu(), exp)
+
+
+def test_preprocess_full_size_properties(ops_mod):
+    """Config-2-shaped batch (256 mixed-resolution images): constant images stay constant (weights sum to one),
+    borders/pad channel are exactly zero, and the result does not depend on the batch an image travels in."""
+    hw = synth.mixed_resolution_sizes(256, seed=0)
+    rng = np.random.default_rng(0)
+    images = []
+    for i, (h, w) in enumerate(hw):
+        if i % 2 == 0:
+            images.append(np.full((h, w, 3), rng.integers(0, 256, 3, dtype=np.uint8), dtype=np.uint8))
+        else:
+            images.append(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+    out = _preprocess(ops_mod, images, 1)
+    assert (out[:, :3].float().abs().sum() + out[:, 227:].float().abs().sum() + out[:, :, :3].float().abs().sum()
+            + out[:, :, 227:].float().abs().sum() + out[..., 3].float().abs().sum()).item() == 0.0
+    for i in range(0, 256, 2):
+        inner = out[i, 3:227, 3:227, :3].float().cpu()
+        colour = pil_resample.normalize(images[i][:1, :1])[:, 0, 0]  # float32 [3]
+        want = torch.from_numpy(colour).bfloat16().float()
+        assert torch.equal(inner, want.expand(224, 224, 3)), f"constant image {i} {hw[i]}"
+    solo = _preprocess(ops_mod, [images[37]], 1)
+    assert torch.equal(solo[0].view(torch.int16), out[37].view(torch.int16))
+
+
+# =============================================================================================== A2 convolutions
+def _conv_ref(x, w, bias, res, stride, relu):
+    k = w.shape[1]
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=k // 2)
+    y = y.permute(0, 2, 3, 1)
+    if res is not None:
+        y = y + res.float()
+    return y.relu() if relu else y
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,k,stride,relu,residual", [
+    (1, 16, 64, 64, 1, 1, False, False),      # smallest flat GEMM
+    (3, 7, 128, 256, 1, 1, True, False),      # M = 147: ragged last tile
+    (8, 56, 64, 256, 1, 1, True, True),       # layer1 conv3 + residual
+    (4, 14, 1024, 256, 1, 1, True, False),    # long K
+    (2, 56, 64, 64, 3, 1, True, False),       # layer1 3x3
+    (8, 28, 128, 128, 3, 1, True, False),
+    (32, 14, 256, 256, 3, 1, True, False),
+    (128, 7, 512, 512, 3, 1, True, False),    # (1,1,128) boxes
+    (6, 7, 512, 512, 3, 1, True, False),      # (7,7,2) boxes, 98 of 128 rows
+    (3, 14, 256, 256, 3, 1, True, False),     # batch not a multiple of the box
+    (2, 56, 128, 128, 3, 2, True, False),     # stride-2 3x3 through the parity views
+    (8, 28, 256, 256, 3, 2, True, False),
+    (2, 56, 256, 512, 1, 2, False, False),    # stride-2 downsample
+    (8, 14, 1024, 2048, 1, 2, False, False),
+])
+def test_conv2d_matches_torch(lib, B, H, Cin, Cout, k, stride, relu, residual):
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Cin + k)
+    x = torch.randn(B, H, H, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, k, k, Cin, device="cuda", generator=g) / (k * k * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    Ho = (H + 2 * (k // 2) - k) // stride + 1
+    res = torch.randn(B, Ho, Ho, Cout, device="cuda", generator=g).bfloat16() if residual else None
+    out = torch.full((B, Ho, Ho, Cout), float("nan"), device="cuda").bfloat16()
+    from irp_b200 import _lib
+    _lib.check(lib.irp_conv2d_nhwc(_ptr(x), _ptr(w), _ptr(bias), _ptr(res), _ptr(out), B, H, H, Cin, Cout, k, stride,
+                                   int(relu), _stream()), "irp_conv2d_nhwc")
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, w, bias, res, stride, relu)
+    assert not torch.isnan(out.float()).any()
+    # bf16 output rounding (2^-9) + fp32 accumulation order
+    assert ((out.float() - ref).abs().max() / ref.abs().max()).item() < 6e-3
+
+
+def test_conv2d_rejects_unsupported_shapes(lib):
+    x = torch.zeros(1, 8, 8, 48, device="cuda", dtype=torch.bfloat16)
+    st = lib.irp_conv2d_nhwc(_ptr(x), _ptr(x), _ptr(x), None, _ptr(x), 1, 8, 8, 48, 64, 1, 1, 0, _stream())
+    assert st == 1 and b"multiples of 64" in lib.irp_last_error()
+    st = lib.irp_conv2d_nhwc(_ptr(x), _ptr(x), _ptr(x), None, _ptr(x), 1, 8, 8, 64, 64, 5, 1, 0, _stream())
+    assert st == 1
+
+
+# =============================================================================================== A2 trunk
+def _golden_images():
+    g = load_golden("embeddings.npz")
+    hw = g["hw"]
+    sizes = hw[:, 0].astype(np.int64) * hw[:, 1] * 3
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    return g, [g["pixels"][offs[i]:offs[i + 1]].reshape(hw[i, 0], hw[i, 1], 3) for i in range(len(hw))]
+
+
+def _embedding_metrics(a, b):
+    cos = (a * b).sum(1) / np.linalg.norm(a, axis=1) / np.linalg.norm(b, axis=1)
+    linf = np.abs(a - b).max(1) / np.abs(b).max(1)
+    return cos.min(), linf.max()
+
+
+def test_embeddings_match_reference_golden(trunk):
+    from irp_b200.stage import OutlierStage, pack_images
+    g, images = _golden_images()
+    stage = OutlierStage(trunk, batch_size=5)
+    feats = stage.embed_packed(pack_images(images), from_host=True).cpu().numpy()
+    cos, linf = _embedding_metrics(feats, g["features"])
+    assert cos >= COS_MIN and linf <= LINF_REL_MAX, (cos, linf)
+
+
+def test_trunk_matches_torchvision_per_layer(lib, trunk):
+    """Every conv's fused output (bias/ReLU/residual epilogue) against torchvision evaluated in fp32 on the GPU."""
+    from irp_b200 import _lib
+    from irp_b200.stage import conv_bn_pairs
+    m = stage_ref.full_resnet50(seed=1234).cuda()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    B = 4
+    x = torch.randn(B, 3, 224, 224, device="cuda", generator=g).bfloat16()
+    xp = torch.zeros(B, 230, 230, 4, device="cuda", dtype=torch.bfloat16)
+    xp[:, 3:227, 3:227, :3] = x.permute(0, 2, 3, 1)
+    feats = {}
+    with torch.no_grad():
+        t = m.relu(m.bn1(m.conv1(x.float())))
+        feats[0] = t
+        t = m.maxpool(t)
+        idx = 1
+        for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
+            for blk in layer:
+                o1 = blk.relu(blk.bn1(blk.conv1(t)))
+                o2 = blk.relu(blk.bn2(blk.conv2(o1)))
+                idt, n = t, 3
+                if blk.downsample is not None:
+                    idt, n = blk.downsample(t), 4
+                    feats[idx + 3] = idt
+                t = blk.relu(blk.bn3(blk.conv3(o2)) + idt)
+                feats[idx], feats[idx + 1], feats[idx + 2] = o1, o2, t
+                idx += n
+        ref_embed = torch.flatten(m.avgpool(t), 1)
+    assert idx == 53 and len(conv_bn_pairs(m)) == 53
+    emb = torch.empty(B, 2048, device="cuda")
+    worst = 0.0
+    for ci in range(53):
+        r = feats[ci].permute(0, 2, 3, 1).contiguous()
+        cap = torch.full(r.shape, float("nan"), device="cuda").bfloat16()
+        _lib.check(lib.irp_resnet50_embed_capture(C.c_void_p(trunk.handle), _ptr(xp), B, _ptr(emb), ci, _ptr(cap),
+                                                  cap.numel(), _stream()), "embed_capture")
+        torch.cuda.synchronize()
+        rel = ((cap.float() - r).abs().max() / r.abs().max()).item()
+        worst = max(worst, rel)
+        assert rel < LINF_REL_MAX, f"conv {ci}: {rel}"
+    cos, linf = _embedding_metrics(emb.cpu().numpy(), ref_embed.cpu().numpy())
+    assert cos >= COS_MIN and linf <= LINF_REL_MAX
+
+
+def test_embedding_is_batch_invariant_at_full_batch(lib):
+    """Property at the BASELINE batch size (256): an image's embedding does not depend on its batch or slot."""
+    from irp_b200.stage import ResNet50Trunk
+    big = ResNet50Trunk(stage_ref.full_resnet50(seed=1234), torch.device("cuda:0"), max_batch=256)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xp = torch.zeros(256, 230, 230, 4, device="cuda", dtype=torch.bfloat16)
+    xp[:, 3:227, 3:227, :3] = torch.randn(256, 224, 224, 3, device="cuda", generator=g).bfloat16()
+    full = big.embed(xp)
+    perm = torch.randperm(256, device="cuda", generator=g)
+    shuffled = big.embed(xp[perm].contiguous())
+    assert torch.equal(shuffled, full[perm])
+    part = big.embed(xp[100:117].contiguous())
+    cos, linf = _embedding_metrics(part.cpu().numpy(), full[100:117].cpu().numpy())
+    assert cos > 0.99999 and linf < 1e-2  # a different tile shape only changes the fp32 summation order
+    assert torch.isfinite(full).all() and (full >= 0).all()
+    big.close()
+
+
+def test_model_callable_like_the_reference(lib):
+    from functions import data_curation as dc
+    model, transform = dc.initialize_model("cuda:0", weights=None, seed=1234, max_batch=8)
+    ref_model, _ = stage_ref.initialize_model("cuda:0", seed=1234)
+    x = torch.randn(3, 3, 224, 224, device="cuda")
+    with torch.no_grad():
+        out = model(x)
+        ref = ref_model(x.bfloat16().float())
+    assert out.shape == (3, 2048, 1, 1) and out.dtype == torch.float32
+    cos, linf = _embedding_metrics(out.flatten(1).cpu().numpy(), ref.flatten(1).cpu().numpy())
+    assert cos >= COS_MIN and linf <= LINF_REL_MAX
+    assert "B200Transform" in repr(transform)
+
+
+# =============================================================================================== A3 PCA
+def _gpu_pca(ops_mod, x, k):
+    xt = torch.from_numpy(x).cuda()
+    n, d = xt.shape
+    shift = xt[: min(256, n)].mean(0).contiguous()
+    acc = torch.zeros(1 + d + d * d, dtype=torch.float64, device="cuda")
+    count, total, scatter = acc[:1], acc[1:1 + d], acc[1 + d:].view(d, d)
+    ops_mod.cov_accumulate(xt, shift, count, total, scatter)
+    mean, comps, evals = ops_mod.pca_fit(count, total, scatter, shift, k)
+    z = ops_mod.pca_transform(xt, mean, comps)
+    return mean.cpu().numpy(), comps.cpu().numpy(), evals.cpu().numpy(), z.cpu().numpy()
+
+
+def test_pca_matches_golden(ops_mod):
+    g = load_golden("pca.npz")
+    x = synth.embedding_like(int(g["n"]), int(g["d"]), seed=int(g["seed"]))
+    k = int(g["k"])
+    mean, comps, evals, z = _gpu_pca(ops_mod, x, k)
+    assert pca_ref.subspace_angle(comps, g["components"]) <= ANGLE_MAX
+    assert ((comps * g["components"]).sum(1) > 0.999).all()  # sign convention + per-component match
+    np.testing.assert_allclose(evals[:k], g["explained_variance"], rtol=1e-4)
+    np.testing.assert_allclose(evals[:k] / evals[k], g["explained_variance_ratio"], rtol=1e-4)
+    np.testing.assert_allclose(mean, g["mean"], atol=1e-5)
+    np.testing.assert_allclose(z[:64], g["z_head"], atol=2e-3 * np.abs(g["z_head"]).max())
+
+
+@pytest.mark.parametrize("n,k", [(1500, 50), (300, 128), (64, 8), (2500, 1)])
+def test_pca_matches_exact_oracle(ops_mod, n, k):
+    x = synth.embedding_like(n, 2048, seed=n + k)
+    mean, comps, evals, z = _gpu_pca(ops_mod, x, k)
+    ref = pca_ref.pca_fit(x, k)
+    assert pca_ref.subspace_angle(comps, ref.components) <= ANGLE_MAX
+    assert np.abs(comps @ comps.T - np.eye(k)).max() < 1e-9
+    np.testing.assert_allclose(evals[:k], ref.explained_variance, rtol=2e-4, atol=1e-6 * ref.explained_variance[0])
+    np.testing.assert_allclose(evals[k], ref.eigenvalues.sum(), rtol=1e-5)
+    zref = pca_ref.pca_transform(x, ref.mean, ref.components)
+    if k > 1:
+        # compare inside the subspace: rotate our scores onto the oracle's basis
+        r = comps @ ref.components.T
+        np.testing.assert_allclose(z.astype(np.float64) @ r, zref, atol=2e-3 * np.abs(zref).max())
+
+
+def test_pca_partial_sums_combine_like_one_pass(ops_mod):
+    """Sharded accumulation (the multi-GPU path on one device): G partial accumulators summed == one pass."""
+    x = synth.embedding_like(2000, 2048, seed=9)
+    xt = torch.from_numpy(x).cuda()
+    d = 2048
+    shift = xt[:256].mean(0).contiguous()
+    one = torch.zeros(1 + d + d * d, dtype=torch.float64, device="cuda")
+    ops_mod.cov_accumulate(xt, shift, one[:1], one[1:1 + d], one[1 + d:].view(d, d))
+    total = torch.zeros_like(one)
+    for lo, hi in [(0, 700), (700, 701), (701, 2000)]:  # ragged shards, including a single-row one
+        part = torch.zeros_like(one)
+        ops_mod.cov_accumulate(xt[lo:hi].contiguous(), shift, part[:1], part[1:1 + d], part[1 + d:].view(d, d))
+        total += part
+    assert total[0].item() == 2000.0
+    np.testing.assert_allclose(total[1:1 + d].cpu().numpy(), one[1:1 + d].cpu().numpy(), rtol=1e-12, atol=1e-9)
+    a = torch.triu(total[1 + d:].view(d, d)).cpu().numpy()
+    b = torch.triu(one[1 + d:].view(d, d)).cpu().numpy()
+    assert np.abs(a - b).max() <= 2e-6 * np.abs(b).max()
+
+
+def test_pca_full_size_properties(ops_mod):
+    """BASELINE size (27 000 x 2048, k=50): orthonormal components, eigen-residual, variance bookkeeping."""
+    n, k = 27000, 50
+    base = torch.from_numpy(synth.embedding_like(3000, 2048, seed=1)).cuda()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xt = (base.repeat(9, 1) + 0.3 * torch.randn(n, 2048, device="cuda", generator=g)).contiguous()
+    d = 2048
+    shift = xt[:256].mean(0).contiguous()
+    acc = torch.zeros(1 + d + d * d, dtype=torch.float64, device="cuda")
+    ops_mod.cov_accumulate(xt, shift, acc[:1], acc[1:1 + d], acc[1 + d:].view(d, d))
+    mean, comps, evals = ops_mod.pca_fit(acc[:1], acc[1:1 + d], acc[1 + d:].view(d, d), shift, k)
+    x64 = xt.double()
+    mu = x64.mean(0)
+    cov = (x64 - mu).T @ (x64 - mu) / (n - 1)
+    assert torch.allclose(mean, mu, atol=1e-5)
+    eye = torch.eye(k, dtype=torch.float64, device="cuda")
+    assert (comps @ comps.T - eye).abs().max().item() < 1e-9
+    resid = (cov @ comps.T - comps.T * evals[:k]).norm(dim=0) / evals[0]
+    assert resid.max().item() < 1e-5
+    ev = evals[:k]
+    assert (ev[:-1] >= ev[1:]).all() and (ev >= 0).all()
+    assert abs(evals[k].item() - torch.trace(cov).item()) / torch.trace(cov).item() < 1e-5
+    z = ops_mod.pca_transform(xt, mean, comps)
+    zref = (x64 - mu) @ comps.T
+    assert (z.double() - zref).abs().max().item() < 1e-3 * zref.abs().max().item()
+    np.testing.assert_allclose(z.double().var(0, unbiased=True).cpu().numpy(), ev.cpu().numpy(), rtol=1e-3)
+
+
+# =============================================================================================== A4 scoring
+def _flags_equal_outside_band(flags, ref_flags, ref_scores, ref_offset):
+    near = np.abs(ref_scores - ref_offset) <= BAND * abs(ref_offset)
+    return int(((flags != ref_flags) & ~near).sum())
+
+
+def test_lof_matches_reference_golden(ops_mod):
+    g = load_golden("lof.npz")
+    z, y = synth.clustered_points(int(g["n"]), int(g["d"]), int(g["classes"]), seed=int(g["seed"]))
+    zt = torch.from_numpy(z).cuda()
+    scores, offs, flags = ops_mod.lof(zt, None, 1, 75, 0.03)
+    np.testing.assert_allclose(scores.cpu().numpy(), g["global_scores"], rtol=2e-6)
+    assert abs(offs[0].item() - float(g["global_offset"])) < 2e-6 * abs(float(g["global_offset"]))
+    assert _flags_equal_outside_band(flags.cpu().numpy().astype(bool), g["global_outliers"], g["global_scores"],
+                                     float(g["global_offset"])) == 0
+    # per class: sklearn label encoding = sorted class names = ids here
+    ids = torch.from_numpy(y.astype(np.int32)).cuda()
+    _, _, cflags = ops_mod.lof(zt, ids, int(g["classes"]), 30, 0.05)
+    bad = 0
+    for c in range(int(g["classes"])):
+        m = y == c
+        ref_flags, near = stage_ref.lof_band(z[m], 30, 0.05, BAND)
+        assert np.array_equal(ref_flags, g["class_outliers"][m])
+        bad += int(((cflags.cpu().numpy()[m].astype(bool) != ref_flags) & ~near).sum())
+    assert bad == 0
+
+
+def test_detect_outliers_drop_in_matches_reference_golden(lib):
+    from functions import data_curation as dc
+    g = load_golden("lof.npz")
+    z, y = synth.clustered_points(int(g["n"]), int(g["d"]), int(g["classes"]), seed=int(g["seed"]))
+    labels = np.array([f"cls{c:02d}" for c in y])
+    cls_out, glob_out = dc.detect_outliers(z, labels)
+    assert cls_out.dtype == bool and glob_out.dtype == bool and cls_out.shape == (len(z),)
+    # no score lies inside the band for this fixture, so the sets must be identical
+    assert np.array_equal(glob_out, g["global_outliers"])
+    assert np.array_equal(cls_out, g["class_outliers"])
+    # the reference's production input: 2-D points, classes smaller than n_neighbors (k clipped with a warning)
+    z2, y2 = synth.clustered_points(int(g["n2"]), int(g["d2"]), int(g["classes2"]), seed=int(g["seed2"]))
+    labels2 = np.array([f"c{c:02d}" for c in y2])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        cls2, glob2 = dc.detect_outliers(z2, labels2)
+    assert any("n_neighbors" in str(x.message) for x in w)
+    assert np.array_equal(glob2, g["global_outliers2"])
+    assert np.array_equal(cls2, g["class_outliers2"])
+
+
+def test_lof_duplicates_and_unsorted_groups(ops_mod):
+    z, y = synth.clustered_points(1200, 16, 5, seed=8)
+    z[:40] = z[100]          # 40 exact duplicates (> k): lrd hits the 1e-10 guard
+    y[:40] = y[100]
+    zt = torch.from_numpy(z).cuda()
+    ids = torch.from_numpy(y.astype(np.int32)).cuda()
+    scores, _, flags = ops_mod.lof(zt, ids, 5, 30, 0.05)
+    bad = 0
+    for c in range(5):
+        m = y == c
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref_flags, near = stage_ref.lof_band(z[m], 30, 0.05, BAND)
+        bad += int(((flags.cpu().numpy()[m].astype(bool) != ref_flags) & ~near).sum())
+    assert bad == 0
+    assert torch.isfinite(scores).all()
+
+
+def test_lof_full_size_properties(ops_mod):
+    """BASELINE size (27 000 x 50): flag counts follow the contamination, flags are permutation-equivariant, and
+    the per-class pass equals running each class alone."""
+    n, d, G = 27000, 50, 10
+    rng = np.random.default_rng(0)
+    y = synth.class_assignment(n, seed=0)
+    centers = rng.standard_normal((G, d)) * 4
+    z = (centers[y] + rng.standard_normal((n, d)) * rng.uniform(0.5, 2.0, (n, 1))).astype(np.float32)
+    zt, ids = torch.from_numpy(z).cuda(), torch.from_numpy(y).cuda()
+    gs, goff, gf = ops_mod.lof(zt, None, 1, 75, 0.03)
+    cs, coff, cf = ops_mod.lof(zt, ids, G, 30, 0.05)
+    assert abs(int(gf.sum()) - 0.03 * n) <= 2
+    for c in range(G):
+        m = ids == c
+        assert abs(int(cf[m].sum()) - 0.05 * int(m.sum())) <= 2
+        solo_s, solo_o, solo_f = ops_mod.lof(zt[m].contiguous(), None, 1, 30, 0.05)
+        assert torch.equal(solo_f, cf[m]) and torch.allclose(solo_s, cs[m], rtol=1e-12, atol=0)
+        assert abs(solo_o[0].item() - coff[c].item()) < 1e-12
+    perm = torch.randperm(n, device="cuda")
+    ps, _, pf = ops_mod.lof(zt[perm].contiguous(), None, 1, 75, 0.03)
+    assert torch.allclose(ps, gs[perm], rtol=1e-9, atol=0)
+    assert int((pf != gf[perm]).sum()) <= 1  # only a tie exactly at the threshold could flip
+    assert (gs <= 0).all() and gs.max().item() < -0.5
+
+
+def test_centroid_scorer_matches_its_oracle(ops_mod):
+    z, y = synth.clustered_points(5000, 50, 10, seed=4)
+    zt, ids = torch.from_numpy(z).cuda(), torch.from_numpy(y.astype(np.int32)).cuda()
+    dist, zs, thr, flags = ops_mod.centroid_zscore(zt, ids, 10, 0.05)
+    rd, rz, rt, rf = lof_ref.centroid_zscore(z, y, 10, 0.05)
+    np.testing.assert_allclose(dist.cpu().numpy(), rd, rtol=1e-12)
+    np.testing.assert_allclose(zs.cpu().numpy(), rz, atol=1e-10)
+    np.testing.assert_allclose(thr.cpu().numpy(), rt, rtol=1e-12)
+    assert np.array_equal(flags.cpu().numpy().astype(bool), rf)
+    dist1, _, thr1, flags1 = ops_mod.centroid_zscore(zt, None, 1, 0.03)
+    rd1, _, rt1, rf1 = lof_ref.centroid_zscore(z, None, 1, 0.03)
+    np.testing.assert_allclose(dist1.cpu().numpy(), rd1, rtol=1e-12)
+    assert np.array_equal(flags1.cpu().numpy().astype(bool), rf1)
+
+
+# =============================================================================================== drop-in stage
+def test_process_image_directory_drop_in(lib, tmp_path, capsys):
+    from PIL import Image
+    from functions import data_curation as dc
+    g, images = _golden_images()
+    for name, img in zip(g["names"], images):
+        p = tmp_path / str(name)
+        p.parent.mkdir(exist_ok=True)
+        Image.fromarray(img).save(p)
+    (tmp_path / "class0" / "broken.png").write_bytes(b"not an image")
+    (tmp_path / "README.txt").write_text("stray file")
+    model, transform = dc.initialize_model("cuda:0", weights=None, seed=int(g["seed"]), max_batch=8)
+    feats, labels, paths = dc.process_image_directory(str(tmp_path), "cuda:0", transform, batch_size=5, model=model)
+    assert "Skipped" in capsys.readouterr().out          # reference prints and continues (:681-682)
+    assert feats.shape == (12, 2048) and feats.dtype == np.float32
+    assert labels.shape == (12,) and paths.shape == (12,)
+    rel = [os.path.relpath(p, tmp_path) for p in paths]
+    order = [rel.index(str(n)) for n in g["names"]]
+    assert list(labels[order]) == list(g["labels"])
+    cos, linf = _embedding_metrics(feats[order], g["features"])
+    assert cos >= COS_MIN and linf <= LINF_REL_MAX
+    # a host-side transform (not the fused one) takes the per-image path and still matches
+    _, ref_tfm = stage_ref.initialize_model("cpu")
+    feats2, _, paths2 = dc.process_image_directory(str(tmp_path), "cuda:0", ref_tfm, batch_size=4, model=model)
+    rel2 = [os.path.relpath(p, tmp_path) for p in paths2]
+    cos, linf = _embedding_metrics(feats2[[rel2.index(str(n)) for n in g["names"]]], g["features"])
+    assert cos >= COS_MIN and linf <= LINF_REL_MAX
+
+
+def test_create_pca_embeddings_returns_a_working_sklearn_pca(lib):
+    from functions import data_curation as dc
+    x = synth.embedding_like(800, 2048, seed=21)
+    labels = np.array([f"c{i % 7}" for i in range(800)])
+    z, le, pca = dc.create_pca_embeddings(x, labels, pca_components=50)
+    zr, ref = stage_ref.pca_exact(x, 50)
+    assert z.shape == (800, 50) and z.dtype == np.float32 and list(le.classes_) == sorted(set(labels))
+    assert pca_ref.subspace_angle(pca.components_, ref.components_) <= ANGLE_MAX
+    np.testing.assert_allclose(pca.explained_variance_ratio_, ref.explained_variance_ratio_, rtol=1e-3)
+    np.testing.assert_allclose(pca.singular_values_, ref.singular_values_, rtol=1e-3)
+    np.testing.assert_allclose(pca.noise_variance_, ref.noise_variance_, rtol=1e-3)
+    np.testing.assert_allclose(pca.transform(x[:10]), z[:10], atol=1e-2)  # sklearn's own transform on our fit
+    with pytest.raises(ValueError):
+        dc.create_pca_embeddings(x[:20], labels[:20], pca_components=50)
+    with pytest.raises(ImportError):
+        dc.create_embeddings(x, labels)  # umap-learn is absent here; the reference fails at import time
+
+
+def test_whole_stage_against_reference_route(trunk):
+    """Config-1-shaped run (reduced to 160 images): every stage fed the oracle's previous-stage output."""
+    from irp_b200.stage import OutlierStage, pack_images
+    images, labels = synth.config1_images(160, 10, seed=0)
+    ids = np.array([int(l[5:]) for l in labels], np.int32)
+    stage = OutlierStage(trunk, batch_size=64, pca_components=20)
+    res = stage.run(pack_images(images), torch.from_numpy(ids), 10, from_host=True)
+    ref_feats = stage_ref.embed_arrays(images, batch_size=32, seed=1234)
+    cos, linf = _embedding_metrics(res.features.cpu().numpy(), ref_feats)
+    assert cos >= COS_MIN and linf <= LINF_REL_MAX
+    # PCA on the ORACLE features (stage-wise parity)
+    xt = torch.from_numpy(ref_feats).cuda()
+    pca = stage.fit_pca(xt)
+    zr, ref = stage_ref.pca_exact(ref_feats, 20)
+    assert pca_ref.subspace_angle(pca.components.cpu().numpy(), ref.components_) <= ANGLE_MAX
+    # scoring on the ORACLE projection
+    zt = torch.from_numpy(zr.astype(np.float32)).cuda()
+    cf, gf, cs, gs = stage.detect(zt, torch.from_numpy(ids).cuda(), 10)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gref, gnear = stage_ref.lof_band(zr.astype(np.float32), 75, 0.03, BAND)
+        assert int(((gf.cpu().numpy() != gref) & ~gnear).sum()) == 0
+        for c in range(10):
+            m = ids == c
+            cref, cnear = stage_ref.lof_band(zr.astype(np.float32)[m], 30, 0.05, BAND)
+            assert int(((cf.cpu().numpy()[m] != cref) & ~cnear).sum()) == 0
+    assert res.class_outliers.shape == (160,) and res.z.shape == (160, 20)

@@ -1,0 +1,138 @@
+"""CPU: the oracle restatements against the golden vectors produced by the unmodified reference
+(oracle/make_golden.py) and against the third-party libraries the reference calls, run in-process."""
+import hashlib
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import lof_ref, pca_ref, pil_resample, stage_ref, synth
+
+
+# ------------------------------------------------------------------ A1 preprocess
+def _golden_image(seed, h, w):
+    return np.random.default_rng(int(seed)).integers(0, 256, (int(h), int(w), 3), dtype=np.uint8)
+
+
+def test_resample_matches_reference_golden_bit_for_bit():
+    g = load_golden("preprocess.npz")
+    for (h, w), seed, crop, sha in zip(g["sizes"], g["seeds"], g["crops"], g["float32_sha256"]):
+        img = _golden_image(seed, h, w)
+        u8 = pil_resample.transform_u8(img)
+        assert np.array_equal(u8, crop), f"{h}x{w}: uint8 crop differs from the reference transform"
+        f32 = pil_resample.normalize(u8)
+        assert hashlib.sha256(f32.tobytes()).hexdigest() == str(sha), f"{h}x{w}: normalised float32 differs"
+
+
+@pytest.mark.parametrize("h,w", [(480, 640), (1000, 700), (232, 232), (640, 232), (60, 57), (225, 1200)])
+def test_resample_matches_pillow_and_torchvision_in_process(h, w):
+    from PIL import Image
+    from torchvision.models import ResNet50_Weights
+    img = np.random.default_rng(h * 10007 + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref = ResNet50_Weights.DEFAULT.transforms()(Image.fromarray(img)).numpy()
+    assert np.array_equal(pil_resample.transform(img), ref)
+
+
+def test_geometry_matches_c_abi_host_helper():
+    from irp_b200 import _lib
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        h, w = int(rng.integers(40, 3000)), int(rng.integers(40, 3000))
+        oh, ow = pil_resample.resized_size(h, w)
+        top, left = pil_resample.crop_offsets(oh, ow)
+        assert _lib.geometry(h, w) == (oh, ow, top, left, pil_resample.max_taps(h, w))
+
+
+def test_bf16_rounding_helper_matches_torch():
+    import torch
+    x = np.random.default_rng(1).standard_normal(10000).astype(np.float32) * 3
+    bits = pil_resample.to_bf16_bits(x)
+    ref = torch.from_numpy(x).bfloat16().view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(bits, ref)
+
+
+# ------------------------------------------------------------------ A2 embeddings
+def test_stage_ref_embeddings_match_reference_golden():
+    g = load_golden("embeddings.npz")
+    hw = g["hw"]
+    sizes = hw[:, 0].astype(np.int64) * hw[:, 1] * 3
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    images = [g["pixels"][offs[i]:offs[i + 1]].reshape(hw[i, 0], hw[i, 1], 3) for i in range(len(hw))]
+    feats = stage_ref.embed_arrays(images, batch_size=1, seed=int(g["seed"]))
+    ref = g["features"]
+    # same library calls as the reference; batch-1 like the reference -> identical up to thread scheduling noise
+    np.testing.assert_allclose(feats, ref, rtol=1e-4, atol=1e-4)
+    cos = (feats * ref).sum(1) / np.linalg.norm(feats, axis=1) / np.linalg.norm(ref, axis=1)
+    assert cos.min() > 0.999999
+
+
+# ------------------------------------------------------------------ A3 PCA
+def test_pca_ref_matches_golden_full_solver():
+    g = load_golden("pca.npz")
+    x = synth.embedding_like(int(g["n"]), int(g["d"]), seed=int(g["seed"]))
+    k = int(g["k"])
+    r = pca_ref.pca_fit(x, k)
+    np.testing.assert_allclose(r.mean, g["mean"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(r.explained_variance, g["explained_variance"], rtol=1e-9)
+    np.testing.assert_allclose(r.explained_variance_ratio, g["explained_variance_ratio"], rtol=1e-9)
+    np.testing.assert_allclose(r.singular_values, g["singular_values"], rtol=1e-9)
+    np.testing.assert_allclose(r.noise_variance, float(g["noise_variance"]), rtol=1e-8)
+    assert pca_ref.subspace_angle(r.components, g["components"]) < 1e-7
+    # identical signs (svd_flip convention) and per-component agreement
+    dots = (r.components * g["components"]).sum(1)
+    assert (dots > 0.999999).all()
+    z = pca_ref.pca_transform(x[:64], r.mean, r.components)
+    np.testing.assert_allclose(z, g["z_head"], atol=1e-7)
+
+
+def test_subspace_angle_helper():
+    rng = np.random.default_rng(0)
+    q = np.linalg.qr(rng.standard_normal((50, 5)))[0].T
+    assert pca_ref.subspace_angle(q, q) < 1e-12
+    rot = q.copy()
+    theta = 1e-4
+    rot[0] = np.cos(theta) * q[0] + np.sin(theta) * np.linalg.qr(rng.standard_normal((50, 6)))[0].T[5]
+    assert 0 < pca_ref.subspace_angle(q, rot) < 2e-4
+
+
+# ------------------------------------------------------------------ A4 LOF
+def test_lof_ref_matches_reference_golden():
+    g = load_golden("lof.npz")
+    z, y = synth.clustered_points(int(g["n"]), int(g["d"]), int(g["classes"]), seed=int(g["seed"]))
+    labels = np.array([f"cls{c:02d}" for c in y])
+    scores = lof_ref.lof_scores(z, 75)
+    np.testing.assert_allclose(scores, g["global_scores"], rtol=2e-6)
+    cls_out, glob_out = lof_ref.detect_outliers(z, labels)
+    assert np.array_equal(glob_out, g["global_outliers"])
+    assert np.array_equal(cls_out, g["class_outliers"])
+
+
+def test_lof_ref_matches_reference_golden_2d_clipped_k():
+    g = load_golden("lof.npz")
+    z, y = synth.clustered_points(int(g["n2"]), int(g["d2"]), int(g["classes2"]), seed=int(g["seed2"]))
+    labels = np.array([f"c{c:02d}" for c in y])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cls_out, glob_out = lof_ref.detect_outliers(z, labels)
+    assert np.array_equal(glob_out, g["global_outliers2"])
+    assert np.array_equal(cls_out, g["class_outliers2"])
+
+
+def test_stage_ref_detect_outliers_is_the_reference_call():
+    g = load_golden("lof.npz")
+    z, y = synth.clustered_points(int(g["n"]), int(g["d"]), int(g["classes"]), seed=int(g["seed"]))
+    labels = np.array([f"cls{c:02d}" for c in y])
+    cls_out, glob_out = stage_ref.detect_outliers(z, labels)
+    assert np.array_equal(cls_out, g["class_outliers"]) and np.array_equal(glob_out, g["global_outliers"])
+
+
+def test_centroid_scorer_definition():
+    z, y = synth.clustered_points(500, 8, 4, seed=2)
+    dist, zs, thr, flags = lof_ref.centroid_zscore(z, y, 4, 0.05)
+    for c in range(4):
+        m = y == c
+        mu = z[m].astype(np.float64).mean(0)
+        np.testing.assert_allclose(dist[m], np.linalg.norm(z[m] - mu, axis=1), rtol=1e-12)
+        assert abs(zs[m].mean()) < 1e-9 and abs(zs[m].std() - 1) < 1e-9
+        assert 0.03 <= flags[m].mean() <= 0.07
