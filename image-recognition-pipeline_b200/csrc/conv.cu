@@ -142,7 +142,8 @@ struct ConvPlan {
   ConvParams p;
   int bn_tile = 128;  // BN of the kernel instance
   ConvKind kind = kConvFlat;
-  int H = 0, W = 0, cin = 0, ksize = 1, stride = 1;
+  bool has_res = false;
+  int H = 0, W = 0, Ho = 0, Wo = 0, cin = 0, cout = 0, ksize = 1, stride = 1;
   int max_batch = 0;
 };
 
@@ -173,6 +174,28 @@ static void choose_box(int Wo, int Ho, int B, int* bw, int* bh, int* bn) {
 
 static inline int floor_div2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
 
+// Output / residual tensor maps: same (bw,bh,bn) box as the A operand, 64 channels per box.
+static int encode_out_maps(ConvPlan* plan, void* out, const void* residual, int max_batch) {
+  ConvParams& p = plan->p;
+  const uint64_t C = static_cast<uint64_t>(plan->cout);
+  uint64_t dims[4], strides[3];
+  if (plan->kind == kConvFlat) {
+    const uint64_t M = static_cast<uint64_t>(max_batch) * plan->Ho * plan->Wo;
+    dims[0] = C; dims[1] = M; dims[2] = 1; dims[3] = 1;
+    strides[0] = C * 2; strides[1] = M * C * 2; strides[2] = M * C * 2;
+  } else {
+    dims[0] = C; dims[1] = plan->Wo; dims[2] = plan->Ho; dims[3] = max_batch;
+    strides[0] = C * 2; strides[1] = static_cast<uint64_t>(plan->Wo) * C * 2;
+    strides[2] = static_cast<uint64_t>(plan->Ho) * plan->Wo * C * 2;
+  }
+  uint32_t box[4] = {64, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
+  IRP_TRY(encode_bf16_map(&p.tmOut, out, 4, dims, strides, box, 128));
+  plan->has_res = residual != nullptr;
+  if (residual) IRP_TRY(encode_bf16_map(&p.tmRes, const_cast<void*>(residual), 4, dims, strides, box, 128));
+  p.out_box_bytes = p.bw * p.bh * p.bn * 128;
+  return IRP_OK;
+}
+
 // Builds tensor maps + static fields. x/w/out pointers are baked into the maps / params.
 static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* bias, const void* residual,
                      void* out, int max_batch, int H, int W, int Cin, int Cout, int ksize, int stride, int relu) {
@@ -186,19 +209,19 @@ static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* 
   memset(&p, 0, sizeof(p));
   plan->H = H;
   plan->W = W;
+  plan->Ho = Ho;
+  plan->Wo = Wo;
   plan->cin = Cin;
+  plan->cout = Cout;
   plan->ksize = ksize;
   plan->stride = stride;
   plan->max_batch = max_batch;
   plan->bn_tile = (Cout % 128 == 0) ? 128 : 64;
   constexpr int BK = 64;
-  p.Cout = Cout;
   p.cin = Cin;
   p.kc_blocks = Cin / BK;
   p.ntaps = ksize * ksize;
   p.bias = bias;
-  p.residual = static_cast<const __nv_bfloat16*>(residual);
-  p.out = static_cast<__nv_bfloat16*>(out);
   p.relu = relu;
   p.n_tiles_n = Cout / plan->bn_tile;
 
@@ -256,8 +279,7 @@ static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* 
     }
   }
   p.a_box_bytes = p.bw * p.bh * p.bn * BK * 2;
-  p.Ho = Ho;
-  p.Wo = Wo;
+  IRP_TRY(encode_out_maps(plan, out, residual, max_batch));
   // weights: [Cout][taps*Cin]
   {
     const uint64_t K = static_cast<uint64_t>(p.ntaps) * Cin;
@@ -269,11 +291,11 @@ static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* 
   return IRP_OK;
 }
 
-template <int BN, int BK, bool STEM>
+template <int BN, int BK, bool STEM, bool RES, int NB>
 static int launch_instance(const ConvParams& p, cudaStream_t stream) {
-  using S = ConvSmem<BN, BK>;
+  using S = ConvSmem<BN, BK, NB>;
   static bool configured = false;
-  auto kernel = conv_gemm_kernel<BN, BK, STEM>;
+  auto kernel = conv_gemm_kernel<BN, BK, STEM, RES, NB>;
   if (!configured) {
     IRP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
     configured = true;
@@ -286,53 +308,55 @@ static int launch_instance(const ConvParams& p, cudaStream_t stream) {
 }
 
 // Launch a planned conv on `batch` images (batch <= plan->max_batch).
-static int launch_conv(const ConvPlan& plan, int batch, cudaStream_t stream) {
+static int launch_conv(const ConvPlan& plan, int batch, cudaStream_t stream, int n_base = 0) {
   ConvParams p = plan.p;
+  p.n_base = n_base;
   if (plan.kind == kConvFlat) {
-    const long long M = static_cast<long long>(batch) * plan.p.Ho * plan.p.Wo;
-    p.B = 1;
-    p.Ho = 1;
-    p.Wo = static_cast<int>(M);
+    const long long M = static_cast<long long>(batch) * plan.Ho * plan.Wo;
     p.tiles_w = static_cast<int>(ceil_div64(M, kTileM));
     p.tiles_h = 1;
     p.tiles_n = 1;
   } else {
-    p.B = batch;
-    p.tiles_w = ceil_div(p.Wo, p.bw);
-    p.tiles_h = ceil_div(p.Ho, p.bh);
+    p.tiles_w = ceil_div(plan.Wo, p.bw);
+    p.tiles_h = ceil_div(plan.Ho, p.bh);
     p.tiles_n = ceil_div(batch, p.bn);
   }
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
-  if (plan.kind == kConvStem) return launch_instance<64, 32, true>(p, stream);
-  if (plan.bn_tile == 128) return launch_instance<128, 64, false>(p, stream);
-  return launch_instance<64, 64, false>(p, stream);
+  const int k_blocks = p.ntaps * p.kc_blocks;
+  if (plan.kind == kConvStem) return launch_instance<64, 32, true, false, 2>(p, stream);
+  if (plan.bn_tile == 128) {
+    if (plan.has_res) return launch_instance<128, 64, false, true, 3>(p, stream);
+    if (k_blocks >= 9) return launch_instance<128, 64, false, false, 1>(p, stream);
+    return launch_instance<128, 64, false, false, 2>(p, stream);
+  }
+  if (plan.has_res) return launch_instance<64, 64, false, true, 3>(p, stream);
+  if (k_blocks >= 9) return launch_instance<64, 64, false, false, 1>(p, stream);
+  return launch_instance<64, 64, false, false, 2>(p, stream);
 }
 
 // Stem through the overlapping 5-D TMA view of the padded NHWC4 input (see conv_gemm.cuh, STEM path).
 static int plan_stem_tma(ConvPlan* plan, const void* x_nhwc4p, const void* w, const float* bias, void* out,
-                         int max_batch) {
+                         int max_batch, int input_batch) {
   ConvParams& p = plan->p;
   memset(&p, 0, sizeof(p));
   plan->kind = kConvStem;
   plan->bn_tile = 64;
   plan->max_batch = max_batch;
+  plan->Ho = 112;
+  plan->Wo = 112;
+  plan->cout = 64;
   constexpr int P = IRP_PAD_HW;
-  p.Cout = 64;
   p.cin = 32;  // K per filter row: 8 pixels x 4 channels
   p.kc_blocks = 1;
   p.ntaps = 7;
   p.bias = bias;
-  p.residual = nullptr;
-  p.out = static_cast<__nv_bfloat16*>(out);
   p.relu = 1;
   p.n_tiles_n = 1;
-  p.Ho = 112;
-  p.Wo = 112;
   p.bw = 16;
   p.bh = 8;
   p.bn = 1;
   p.a_box_bytes = kTileM * 32 * 2;
-  uint64_t dims[5] = {32, 112, 2, P / 2, static_cast<uint64_t>(max_batch)};
+  uint64_t dims[5] = {32, 112, 2, P / 2, static_cast<uint64_t>(input_batch)};
   uint64_t strides[4] = {16, static_cast<uint64_t>(P) * 8, static_cast<uint64_t>(P) * 16,
                          static_cast<uint64_t>(P) * P * 8};
   uint32_t box[5] = {32, 16, 1, 8, 1};
@@ -341,6 +365,7 @@ static int plan_stem_tma(ConvPlan* plan, const void* x_nhwc4p, const void* w, co
   uint64_t ws[1] = {7 * 32 * 2};
   uint32_t wb[2] = {32, 64};
   IRP_TRY(encode_bf16_map(&p.tmB, const_cast<void*>(w), 2, wd, ws, wb, 64));
+  IRP_TRY(encode_out_maps(plan, out, nullptr, max_batch));
   return IRP_OK;
 }
 
@@ -398,6 +423,8 @@ static const std::vector<ConvSpec>& specs() {
 
 struct irp_resnet50 {
   int max_batch = 0;
+  int micro = 0;  // images per pass through the trunk (activation arena size); inter-layer tensors of one
+                  // micro-batch are meant to stay resident in the 126 MB L2
   int stem_mode = 0;  // 0: overlapping TMA view, 1: explicit im2col + flat GEMM
   std::vector<ConvPlan> plans;
   std::vector<__nv_bfloat16*> weights;
@@ -418,11 +445,11 @@ static size_t weight_elems(const ConvSpec& s, int stem_mode) {
 
 static int resnet50_plan(irp_resnet50* net, const void* d_x) {
   const auto& sp = specs();
-  const int B = net->max_batch;
+  const int B = net->micro;
   enum { A = 0, Bb = 1, T1 = 2, T2 = 3, DS = 4, STEM = 5 };
   // stem
   if (net->stem_mode == 0) {
-    IRP_TRY(plan_stem_tma(&net->plans[0], d_x, net->weights[0], net->biases[0], net->buf[STEM], B));
+    IRP_TRY(plan_stem_tma(&net->plans[0], d_x, net->weights[0], net->biases[0], net->buf[STEM], B, net->max_batch));
   } else {
     IRP_TRY(plan_conv(&net->plans[0], net->im2col, net->weights[0], net->biases[0], nullptr, net->buf[STEM], B, 112,
                       112, 192, 64, 1, 1, 1));
@@ -480,6 +507,11 @@ int irp_resnet50_create(irp_resnet50** out, int max_batch) {
   if (!net) return IRP_ERR_NOMEM;
   const auto& sp = specs();
   net->max_batch = max_batch;
+  net->micro = max_batch;
+  if (const char* mb = getenv("IRP_MICRO_BATCH")) {
+    const int v = atoi(mb);
+    if (v > 0 && v < max_batch) net->micro = v;
+  }
   const char* mode = getenv("IRP_STEM_MODE");
   net->stem_mode = (mode && mode[0] == '1') ? 1 : 0;
   net->plans.resize(sp.size());
@@ -490,10 +522,10 @@ int irp_resnet50_create(irp_resnet50** out, int max_batch) {
                              112 * 112 * 64};
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < 6 && e == cudaSuccess; ++i)
-    e = cudaMalloc(reinterpret_cast<void**>(&net->buf[i]), per_img[i] * max_batch * sizeof(__nv_bfloat16));
+    e = cudaMalloc(reinterpret_cast<void**>(&net->buf[i]), per_img[i] * net->micro * sizeof(__nv_bfloat16));
   if (e == cudaSuccess && net->stem_mode == 1)
     e = cudaMalloc(reinterpret_cast<void**>(&net->im2col),
-                   static_cast<size_t>(max_batch) * 112 * 112 * 192 * sizeof(__nv_bfloat16));
+                   static_cast<size_t>(net->micro) * 112 * 112 * 192 * sizeof(__nv_bfloat16));
   for (size_t i = 0; i < sp.size() && e == cudaSuccess; ++i) {
     e = cudaMalloc(reinterpret_cast<void**>(&net->weights[i]),
                    weight_elems(sp[i], net->stem_mode) * sizeof(__nv_bfloat16));
@@ -557,51 +589,55 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
   if (!net->planned || net->planned_input != d_x) IRP_TRY(resnet50_plan(net, d_x));
   const auto& sp = specs();
   enum { A = 0, STEM = 5 };
-  auto capture = [&](int idx) -> int {
-    if (idx != capture_index || d_capture == nullptr) return IRP_OK;
-    const ConvSpec& s = sp[idx];
-    const int ho = s.role == 0 ? 112 : s.H / s.stride, wo = s.role == 0 ? 112 : s.W / s.stride;
-    const size_t elems = static_cast<size_t>(batch) * ho * wo * s.cout;
-    IRP_REQUIRE(elems <= capture_capacity, "capture buffer too small: need %zu elements", elems);
-    IRP_CUDA_OK(cudaMemcpyAsync(d_capture, net->buf[net->out_buf[idx]], elems * sizeof(__nv_bfloat16),
-                                cudaMemcpyDeviceToDevice, st));
-    return IRP_OK;
-  };
-  if (net->stem_mode == 1) {
-    const long long total = static_cast<long long>(batch) * 112 * 112 * (192 / 8);
-    stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(d_x), net->im2col,
-                                                             batch);
-    IRP_CUDA_OK(cudaGetLastError());
-  }
-  IRP_TRY(launch_conv(net->plans[0], batch, st));
-  IRP_TRY(capture(0));
-  {
-    const long long total = static_cast<long long>(batch) * 56 * 56 * (64 / 8);
-    maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(net->buf[STEM], net->buf[A], batch, 112, 112, 64, 56,
-                                                              56);
-    IRP_CUDA_OK(cudaGetLastError());
-  }
-  size_t i = 1;
-  int last = 0;
-  while (i < sp.size()) {
-    const bool has_ds = (i + 3 < sp.size()) && sp[i + 3].role == 4;
-    IRP_TRY(launch_conv(net->plans[i], batch, st));
-    IRP_TRY(capture(static_cast<int>(i)));
-    IRP_TRY(launch_conv(net->plans[i + 1], batch, st));
-    IRP_TRY(capture(static_cast<int>(i + 1)));
-    if (has_ds) {
-      IRP_TRY(launch_conv(net->plans[i + 3], batch, st));
-      IRP_TRY(capture(static_cast<int>(i + 3)));
+  for (int s0 = 0; s0 < batch; s0 += net->micro) {
+    const int mb = batch - s0 < net->micro ? batch - s0 : net->micro;
+    auto capture = [&](int idx) -> int {
+      if (idx != capture_index || d_capture == nullptr) return IRP_OK;
+      const ConvSpec& s = sp[idx];
+      const int ho = s.role == 0 ? 112 : s.H / s.stride, wo = s.role == 0 ? 112 : s.W / s.stride;
+      const size_t per_img = static_cast<size_t>(ho) * wo * s.cout;
+      IRP_REQUIRE(per_img * batch <= capture_capacity, "capture buffer too small: need %zu elements", per_img * batch);
+      IRP_CUDA_OK(cudaMemcpyAsync(static_cast<__nv_bfloat16*>(d_capture) + per_img * s0, net->buf[net->out_buf[idx]],
+                                  per_img * mb * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st));
+      return IRP_OK;
+    };
+    if (net->stem_mode == 1) {
+      const long long total = static_cast<long long>(mb) * 112 * 112 * (192 / 8);
+      stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(d_x) + static_cast<size_t>(s0) * IRP_PAD_HW * IRP_PAD_HW * 4, net->im2col,
+          mb);
+      IRP_CUDA_OK(cudaGetLastError());
     }
-    IRP_TRY(launch_conv(net->plans[i + 2], batch, st));
-    IRP_TRY(capture(static_cast<int>(i + 2)));
-    last = static_cast<int>(i + 2);
-    i += has_ds ? 4 : 3;
-  }
-  {
-    const long long total = static_cast<long long>(batch) * (2048 / 2);
-    avgpool_kernel<<<grid_for(total, 128), 128, 0, st>>>(net->buf[net->out_buf[last]], d_embed, batch, 49, 2048);
-    IRP_CUDA_OK(cudaGetLastError());
+    IRP_TRY(launch_conv(net->plans[0], mb, st, s0));
+    IRP_TRY(capture(0));
+    {
+      const long long total = static_cast<long long>(mb) * 56 * 56 * (64 / 8);
+      maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(net->buf[STEM], net->buf[A], mb, 112, 112, 64, 56, 56);
+      IRP_CUDA_OK(cudaGetLastError());
+    }
+    size_t i = 1;
+    int last = 0;
+    while (i < sp.size()) {
+      const bool has_ds = (i + 3 < sp.size()) && sp[i + 3].role == 4;
+      IRP_TRY(launch_conv(net->plans[i], mb, st));
+      IRP_TRY(capture(static_cast<int>(i)));
+      IRP_TRY(launch_conv(net->plans[i + 1], mb, st));
+      IRP_TRY(capture(static_cast<int>(i + 1)));
+      if (has_ds) {
+        IRP_TRY(launch_conv(net->plans[i + 3], mb, st));
+        IRP_TRY(capture(static_cast<int>(i + 3)));
+      }
+      IRP_TRY(launch_conv(net->plans[i + 2], mb, st));
+      IRP_TRY(capture(static_cast<int>(i + 2)));
+      last = static_cast<int>(i + 2);
+      i += has_ds ? 4 : 3;
+    }
+    {
+      const long long total = static_cast<long long>(mb) * (2048 / 2);
+      avgpool_kernel<<<grid_for(total, 128), 128, 0, st>>>(net->buf[net->out_buf[last]],
+                                                          d_embed + static_cast<size_t>(s0) * 2048, mb, 49, 2048);
+      IRP_CUDA_OK(cudaGetLastError());
+    }
   }
   return IRP_OK;
 }

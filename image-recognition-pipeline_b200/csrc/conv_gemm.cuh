@@ -11,6 +11,10 @@
 //   each a plain strided tensor map.  Accumulators live in TMEM (double buffered) so the epilogue of tile i
 //   overlaps the main loop of tile i+1.
 //
+// Epilogue: TMEM -> registers -> (+bias, +residual, ReLU, bf16) -> swizzled shared-memory staging tile -> TMA
+// store with the same box geometry as the A loads (TMA clips rows outside the tensor, so ragged tiles need no
+// predication).  The residual tile is prefetched by TMA into the staging buffer it will be overwritten in.
+//
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
 #pragma once
 #include <cuda.h>
@@ -24,59 +28,69 @@ namespace irp {
 constexpr int kConvThreads = 192;
 constexpr int kMaxTaps = 9;
 constexpr int kTileM = 128;
+constexpr int kStgChunkBytes = kTileM * 128;  // one 64-channel column chunk of the output tile (128 B rows)
 
 struct alignas(64) ConvParams {
   CUtensorMap tmA[4];  // activation views (index = parity for stride 2; [0] only for stride 1 / stem)
   CUtensorMap tmB;     // weights [Cout][K] bf16, K-major
+  CUtensorMap tmOut;   // output  (Cout, Wo, Ho, B) / flat (Cout, M, 1, 1), box (64, bw, bh, bn)
+  CUtensorMap tmRes;   // residual, same geometry as tmOut (valid only for the RES instances)
   // M tiling: box (bw,bh,bn) in output coordinates
   int bw, bh, bn;
   int tiles_w, tiles_h, tiles_n;
   int n_tiles_n;  // Cout / BN
   int num_tiles;
-  int a_box_bytes;  // bytes one A TMA box delivers (rows_in_box * BK * 2)
+  int a_box_bytes;    // bytes one A TMA box delivers (rows_in_box * BK * 2)
+  int out_box_bytes;  // bytes one 64-channel output/residual box moves (rows_in_box * 128)
   // problem
-  int B, Ho, Wo, Cout;
   int ntaps, kc_blocks;  // K loop = ntaps * kc_blocks blocks of BK
   int cin;               // channels per tap in the weight matrix (K offset of tap t = t*cin)
+  int n_base;            // stem only: first image of this micro-batch inside the input tensor map
   int8_t tap_map[kMaxTaps], tap_dw[kMaxTaps], tap_dh[kMaxTaps];
   // epilogue
-  const float* bias;             // [Cout]
-  const __nv_bfloat16* residual;  // NHWC [B,Ho,Wo,Cout] or nullptr
-  __nv_bfloat16* out;             // NHWC [B,Ho,Wo,Cout]
+  const float* bias;  // [Cout]
   int relu;
 };
 
-template <int BN, int BK>
+template <int BN, int BK, int NB>
 struct ConvSmem {
   static constexpr int kABytes = kTileM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBudget = 200 * 1024;
+  static constexpr int kStgBytes = (BN / 64) * kStgChunkBytes;  // one staging buffer
+  static constexpr int kBudget = 220 * 1024 - NB * kStgBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotalBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024: manual alignment
+  static constexpr int kBarrierBytes = 512;
+  static constexpr int kTotalBytes = kStages * kStageBytes + NB * kStgBytes + kBarrierBytes + 1024;
+  static_assert(kStages >= 2, "not enough shared memory for a pipeline");
 };
 
-template <int BN, int BK, bool STEM>
+// NB = staging buffers: 3 with a residual (prefetch one tile ahead), else 1 (long K loops) or 2 (short ones).
+template <int BN, int BK, bool STEM, bool RES, int NB>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
-  using S = ConvSmem<BN, BK>;
+  using S = ConvSmem<BN, BK, NB>;
   constexpr int kStages = S::kStages;
   constexpr int kSwz = BK * 2;            // swizzle span in bytes == one K block row
   constexpr uint32_t kTmemCols = 2 * BN;  // double-buffered fp32 accumulator (power of two >= 32)
+  constexpr int kChunks = BN / 64;        // 64-channel column chunks per tile
   static_assert(kTmemCols >= 32 && kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns");
+  static_assert(!RES || NB == 3, "residual prefetch needs three staging buffers");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint8_t* smem_stg = smem + kStages * S::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + NB * S::kStgBytes);
   uint64_t* full_bar = bars;                 // [kStages] TMA -> MMA
   uint64_t* empty_bar = bars + kStages;      // [kStages] MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kStages;  // [2] MMA -> epilogue
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_full = tempty_bar + 2;       // [NB] residual tile landed in staging buffer
+  uint64_t* stg_empty = res_full + NB;       // [NB] staging buffer may be refilled by the producer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_empty + NB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -84,6 +98,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmOut);
+    if (RES) tma_prefetch_desc(&p.tmRes);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -91,6 +107,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 128);
+    }
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(&res_full[i], 1);
+      mbar_init(&stg_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -110,7 +130,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int j = 0;  // local tile counter
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
         const int n_tile = tile % p.n_tiles_n;
         int m_tile = tile / p.n_tiles_n;
         const int tw = m_tile % p.tiles_w;
@@ -118,6 +139,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         const int th = m_tile % p.tiles_h;
         const int tn = m_tile / p.tiles_h;
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+        if (RES) {
+          // residual tile -> the staging buffer the epilogue will overwrite in place
+          const int b = j % NB;
+          mbar_wait(&stg_empty[b], (j / NB) & 1);
+          mbar_arrive_expect_tx(&res_full[b], kChunks * p.out_box_bytes);
+#pragma unroll
+          for (int cc = 0; cc < kChunks; ++cc)
+            tma_load_4d(smem_stg + b * S::kStgBytes + cc * kStgChunkBytes, &p.tmRes, &res_full[b],
+                        n_tile * BN + cc * 64, w0, h0, n0);
+        }
         for (int t = 0; t < p.ntaps; ++t) {
           for (int kc = 0; kc < p.kc_blocks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -125,7 +156,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             if constexpr (STEM) {
               // 5-D view (32 = 8 px * 4 ch, wo, row parity, row pair, n): filter row t of the 7x7/2 stem
               tma_load_5d(smem_a + stage * S::kABytes, &p.tmA[0], &full_bar[stage], 0, w0, t & 1, h0 + (t >> 1),
-                          n0);
+                          n0 + p.n_base);
             } else {
               tma_load_4d(smem_a + stage * S::kABytes, &p.tmA[p.tap_map[t]], &full_bar[stage], kc * BK,
                           w0 + p.tap_dw[t], h0 + p.tap_dh[t], n0);
@@ -177,76 +208,99 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     // ============================ epilogue (warps 2..5) ============================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;
-    const int w_l = row % p.bw;
-    const int h_l = (row / p.bw) % p.bh;
-    const int n_l = row / (p.bw * p.bh);
+    const bool leader = (threadIdx.x == 64);  // issues the TMA stores, owns their bulk groups
+    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+    const uint32_t swz = static_cast<uint32_t>(row & 7);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int j = 0;
+    if (RES && leader) mbar_arrive(&stg_empty[0]);  // first use of buffer 0 needs no predecessor
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
       const int n_tile = tile % p.n_tiles_n;
       int m_tile = tile / p.n_tiles_n;
       const int tw = m_tile % p.tiles_w;
       m_tile /= p.tiles_w;
       const int th = m_tile % p.tiles_h;
       const int tn = m_tile / p.tiles_h;
-      const int w = tw * p.bw + w_l, h = th * p.bh + h_l, n = tn * p.bn + n_l;
-      const bool valid = (n_l < p.bn) && (n < p.B) && (h < p.Ho) && (w < p.Wo);
-      const size_t pix = (static_cast<size_t>(n) * p.Ho + h) * p.Wo + w;
-      const size_t off = pix * p.Cout + static_cast<size_t>(n_tile) * BN;
+      const int b = j % NB;
+      uint8_t* stg = smem_stg + b * S::kStgBytes;
+
+      if (RES) {
+        // release the buffer of the NEXT tile (its previous store has finished reading), then wait for our residual
+        if (leader) {
+          tma_store_wait_read<(NB >= 2 ? NB - 2 : 0)>();
+          mbar_arrive(&stg_empty[(j + 1) % NB]);
+        }
+        mbar_wait(&res_full[b], (j / NB) & 1);
+      } else {
+        if (leader) tma_store_wait_read<NB - 1>();
+        named_bar_sync(1, 128);  // buffer b is free for everyone
+      }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32b_x32(taddr + c, v);
+        uint8_t* chunk = stg + (c >> 6) * kStgChunkBytes + row_off;
+        const int piece0 = (c & 32) >> 3;  // first 16-byte piece of this half chunk: 0 or 4
         uint4 rv[4];
-        const bool has_res = (p.residual != nullptr) && valid;
-        if (has_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c);
+        if (RES) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) rv[i] = __ldg(rp + i);
+          for (int i = 0; i < 4; ++i)
+            rv[i] = *reinterpret_cast<const uint4*>(chunk + (((piece0 + i) ^ swz) << 4));
         }
         const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + c);
         __syncwarp();
         tmem_ld_wait();
-        uint32_t o[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = __ldg(bp + i);
-          float x0 = __uint_as_float(v[4 * i + 0]) + b.x;
-          float x1 = __uint_as_float(v[4 * i + 1]) + b.y;
-          float x2 = __uint_as_float(v[4 * i + 2]) + b.z;
-          float x3 = __uint_as_float(v[4 * i + 3]) + b.w;
-          if (has_res) {
-            const uint32_t* r32 = reinterpret_cast<const uint32_t*>(rv);
-            x0 += bf16_lo(r32[2 * i]);
-            x1 += bf16_hi(r32[2 * i]);
-            x2 += bf16_lo(r32[2 * i + 1]);
-            x3 += bf16_hi(r32[2 * i + 1]);
+        for (int i = 0; i < 4; ++i) {
+          const float4 b0 = __ldg(bp + 2 * i), b1 = __ldg(bp + 2 * i + 1);
+          float x[8];
+          x[0] = __uint_as_float(v[8 * i + 0]) + b0.x;
+          x[1] = __uint_as_float(v[8 * i + 1]) + b0.y;
+          x[2] = __uint_as_float(v[8 * i + 2]) + b0.z;
+          x[3] = __uint_as_float(v[8 * i + 3]) + b0.w;
+          x[4] = __uint_as_float(v[8 * i + 4]) + b1.x;
+          x[5] = __uint_as_float(v[8 * i + 5]) + b1.y;
+          x[6] = __uint_as_float(v[8 * i + 6]) + b1.z;
+          x[7] = __uint_as_float(v[8 * i + 7]) + b1.w;
+          if (RES) {
+            const uint32_t* r32 = reinterpret_cast<const uint32_t*>(&rv[i]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              x[2 * q] += bf16_lo(r32[q]);
+              x[2 * q + 1] += bf16_hi(r32[q]);
+            }
           }
           if (p.relu) {
-            x0 = fmaxf(x0, 0.f);
-            x1 = fmaxf(x1, 0.f);
-            x2 = fmaxf(x2, 0.f);
-            x3 = fmaxf(x3, 0.f);
-          }
-          o[2 * i] = pack_bf16x2(x0, x1);
-          o[2 * i + 1] = pack_bf16x2(x2, x3);
-        }
-        if (valid) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + off + c);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) op[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            for (int q = 0; q < 8; ++q) x[q] = fmaxf(x[q], 0.f);
+          }
+          *reinterpret_cast<uint4*>(chunk + (((piece0 + i) ^ swz) << 4)) =
+              make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                         pack_bf16x2(x[6], x[7]));
         }
       }
+      // accumulator drained -> MMA may reuse it
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
+      // staging tile complete -> async proxy -> TMA store
+      fence_proxy_async();
+      named_bar_sync(2, 128);
+      if (leader) {
+#pragma unroll
+        for (int cc = 0; cc < kChunks; ++cc)
+          tma_store_4d(&p.tmOut, stg + cc * kStgChunkBytes, n_tile * BN + cc * 64, tw * p.bw, th * p.bh, tn * p.bn);
+        tma_store_commit();
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (leader) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
