@@ -291,20 +291,71 @@ static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* 
   return IRP_OK;
 }
 
-template <int BN, int BK, bool STEM, bool RES, int NB>
+template <int BN, int BK, bool STEM, bool RES, int NB, int CM = 1, int CN = 1>
 static int launch_instance(const ConvParams& p, cudaStream_t stream) {
   using S = ConvSmem<BN, BK, NB>;
+  constexpr int kCluster = CM * CN;
   static bool configured = false;
-  auto kernel = conv_gemm_kernel<BN, BK, STEM, RES, NB>;
+  static int max_ctas = 0;
+  auto kernel = conv_gemm_kernel<BN, BK, STEM, RES, NB, CM, CN>;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = S::kTotalBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = kCluster > 1 ? 1 : 0;
   if (!configured) {
     IRP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
+    max_ctas = num_sms();
+    if (kCluster > 1) {
+      // how many clusters can be co-resident (GPC granularity strands a few SMs for cluster size 4)
+      cfg.gridDim = dim3(num_sms() / kCluster * kCluster);
+      int clusters = 0;
+      IRP_CUDA_OK(cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg));
+      if (clusters < 1) clusters = 1;
+      max_ctas = clusters * kCluster;
+    }
     configured = true;
   }
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int num_groups = ceil_div(m_tiles, CM) * (p.n_tiles_n / CN);
+  int grid = num_groups * kCluster;
+  if (grid > max_ctas) grid = max_ctas;
   if (grid <= 0) return IRP_OK;
-  kernel<<<grid, kConvThreads, S::kTotalBytes, stream>>>(p);
-  IRP_CUDA_OK(cudaGetLastError());
+  cfg.gridDim = dim3(grid);
+  IRP_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
   return IRP_OK;
+}
+
+// cluster shape policy: 0 = none, 21 = 2x1 (share weights), 12 = 1x2 (share activations), 22 = 2x2
+static int cluster_policy(const ConvPlan& plan, int k_blocks) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("IRP_CLUSTER");
+    forced = e ? atoi(e) : 0;
+    if (!e) forced = 1000;  // no override
+  }
+  const int n_tiles = plan.cout / plan.bn_tile;
+  int want = forced == 1000 ? 0 : forced;
+  if ((want == 22 || want == 12) && (n_tiles % 2) != 0) want = want == 22 ? 21 : 0;
+  (void)k_blocks;
+  return want;
+}
+
+template <int BN, bool RES, int NB>
+static int launch_clustered(const ConvParams& p, int shape, cudaStream_t stream) {
+  switch (shape) {
+    case 21: return launch_instance<BN, 64, false, RES, NB, 2, 1>(p, stream);
+    case 12: return launch_instance<BN, 64, false, RES, NB, 1, 2>(p, stream);
+    case 22: return launch_instance<BN, 64, false, RES, NB, 2, 2>(p, stream);
+    default: return launch_instance<BN, 64, false, RES, NB, 1, 1>(p, stream);
+  }
 }
 
 // Launch a planned conv on `batch` images (batch <= plan->max_batch).
@@ -325,9 +376,10 @@ static int launch_conv(const ConvPlan& plan, int batch, cudaStream_t stream, int
   const int k_blocks = p.ntaps * p.kc_blocks;
   if (plan.kind == kConvStem) return launch_instance<64, 32, true, false, 2>(p, stream);
   if (plan.bn_tile == 128) {
-    if (plan.has_res) return launch_instance<128, 64, false, true, 3>(p, stream);
-    if (k_blocks >= 9) return launch_instance<128, 64, false, false, 1>(p, stream);
-    return launch_instance<128, 64, false, false, 2>(p, stream);
+    const int shape = cluster_policy(plan, k_blocks);
+    if (plan.has_res) return launch_clustered<128, true, 3>(p, shape, stream);
+    if (k_blocks >= 9) return launch_clustered<128, false, 1>(p, shape, stream);
+    return launch_clustered<128, false, 2>(p, shape, stream);
   }
   if (plan.has_res) return launch_instance<64, 64, false, true, 3>(p, stream);
   if (k_blocks >= 9) return launch_instance<64, 64, false, false, 1>(p, stream);

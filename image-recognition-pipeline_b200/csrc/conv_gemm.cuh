@@ -67,7 +67,10 @@ struct ConvSmem {
 };
 
 // NB = staging buffers: 3 with a residual (prefetch one tile ahead), else 1 (long K loops) or 2 (short ones).
-template <int BN, int BK, bool STEM, bool RES, int NB>
+// CM x CN = thread-block cluster shape: the CN CTAs of a cluster row share one A (activation) tile and the CM
+// CTAs of a column share one B (weight) tile; each k-block's tile is fetched from L2 ONCE by one CTA of the group
+// and TMA-multicast to the others, which divides the L2->SM operand traffic (the limiter at 128x128 tiles).
+template <int BN, int BK, bool STEM, bool RES, int NB, int CM = 1, int CN = 1>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   using S = ConvSmem<BN, BK, NB>;
   constexpr int kStages = S::kStages;
@@ -95,6 +98,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  constexpr int kCluster = CM * CN;
+  const int crank = kCluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int rm = crank % CM, rn = crank / CM;  // position inside the cluster
+  const int cluster_id = blockIdx.x / kCluster;
+  const int num_clusters = gridDim.x / kCluster;
+  // tile groups: CM consecutive M tiles x CN consecutive N tiles
+  const int groups_n = p.n_tiles_n / CN;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int num_groups = ((m_tiles + CM - 1) / CM) * groups_n;
+  // CTAs that may write into my smem slots / whose slots I may write: my cluster row and column
+  uint16_t row_mask = 0, col_mask = 0;
+#pragma unroll
+  for (int i = 0; i < CN; ++i) row_mask |= static_cast<uint16_t>(1u << (rm + CM * i));  // same rm: share A
+#pragma unroll
+  for (int i = 0; i < CM; ++i) col_mask |= static_cast<uint16_t>(1u << (i + CM * rn));  // same rn: share B
+  const uint16_t peer_mask = row_mask | col_mask;
+
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB);
@@ -102,7 +122,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (RES) tma_prefetch_desc(&p.tmRes);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CM + CN - 1);  // one MMA commit from every CTA sharing a tile with me
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -120,6 +140,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // barrier inits visible before any peer multicasts / arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -131,9 +152,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       int stage = 0;
       uint32_t phase = 0;
       int j = 0;  // local tile counter
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
-        const int n_tile = tile % p.n_tiles_n;
-        int m_tile = tile / p.n_tiles_n;
+      int kb_global = 0;  // k-block counter (decides which CTA of a group fetches the shared tile)
+      for (int g = cluster_id; g < num_groups; g += num_clusters, ++j) {
+        const int n_tile = (g % groups_n) * CN + rn;
+        int m_tile = (g / groups_n) * CM + rm;  // may be a phantom tile past the end: loads zero-fill, stores clip
         const int tw = m_tile % p.tiles_w;
         m_tile /= p.tiles_w;
         const int th = m_tile % p.tiles_h;
@@ -157,11 +179,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               // 5-D view (32 = 8 px * 4 ch, wo, row parity, row pair, n): filter row t of the 7x7/2 stem
               tma_load_5d(smem_a + stage * S::kABytes, &p.tmA[0], &full_bar[stage], 0, w0, t & 1, h0 + (t >> 1),
                           n0 + p.n_base);
+            } else if constexpr (CN > 1) {
+              if (kb_global % CN == rn)
+                tma_load_4d_mc(smem_a + stage * S::kABytes, &p.tmA[p.tap_map[t]], &full_bar[stage], kc * BK,
+                               w0 + p.tap_dw[t], h0 + p.tap_dh[t], n0, row_mask);
             } else {
               tma_load_4d(smem_a + stage * S::kABytes, &p.tmA[p.tap_map[t]], &full_bar[stage], kc * BK,
                           w0 + p.tap_dw[t], h0 + p.tap_dh[t], n0);
             }
-            tma_load_2d(smem_b + stage * S::kBBytes, &p.tmB, &full_bar[stage], t * p.cin + kc * BK, n_tile * BN);
+            if constexpr (CM > 1) {
+              if (kb_global % CM == rm)
+                tma_load_2d_mc(smem_b + stage * S::kBBytes, &p.tmB, &full_bar[stage], t * p.cin + kc * BK,
+                               n_tile * BN, col_mask);
+            } else {
+              tma_load_2d(smem_b + stage * S::kBBytes, &p.tmB, &full_bar[stage], t * p.cin + kc * BK, n_tile * BN);
+            }
+            ++kb_global;
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -178,7 +211,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int g = cluster_id; g < num_groups; g += num_clusters) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -193,7 +226,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             const uint64_t db = umma_smem_desc<kSwz>(b_addr + k * 32);
             umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (here and in every CTA that multicasts into it) once these MMAs have read it
+          if constexpr (kCluster > 1) umma_commit_mc(&empty_bar[stage], peer_mask);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -215,9 +250,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint32_t acc_phase = 0;
     int j = 0;
     if (RES && leader) mbar_arrive(&stg_empty[0]);  // first use of buffer 0 needs no predecessor
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
-      const int n_tile = tile % p.n_tiles_n;
-      int m_tile = tile / p.n_tiles_n;
+    for (int g = cluster_id; g < num_groups; g += num_clusters, ++j) {
+      const int n_tile = (g % groups_n) * CN + rn;
+      int m_tile = (g / groups_n) * CM + rm;
       const int tw = m_tile % p.tiles_w;
       m_tile /= p.tiles_w;
       const int th = m_tile % p.tiles_h;
@@ -305,6 +340,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
