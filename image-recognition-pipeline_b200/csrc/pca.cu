@@ -385,75 +385,98 @@ __global__ void __launch_bounds__(kTriThreads) tridiag_step_kernel(double* __res
 }
 
 // ============================================================================================================
-// 5. top-k eigenvalues of the tridiagonal by multisection (one warp per eigenvalue, 32 shifts per round).
-//    Sturm count with LAPACK's pivmin safeguard (dlaebz).
+// 5. top-k eigenvalues of the tridiagonal by multisection: one CTA per eigenvalue, one shift per thread and round.
+//    Sturm count = sign changes of the leading-minor polynomials p_i(x) (three-term recurrence, division free,
+//    rescaled every 8 steps; a zero takes the sign opposite to its predecessor -- Wilkinson).  The matrix is scaled
+//    by 1/||T|| so the recurrence cannot overflow between rescalings.
 // ============================================================================================================
-__global__ void __launch_bounds__(128) bisect_topk_kernel(const double* __restrict__ diag,
-                                                          const double* __restrict__ off, int n, int k,
-                                                          double* __restrict__ evals, double* __restrict__ tnorm) {
+constexpr int kBisThreads = 128;
+
+__global__ void __launch_bounds__(kBisThreads) bisect_topk_kernel(const double* __restrict__ diag,
+                                                                  const double* __restrict__ off, int n, int k,
+                                                                  double* __restrict__ evals,
+                                                                  double* __restrict__ tnorm) {
   extern __shared__ double sh[];
   double* d = sh;
-  double* e2 = sh + n;  // e2[i] = off[i-1]^2 for i>=1
-  __shared__ double red[4];
-  double gl = INFINITY, gu = -INFINITY, emax = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  double* e2 = sh + n;  // e2[i] = (off[i-1]/||T||)^2 for i>=1
+  __shared__ double s_gl[kBisThreads / 32], s_gu[kBisThreads / 32];
+  double gl = INFINITY, gu = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += kBisThreads) {
     const double di = diag[i];
-    const double el = i > 0 ? off[i - 1] : 0.0, er = i < n - 1 ? off[i] : 0.0;
-    d[i] = di;
-    e2[i] = el * el;
-    gl = fmin(gl, di - fabs(el) - fabs(er));
-    gu = fmax(gu, di + fabs(el) + fabs(er));
-    emax = fmax(emax, fabs(el));
+    const double el = i > 0 ? fabs(off[i - 1]) : 0.0, er = i < n - 1 ? fabs(off[i]) : 0.0;
+    gl = fmin(gl, di - el - er);
+    gu = fmax(gu, di + el + er);
   }
-  // block min/max
   for (int o = 16; o > 0; o >>= 1) {
     gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
     gu = fmax(gu, __shfl_xor_sync(0xffffffffu, gu, o));
-    emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
   }
-  __shared__ double s_gl[4], s_gu[4], s_em[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) {
     s_gl[warp] = gl;
     s_gu[warp] = gu;
-    s_em[warp] = emax;
   }
   __syncthreads();
-  gl = fmin(fmin(s_gl[0], s_gl[1]), fmin(s_gl[2], s_gl[3]));
-  gu = fmax(fmax(s_gu[0], s_gu[1]), fmax(s_gu[2], s_gu[3]));
-  emax = fmax(fmax(s_em[0], s_em[1]), fmax(s_em[2], s_em[3]));
-  (void)red;
-  const double tn = fmax(fabs(gl), fabs(gu));
-  const double pivmin = fmax(2.2250738585072014e-308 * fmax(1.0, emax * emax), 1e-300);
-  if (blockIdx.x == 0 && threadIdx.x == 0) tnorm[0] = tn;
-  const int which = blockIdx.x * 4 + warp;  // which-th largest
+  gl = s_gl[0];
+  gu = s_gu[0];
+  for (int w = 1; w < kBisThreads / 32; ++w) {
+    gl = fmin(gl, s_gl[w]);
+    gu = fmax(gu, s_gu[w]);
+  }
+  double tn = fmax(fabs(gl), fabs(gu));
+  if (!(tn > 0.0)) tn = 1.0;
+  const double inv = 1.0 / tn;
+  for (int i = threadIdx.x; i < n; i += kBisThreads) {
+    d[i] = diag[i] * inv;
+    const double e = i > 0 ? off[i - 1] * inv : 0.0;
+    e2[i] = e * e;
+  }
+  __syncthreads();
+  const int which = blockIdx.x;  // which-th largest
+  if (which == 0 && threadIdx.x == 0) tnorm[0] = tn;
   if (which >= k) return;
   const int idx = n - 1 - which;  // ascending 0-based index
-  double lo = gl - 2.0 * tn * 2.220446049250313e-16 * n - 2.0 * pivmin;
-  double hi = gu + 2.0 * tn * 2.220446049250313e-16 * n + 2.0 * pivmin;
-  for (int round = 0; round < 13; ++round) {
-    const double x = lo + (hi - lo) * (static_cast<double>(lane + 1) / 33.0);
-    double q = d[0] - x;
-    int cnt = q < 0.0;
+  const double slack = 4.0 * 2.220446049250313e-16 * n;
+  double lo = gl * inv - slack, hi = gu * inv + slack;
+  for (int round = 0; round < 9; ++round) {
+    const double x = lo + (hi - lo) * (static_cast<double>(threadIdx.x + 1) / (kBisThreads + 1));
+    double pm1 = 1.0, p = d[0] - x;
+    int sgn = (p > 0.0) ? 1 : -1;  // p == 0 counts as a sign change against p_0 = 1
+    int cnt = sgn < 0;
     for (int i = 1; i < n; ++i) {
-      if (fabs(q) < pivmin) q = -pivmin;
-      q = d[i] - x - e2[i] / q;
-      cnt += q < 0.0;
+      const double pn = fma(d[i] - x, p, -e2[i] * pm1);
+      const int s = pn > 0.0 ? 1 : (pn < 0.0 ? -1 : -sgn);
+      cnt += (s != sgn);
+      sgn = s;
+      pm1 = p;
+      p = pn;
+      if ((i & 7) == 0) {
+        const double a = fabs(p);
+        if (a > 1e100) {
+          p *= 1e-100;
+          pm1 *= 1e-100;
+        } else if (a < 1e-100) {
+          p *= 1e100;
+          pm1 *= 1e100;
+        }
+      }
     }
-    // lanes with cnt <= idx lie at or below the eigenvalue
-    const unsigned below = __ballot_sync(0xffffffffu, cnt <= idx);
-    const int nb = __popc(below);  // monotone: lanes 0..nb-1
-    const double new_lo = nb > 0 ? __shfl_sync(0xffffffffu, x, nb - 1) : lo;
-    const double new_hi = nb < 32 ? __shfl_sync(0xffffffffu, x, nb < 32 ? nb : 31) : hi;
+    // threads whose shift is at or below the eigenvalue see cnt <= idx; monotone in the thread index
+    const int nb = __syncthreads_count(cnt <= idx);
+    const double w = (hi - lo) / (kBisThreads + 1);
+    const double new_lo = nb > 0 ? lo + w * nb : lo;
+    const double new_hi = nb < kBisThreads ? lo + w * (nb + 1) : hi;
     lo = new_lo;
     hi = new_hi;
   }
-  if (lane == 0) evals[which] = 0.5 * (lo + hi);
+  if (threadIdx.x == 0) evals[which] = 0.5 * (lo + hi) * tn;
 }
 
 // ============================================================================================================
-// 6. inverse iteration on the tridiagonal (one thread per eigenvector; Gaussian elimination with partial pivoting
-//    as in LAPACK dgtsv), pseudo-random start, 3 solves.  work: [k][5][n] doubles.
+// 6. inverse iteration on the tridiagonal: one warp per eigenvector, everything in shared memory.
+//    (T - lambda I) is factored ONCE with partial pivoting (LAPACK dgttrf), then three solves (dgttrs) from a
+//    pseudo-random start, normalising in between.  Lane 0 walks the recurrences, the warp does the vector parts.
+//    dynamic smem: dd, rd, du, du2, fl (multipliers) [n doubles each], b [n], piv [n bytes]
 // ============================================================================================================
 __device__ __forceinline__ double hash_unit(uint32_t a, uint32_t b) {
   uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u;
@@ -465,69 +488,116 @@ __device__ __forceinline__ double hash_unit(uint32_t a, uint32_t b) {
   return (static_cast<double>(h) / 4294967296.0) - 0.5;
 }
 
-__global__ void inverse_iteration_kernel(const double* __restrict__ diag, const double* __restrict__ off, int n, int k,
-                                         const double* __restrict__ evals, const double* __restrict__ tnorm,
-                                         double* __restrict__ work, double* __restrict__ Z) {
-  const int which = blockIdx.x * blockDim.x + threadIdx.x;
-  if (which >= k) return;
-  double* dl = work + static_cast<size_t>(which) * 5 * n;
-  double* dd = dl + n;
-  double* du = dd + n;
+__global__ void __launch_bounds__(32) inverse_iteration_kernel(const double* __restrict__ diag,
+                                                               const double* __restrict__ off, int n, int k,
+                                                               const double* __restrict__ evals,
+                                                               const double* __restrict__ tnorm,
+                                                               double* __restrict__ Z) {
+  extern __shared__ double shi[];
+  double* dd = shi;
+  double* rd = dd + n;
+  double* du = rd + n;
   double* du2 = du + n;
-  double* b = du2 + n;
+  double* fl = du2 + n;
+  double* b = fl + n;
+  uint8_t* piv = reinterpret_cast<uint8_t*>(b + n);
+  const int which = blockIdx.x;
+  if (which >= k) return;
+  const int lane = threadIdx.x;
   const double lam = evals[which];
   const double pivmin = fmax(tnorm[0], 1e-300) * 2.220446049250313e-16;
-  for (int i = 0; i < n; ++i) b[i] = hash_unit(static_cast<uint32_t>(which), static_cast<uint32_t>(i));
-  for (int iter = 0; iter < 3; ++iter) {
-    for (int i = 0; i < n; ++i) {
-      dd[i] = diag[i] - lam;
-      if (i < n - 1) {
-        dl[i] = off[i];
-        du[i] = off[i];
-      }
-      du2[i] = 0.0;
-    }
-    // forward elimination with partial pivoting
+  for (int i = lane; i < n; i += 32) {
+    dd[i] = diag[i] - lam;
+    du[i] = i < n - 1 ? off[i] : 0.0;
+    fl[i] = i < n - 1 ? off[i] : 0.0;  // sub-diagonal, overwritten by the multipliers
+    du2[i] = 0.0;
+    piv[i] = 0;
+    b[i] = hash_unit(static_cast<uint32_t>(which), static_cast<uint32_t>(i));
+  }
+  __syncwarp();
+  if (lane == 0) {
+    // dgttrf
+    double di = dd[0];
     for (int i = 0; i < n - 1; ++i) {
-      if (fabs(dd[i]) >= fabs(dl[i])) {
-        if (fabs(dd[i]) < pivmin) dd[i] = copysign(pivmin, dd[i] == 0.0 ? 1.0 : dd[i]);
-        const double f = dl[i] / dd[i];
-        dd[i + 1] -= f * du[i];
-        b[i + 1] -= f * b[i];
-        du2[i] = 0.0;
+      const double li = fl[i];
+      double dn = dd[i + 1];
+      if (fabs(di) >= fabs(li)) {
+        if (fabs(di) < pivmin) di = copysign(pivmin, di == 0.0 ? 1.0 : di);
+        const double f = li / di;
+        fl[i] = f;
+        dd[i] = di;
+        rd[i] = 1.0 / di;
+        dn -= f * du[i];
       } else {
-        const double f = dd[i] / dl[i];
-        dd[i] = dl[i];
-        const double tmp = dd[i + 1];
-        dd[i + 1] = du[i] - f * tmp;
+        const double f = di / li;
+        dd[i] = li;
+        rd[i] = 1.0 / li;
+        fl[i] = f;
+        const double tmp = du[i];
+        du[i] = dn;
+        dn = tmp - f * dn;
         if (i < n - 2) {
           du2[i] = du[i + 1];
-          du[i + 1] = -f * du2[i];
+          du[i + 1] = -f * du[i + 1];
         }
-        du[i] = tmp;
-        const double tb = b[i];
-        b[i] = b[i + 1];
-        b[i + 1] = tb - f * b[i + 1];
+        piv[i] = 1;
+      }
+      di = dn;
+    }
+    if (fabs(di) < pivmin) di = copysign(pivmin, di == 0.0 ? 1.0 : di);
+    dd[n - 1] = di;
+    rd[n - 1] = 1.0 / di;
+  }
+  __syncwarp();
+  for (int iter = 0; iter < 3; ++iter) {
+    if (lane == 0) {
+      // dgttrs: L solve
+      double bi = b[0];
+      for (int i = 0; i < n - 1; ++i) {
+        const double bn = b[i + 1];
+        if (!piv[i]) {
+          b[i] = bi;
+          bi = bn - fl[i] * bi;
+        } else {
+          b[i] = bn;
+          bi = bi - fl[i] * bn;
+        }
+      }
+      b[n - 1] = bi;
+      // U solve
+      double x1 = b[n - 1] * rd[n - 1];
+      b[n - 1] = x1;
+      double x2 = 0.0;
+      if (n > 1) {
+        const double x0 = (b[n - 2] - du[n - 2] * x1) * rd[n - 2];
+        b[n - 2] = x0;
+        x2 = x1;
+        x1 = x0;
+      }
+      for (int i = n - 3; i >= 0; --i) {
+        const double x0 = (b[i] - du[i] * x1 - du2[i] * x2) * rd[i];
+        b[i] = x0;
+        x2 = x1;
+        x1 = x0;
       }
     }
-    if (fabs(dd[n - 1]) < pivmin) dd[n - 1] = copysign(pivmin, dd[n - 1] == 0.0 ? 1.0 : dd[n - 1]);
-    // back substitution
-    b[n - 1] /= dd[n - 1];
-    if (n > 1) b[n - 2] = (b[n - 2] - du[n - 2] * b[n - 1]) / dd[n - 2];
-    for (int i = n - 3; i >= 0; --i) b[i] = (b[i] - du[i] * b[i + 1] - du2[i] * b[i + 2]) / dd[i];
+    __syncwarp();
     // normalise (max-abs first to stay in range)
     double mx = 0.0;
-    for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(b[i]));
-    const double inv = mx > 0.0 ? 1.0 / mx : 1.0;
-    double s = 0.0;
-    for (int i = 0; i < n; ++i) {
-      b[i] *= inv;
-      s += b[i] * b[i];
+    for (int i = lane; i < n; i += 32) mx = fmax(mx, fabs(b[i]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const double invm = mx > 0.0 ? 1.0 / mx : 1.0;
+    double ss = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      const double v = b[i] * invm;
+      ss += v * v;
     }
-    const double rn = 1.0 / sqrt(s);
-    for (int i = 0; i < n; ++i) b[i] *= rn;
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const double rn = invm / sqrt(ss);
+    for (int i = lane; i < n; i += 32) b[i] *= rn;
+    __syncwarp();
   }
-  for (int i = 0; i < n; ++i) Z[static_cast<size_t>(which) * n + i] = b[i];
+  for (int i = lane; i < n; i += 32) Z[static_cast<size_t>(which) * n + i] = b[i];
 }
 
 // Re-orthogonalise eigenvectors whose eigenvalues are numerically degenerate (|gap| < 1e-8 ||T||); single CTA.
@@ -561,37 +631,68 @@ __global__ void __launch_bounds__(256) cluster_mgs_kernel(double* __restrict__ Z
 }
 
 // ============================================================================================================
-// 7. back-transform y = H_0 H_1 ... H_{n-2} z (one CTA per eigenvector), then sklearn's sign convention:
-//    the entry of largest magnitude (first on ties) is made positive.
+// 7. back-transform y = H_0 H_1 ... H_{n-2} z (one CTA per eigenvector; z lives in registers, the next reflector
+//    row is prefetched while the current one is reduced), then sklearn's sign convention: the entry of largest
+//    magnitude (first on ties) is made positive.
 // ============================================================================================================
-__global__ void __launch_bounds__(256) back_transform_kernel(const double* __restrict__ V,
-                                                             const double* __restrict__ tau, int n,
-                                                             const double* __restrict__ Z,
-                                                             double* __restrict__ comps) {
-  extern __shared__ double z[];
-  __shared__ double red[8];
-  __shared__ double s_best;
+constexpr int kBtThreads = 256;
+constexpr int kBtPerThread = 16;  // supports n <= 4096
+
+__global__ void __launch_bounds__(kBtThreads) back_transform_kernel(const double* __restrict__ V,
+                                                                    const double* __restrict__ tau, int n,
+                                                                    const double* __restrict__ Z,
+                                                                    double* __restrict__ comps) {
+  __shared__ double red[2][kBtThreads / 32];
+  __shared__ double wb[kBtThreads / 32];
+  __shared__ int wi[kBtThreads / 32];
   __shared__ int s_idx;
   const int which = blockIdx.x;
-  for (int c = threadIdx.x; c < n; c += blockDim.x) z[c] = Z[static_cast<size_t>(which) * n + c];
-  __syncthreads();
-  for (int t = n - 2; t >= 0; --t) {
-    const double tt = tau[t];
-    if (tt == 0.0) continue;  // uniform across the block
-    const double* vt = V + static_cast<size_t>(t) * n;
-    double part = 0.0;
-    for (int c = t + 1 + threadIdx.x; c < n; c += blockDim.x) part += vt[c] * z[c];
-    const double s = tt * block_sum(part, red);
-    for (int c = t + 1 + threadIdx.x; c < n; c += blockDim.x) z[c] -= s * vt[c];
-    __syncthreads();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double z[kBtPerThread], vc[kBtPerThread], vnx[kBtPerThread];
+#pragma unroll
+  for (int j = 0; j < kBtPerThread; ++j) {
+    const int c = tid + kBtThreads * j;
+    z[j] = c < n ? Z[static_cast<size_t>(which) * n + c] : 0.0;
   }
-  __syncthreads();
+  auto load_row = [&](int t, double (&dst)[kBtPerThread]) {
+    const double* vt = V + static_cast<size_t>(t) * n;
+#pragma unroll
+    for (int j = 0; j < kBtPerThread; ++j) {
+      const int c = tid + kBtThreads * j;
+      dst[j] = (c > t && c < n) ? vt[c] : 0.0;
+    }
+  };
+  if (n >= 2) load_row(n - 2, vc);
+  int parity = 0;
+  for (int t = n - 2; t >= 0; --t) {
+    if (t > 0) load_row(t - 1, vnx);
+    const double tt = tau[t];
+    double part = 0.0;
+#pragma unroll
+    for (int j = 0; j < kBtPerThread; ++j) part += vc[j] * z[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) red[parity][warp] = part;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBtThreads / 32; ++w) s += red[parity][w];
+    s *= tt;
+#pragma unroll
+    for (int j = 0; j < kBtPerThread; ++j) {
+      z[j] -= s * vc[j];
+      vc[j] = vnx[j];
+    }
+    parity ^= 1;
+  }
   // argmax |z| (first occurrence)
   double best = -1.0;
   int bidx = n;
-  for (int c = threadIdx.x; c < n; c += blockDim.x) {
-    const double a = fabs(z[c]);
-    if (a > best) {
+#pragma unroll
+  for (int j = 0; j < kBtPerThread; ++j) {
+    const int c = tid + kBtThreads * j;
+    const double a = fabs(z[j]);
+    if (c < n && (a > best || (a == best && c < bidx))) {
       best = a;
       bidx = c;
     }
@@ -604,28 +705,41 @@ __global__ void __launch_bounds__(256) back_transform_kernel(const double* __res
       bidx = oi;
     }
   }
-  __shared__ double wb[8];
-  __shared__ int wi[8];
-  if ((threadIdx.x & 31) == 0) {
-    wb[threadIdx.x >> 5] = best;
-    wi[threadIdx.x >> 5] = bidx;
+  if (lane == 0) {
+    wb[warp] = best;
+    wi[warp] = bidx;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double b = wb[0];
+  if (tid == 0) {
+    double bb = wb[0];
     int bi = wi[0];
-    for (int i = 1; i < 8; ++i)
-      if (wb[i] > b || (wb[i] == b && wi[i] < bi)) {
-        b = wb[i];
+    for (int i = 1; i < kBtThreads / 32; ++i)
+      if (wb[i] > bb || (wb[i] == bb && wi[i] < bi)) {
+        bb = wb[i];
         bi = wi[i];
       }
-    s_best = b;
     s_idx = bi;
   }
   __syncthreads();
-  (void)s_best;
-  const double sign = z[s_idx] < 0.0 ? -1.0 : 1.0;
-  for (int c = threadIdx.x; c < n; c += blockDim.x) comps[static_cast<size_t>(which) * n + c] = sign * z[c];
+  // the owner of the arg-max entry publishes the sign
+  __shared__ double s_sign;
+  {
+    const int c = s_idx;
+    if (c % kBtThreads == tid) {
+      double val = 0.0;
+#pragma unroll
+      for (int j = 0; j < kBtPerThread; ++j)
+        if (tid + kBtThreads * j == c) val = z[j];
+      s_sign = val < 0.0 ? -1.0 : 1.0;
+    }
+  }
+  __syncthreads();
+  const double sign = s_sign;
+#pragma unroll
+  for (int j = 0; j < kBtPerThread; ++j) {
+    const int c = tid + kBtThreads * j;
+    if (c < n) comps[static_cast<size_t>(which) * n + c] = sign * z[j];
+  }
 }
 
 // clip negative eigenvalues to zero (sklearn _pca.py:626)
@@ -817,22 +931,23 @@ int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scat
                                      static_cast<int>(bis_smem)));
     bis_cfg = bis_smem;
   }
-  bisect_topk_kernel<<<ceil_div(k, 4), 128, bis_smem, st>>>(diag, off, n, k, d_eigenvalues, scal + 1);
+  bisect_topk_kernel<<<k, kBisThreads, bis_smem, st>>>(diag, off, n, k, d_eigenvalues, scal + 1);
   IRP_CUDA_OK(cudaGetLastError());
   // ---- eigenvectors of T ----
-  inverse_iteration_kernel<<<ceil_div(k, 32), 32, 0, st>>>(diag, off, n, k, d_eigenvalues, scal + 1, work, Z);
+  const size_t ii_smem = 6 * static_cast<size_t>(n) * sizeof(double) + static_cast<size_t>(n) + 16;
+  static size_t ii_cfg = 0;
+  if (ii_smem > 32 * 1024 && ii_smem > ii_cfg) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(inverse_iteration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(ii_smem)));
+    ii_cfg = ii_smem;
+  }
+  (void)work;
+  inverse_iteration_kernel<<<k, 32, ii_smem, st>>>(diag, off, n, k, d_eigenvalues, scal + 1, Z);
   IRP_CUDA_OK(cudaGetLastError());
   cluster_mgs_kernel<<<1, 256, 0, st>>>(Z, n, k, d_eigenvalues, scal + 1);
   IRP_CUDA_OK(cudaGetLastError());
   // ---- back-transform + sign ----
-  const size_t bt_smem = static_cast<size_t>(n) * sizeof(double);
-  static size_t bt_cfg = 0;
-  if (bt_smem > 32 * 1024 && bt_smem > bt_cfg) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(back_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(bt_smem)));
-    bt_cfg = bt_smem;
-  }
-  back_transform_kernel<<<k, 256, bt_smem, st>>>(V, tau, n, Z, d_components);
+  back_transform_kernel<<<k, kBtThreads, 0, st>>>(V, tau, n, Z, d_components);
   IRP_CUDA_OK(cudaGetLastError());
   clip_evals_kernel<<<ceil_div(k, 128), 128, 0, st>>>(d_eigenvalues, k);
   IRP_CUDA_OK(cudaGetLastError());
