@@ -29,6 +29,7 @@ constexpr int kChunkRows = 24;       // source rows horizontally filtered per pa
 constexpr int kRowElems = kCrop * 3; // 672 (x, c) elements per filtered row
 constexpr int kThreads = 256;
 constexpr int kElemsPerThread = 3;   // ceil(672 / 256)
+constexpr int kFastTaps = 6;         // tap bound of the shared-memory-staged fast path (downscale <= 2.5x)
 
 // plan layout per image (int32): [axis 0 | axis 1], each axis: first[224], count[224], coef[224][max_taps]
 __host__ __device__ inline size_t plan_ints_per_axis(int max_taps) { return static_cast<size_t>(kCrop) * (2 + max_taps); }
@@ -61,7 +62,8 @@ __host__ __device__ inline Geometry compute_geometry(int h, int w) {
 }
 
 __global__ void resample_plan_kernel(const int32_t* __restrict__ hw, int n_images, int max_taps,
-                                     int32_t* __restrict__ plan, int32_t* __restrict__ status) {
+                                     int32_t* __restrict__ plan, int32_t* __restrict__ status,
+                                     int32_t* __restrict__ img_taps) {
   const int img = blockIdx.x;
   const int j = threadIdx.x;
   if (img >= n_images || j >= 2 * kCrop) return;
@@ -82,6 +84,7 @@ __global__ void resample_plan_kernel(const int32_t* __restrict__ hw, int n_image
     first[o] = xx;
     count[o] = 1;
     coef[0] = 1 << kPrecisionBits;
+    atomicMax(&img_taps[img], 1);
     return;
   }
   // Pillow precompute_coeffs (bilinear: support 1.0), evaluated in fp64 without FMA contraction.
@@ -117,6 +120,7 @@ __global__ void resample_plan_kernel(const int32_t* __restrict__ hw, int n_image
   }
   first[o] = xmin;
   count[o] = n;
+  atomicMax(&img_taps[img], n);
 }
 
 __device__ __forceinline__ int clip8_fixed(int acc) {
@@ -131,8 +135,10 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(const uint8_t* __res
                                                             const int64_t* __restrict__ offsets,
                                                             const int32_t* __restrict__ hw, int max_taps,
                                                             const int32_t* __restrict__ plan,
+                                                            const int32_t* __restrict__ img_taps,
                                                             __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t smem[];
+  if (img_taps[blockIdx.y] <= kFastTaps) return;  // handled by resample_fast_kernel
   const int T = max_taps;
   int32_t* hfirst = reinterpret_cast<int32_t*>(smem);
   int32_t* hcount = hfirst + kCrop;
@@ -279,6 +285,220 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(const uint8_t* __res
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fast path (<= kFastTaps taps per output, i.e. downscale factors up to 2.5): the source rows a band needs are
+// first staged in shared memory with 16-byte coalesced loads (rows are realigned to 16 bytes, the per-row byte
+// shift is remembered), the horizontal pass then reads bytes from shared memory with its tap weights held in
+// registers, the vertical pass reads the uint8 intermediate rows from shared memory.
+// dynamic smem: int32 vfirst[TH], vcount[TH], vcoef[TH*8], rshift[kFastRows]; bf16 lut[768];
+//               uint8 hbuf[kFastRows*672]; uint8 inbuf[kFastInBytes + 64]; bf16 obuf[...]
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kFastRows = 24;             // source rows staged per pass
+constexpr int kFastInBytes = 28 * 1024;   // staging budget for those rows
+
+// NT = tap count every output of this image is padded to (zero weights beyond its own count), so the inner
+// loops are fully unrolled without predication.
+template <int LAYOUT, int TH, int NT>
+__device__ __forceinline__ void resample_fast_body(uint8_t* smem, const uint8_t* __restrict__ pixels,
+                                                   const int64_t* __restrict__ offsets,
+                                                   const int32_t* __restrict__ hw, int max_taps,
+                                                   const int32_t* __restrict__ plan,
+                                                   __nv_bfloat16* __restrict__ out) {
+  const int img = blockIdx.y;
+  const int T = max_taps;
+  int32_t* vfirst = reinterpret_cast<int32_t*>(smem);
+  int32_t* vcount = vfirst + TH;
+  int32_t* vcoef = vcount + TH;                 // [TH][kFastTaps] (first NT used)
+  int32_t* rshift = vcoef + TH * kFastTaps;     // [kFastRows]
+  __nv_bfloat16* lut = reinterpret_cast<__nv_bfloat16*>(rshift + kFastRows);
+  uint8_t* hbuf = reinterpret_cast<uint8_t*>(lut + 768);
+  uint8_t* inbuf = hbuf + kFastRows * kRowElems;
+  __nv_bfloat16* obuf = reinterpret_cast<__nv_bfloat16*>(inbuf + kFastInBytes + 64);
+
+  const int band = blockIdx.x;
+  const int y0 = band * TH;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int w = hw[2 * img + 1];
+  const uint8_t* src = pixels + offsets[img];
+  const size_t row_bytes = static_cast<size_t>(w) * 3;
+  const int32_t* plan_h = plan + (static_cast<size_t>(img) * 2 + 0) * plan_ints_per_axis(T);
+  const int32_t* plan_v = plan + (static_cast<size_t>(img) * 2 + 1) * plan_ints_per_axis(T);
+
+  // ---- vertical tables, LUT ----
+  if (tid < TH) {
+    vfirst[tid] = plan_v[y0 + tid];
+    vcount[tid] = plan_v[kCrop + y0 + tid];
+  }
+  for (int i = tid; i < TH * kFastTaps; i += kThreads) {
+    const int y = i / kFastTaps, t = i % kFastTaps;
+    // weights past the output's own tap count are not written by the plan kernel: pad with zeros
+    vcoef[i] = t < plan_v[kCrop + y0 + y] ? plan_v[2 * kCrop + static_cast<size_t>(y0 + y) * T + t] : 0;
+  }
+  for (int i = tid; i < 768; i += kThreads) {
+    const int c = i >> 8, v = i & 255;
+    const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+    const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+    const float f = __fdiv_rn(static_cast<float>(v), 255.0f);
+    lut[i] = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(f, mean), stdv));
+  }
+  // ---- this thread's horizontal taps (fixed (x, c) elements for every row) ----
+  const int col_first = plan_h[0] * 3;                                      // first source byte any output needs
+  const int col_last = (plan_h[kCrop - 1] + plan_h[2 * kCrop - 1]) * 3;     // one past the last
+  const int width_bytes = col_last - col_first;
+  const int pitch = ((width_bytes + 15) & ~15) + 16;
+  int hoff[kElemsPerThread], hcf[kElemsPerThread][NT];
+#pragma unroll
+  for (int k = 0; k < kElemsPerThread; ++k) {
+    const int e = min(tid + k * kThreads, kRowElems - 1);  // surplus threads shadow the last element
+    const int x = e / 3, c = e - x * 3;
+    const int n = plan_h[kCrop + x];
+    hoff[k] = plan_h[x] * 3 + c - col_first;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) hcf[k][t] = t < n ? plan_h[2 * kCrop + static_cast<size_t>(x) * T + t] : 0;
+  }
+  __syncthreads();
+
+  int row_lo = vfirst[0], row_hi = vfirst[0] + vcount[0];
+#pragma unroll
+  for (int y = 1; y < TH; ++y) {
+    row_lo = min(row_lo, vfirst[y]);
+    row_hi = max(row_hi, vfirst[y] + vcount[y]);
+  }
+  int rows_cap = kFastInBytes / pitch;
+  if (rows_cap > kFastRows) rows_cap = kFastRows;
+
+  int acc[TH][kElemsPerThread];
+#pragma unroll
+  for (int y = 0; y < TH; ++y)
+#pragma unroll
+    for (int k = 0; k < kElemsPerThread; ++k) acc[y][k] = 1 << (kPrecisionBits - 1);
+
+  const int vec_per_row = pitch >> 4;
+  for (int chunk = row_lo; chunk < row_hi; chunk += rows_cap) {
+    const int rows = min(rows_cap, row_hi - chunk);
+    // ---- stage source rows: 16-byte loads from the 16-byte-aligned address at or before the first byte ----
+    for (int r = warp; r < rows; r += kThreads / 32) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(src + static_cast<size_t>(chunk + r) * row_bytes + col_first);
+      const uintptr_t al = a & ~static_cast<uintptr_t>(15);
+      const int shift = static_cast<int>(a - al);
+      if (lane == 0) rshift[r] = shift;
+      const int nvec = (shift + width_bytes + 15) >> 4;
+      const uint4* gp = reinterpret_cast<const uint4*>(al);
+      uint4* sp = reinterpret_cast<uint4*>(inbuf + static_cast<size_t>(r) * pitch);
+      for (int v = lane; v < nvec && v < vec_per_row; v += 32) sp[v] = __ldg(gp + v);
+    }
+    __syncthreads();
+    // ---- horizontal pass from shared memory ----
+    for (int r = 0; r < rows; ++r) {
+      const uint8_t* rp = inbuf + static_cast<size_t>(r) * pitch + rshift[r];
+#pragma unroll
+      for (int k = 0; k < kElemsPerThread; ++k) {
+        const int e = tid + k * kThreads;
+        const uint8_t* sp = rp + hoff[k];
+        int a = 1 << (kPrecisionBits - 1);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) a += static_cast<int>(sp[3 * t]) * hcf[k][t];  // padded taps read slack, weight 0
+        if (e < kRowElems) hbuf[r * kRowElems + e] = static_cast<uint8_t>(clip8_fixed(a));
+      }
+    }
+    __syncthreads();
+    // ---- vertical pass: taps that fall in this chunk ----
+#pragma unroll
+    for (int y = 0; y < TH; ++y) {
+      const int vf = vfirst[y];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int rr = vf + t - chunk;  // staged row of this tap; weight is 0 beyond the output's own count
+        const int cf = (rr >= 0 && rr < rows) ? vcoef[y * kFastTaps + t] : 0;
+        const uint8_t* hp = hbuf + min(max(rr, 0), kFastRows - 1) * kRowElems;
+#pragma unroll
+        for (int k = 0; k < kElemsPerThread; ++k) {
+          const int e = min(tid + k * kThreads, kRowElems - 1);
+          acc[y][k] += static_cast<int>(hp[e]) * cf;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- normalise + stage + 16-byte stores ----
+  if (LAYOUT == IRP_LAYOUT_NHWC4P) {
+    uint32_t* z = reinterpret_cast<uint32_t*>(obuf);
+    for (int i = tid; i < TH * kPad * 2; i += kThreads) z[i] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int y = 0; y < TH; ++y)
+#pragma unroll
+      for (int k = 0; k < kElemsPerThread; ++k) {
+        const int e = tid + k * kThreads;
+        if (e < kRowElems) {
+          const int x = e / 3, c = e - x * 3;
+          obuf[(y * kPad + 3 + x) * 4 + c] = lut[c * 256 + clip8_fixed(acc[y][k])];
+        }
+      }
+    __syncthreads();
+    constexpr int kVecPerRow = kPad * 8 / 16;
+    uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * kPad + 3 + y0) * kPad * 4);
+    const uint4* sv = reinterpret_cast<const uint4*>(obuf);
+    for (int i = tid; i < TH * kVecPerRow; i += kThreads) dst[i] = sv[i];
+    if (band == 0) {
+      uint4* top = reinterpret_cast<uint4*>(out + static_cast<size_t>(img) * kPad * kPad * 4);
+      for (int i = tid; i < 3 * kVecPerRow; i += kThreads) top[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (band == gridDim.x - 1) {
+      uint4* bot = reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * kPad + 3 + kCrop) * kPad * 4);
+      for (int i = tid; i < 3 * kVecPerRow; i += kThreads) bot[i] = make_uint4(0, 0, 0, 0);
+    }
+  } else {
+#pragma unroll
+    for (int y = 0; y < TH; ++y)
+#pragma unroll
+      for (int k = 0; k < kElemsPerThread; ++k) {
+        const int e = tid + k * kThreads;
+        if (e < kRowElems) {
+          const int x = e / 3, c = e - x * 3;
+          obuf[(c * TH + y) * kCrop + x] = lut[c * 256 + clip8_fixed(acc[y][k])];
+        }
+      }
+    __syncthreads();
+    constexpr int kVecPerRow = kCrop * 2 / 16;  // 28
+    const uint4* sv = reinterpret_cast<const uint4*>(obuf);
+    for (int i = tid; i < 3 * TH * kVecPerRow; i += kThreads) {
+      const int v = i % kVecPerRow;
+      const int y = (i / kVecPerRow) % TH;
+      const int c = i / (kVecPerRow * TH);
+      uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(img) * 3 + c) * kCrop + y0 + y) * kCrop);
+      dst[v] = sv[i];
+    }
+  }
+}
+
+template <int LAYOUT, int TH>
+__global__ void __launch_bounds__(kThreads, 3) resample_fast_kernel(const uint8_t* __restrict__ pixels,
+                                                                    const int64_t* __restrict__ offsets,
+                                                                    const int32_t* __restrict__ hw, int max_taps,
+                                                                    const int32_t* __restrict__ plan,
+                                                                    const int32_t* __restrict__ img_taps,
+                                                                    __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int nt = img_taps[blockIdx.y];
+  if (nt > kFastTaps) return;  // handled by the generic kernel
+  if (nt <= 2) resample_fast_body<LAYOUT, TH, 2>(smem, pixels, offsets, hw, max_taps, plan, out);
+  else if (nt == 3) resample_fast_body<LAYOUT, TH, 3>(smem, pixels, offsets, hw, max_taps, plan, out);
+  else if (nt == 4) resample_fast_body<LAYOUT, TH, 4>(smem, pixels, offsets, hw, max_taps, plan, out);
+  else if (nt == 5) resample_fast_body<LAYOUT, TH, 5>(smem, pixels, offsets, hw, max_taps, plan, out);
+  else resample_fast_body<LAYOUT, TH, 6>(smem, pixels, offsets, hw, max_taps, plan, out);
+}
+
+template <int TH>
+static size_t fast_smem_bytes(int layout) {
+  size_t b = (static_cast<size_t>(TH) * (2 + kFastTaps) + kFastRows) * 4 + 768 * 2;
+  b += static_cast<size_t>(kFastRows) * kRowElems + kFastInBytes + 64;
+  b += layout == IRP_LAYOUT_NHWC4P ? static_cast<size_t>(TH) * kPad * 4 * 2 : static_cast<size_t>(3) * TH * kCrop * 2;
+  return b;
+}
+
 static size_t resample_smem_bytes(int max_taps, int layout) {
   size_t b = static_cast<size_t>(kCrop) * (2 + max_taps) * 4 + static_cast<size_t>(kBandRows) * (2 + max_taps) * 4 +
              768 * 2;
@@ -294,11 +514,45 @@ static size_t resample_smem_bytes(int max_taps, int layout) {
 
 using namespace irp;
 
+template <int LAYOUT>
+static int launch_resample(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
+                           int max_taps, const int32_t* plan, const int32_t* img_taps, __nv_bfloat16* out,
+                           cudaStream_t st) {
+  constexpr int TH = 8;
+  {
+    const size_t smem = fast_smem_bytes<TH>(LAYOUT);
+    auto k = resample_fast_kernel<LAYOUT, TH>;
+    static bool cfg = false;
+    if (!cfg) {
+      IRP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      cfg = true;
+    }
+    dim3 grid(kCrop / TH, n_images);
+    k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, img_taps, out);
+    IRP_CUDA_OK(cudaGetLastError());
+  }
+  if (max_taps > kFastTaps) {  // some image may need the generic many-tap path
+    const size_t smem = resample_smem_bytes(max_taps, LAYOUT);
+    IRP_REQUIRE(smem <= 227 * 1024, "preprocess: max_taps %d needs %zu bytes of shared memory", max_taps, smem);
+    auto k = resample_kernel<LAYOUT>;
+    static size_t cfg = 0;
+    if (smem > 48 * 1024 && smem > cfg) {
+      IRP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      cfg = smem;
+    }
+    dim3 grid(kCrop / kBandRows, n_images);
+    k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, img_taps, out);
+    IRP_CUDA_OK(cudaGetLastError());
+  }
+  return IRP_OK;
+}
+
 extern "C" {
 
 size_t irp_preprocess_workspace_bytes(int n_images, int max_taps) {
   if (n_images <= 0 || max_taps <= 0) return 0;
-  return static_cast<size_t>(n_images) * 2 * plan_ints_per_axis(max_taps) * sizeof(int32_t) + 16;
+  return static_cast<size_t>(n_images) * 2 * plan_ints_per_axis(max_taps) * sizeof(int32_t) + 16 +
+         static_cast<size_t>(n_images) * sizeof(int32_t);
 }
 
 int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
@@ -313,28 +567,19 @@ int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int3
               "preprocess: workspace %zu < %zu bytes", workspace_bytes,
               irp_preprocess_workspace_bytes(n_images, max_taps));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // status word lives in the last 16 bytes of the workspace
+  // workspace: plan tables | status word (16 bytes) | per-image max tap count
   int32_t* plan = static_cast<int32_t*>(d_workspace);
-  int32_t* status =
-      reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_workspace) +
-                                 static_cast<size_t>(n_images) * 2 * plan_ints_per_axis(max_taps) * sizeof(int32_t));
-  IRP_CUDA_OK(cudaMemsetAsync(status, 0, 16, st));
-  resample_plan_kernel<<<n_images, 2 * kCrop, 0, st>>>(d_hw, n_images, max_taps, plan, status);
+  const size_t plan_bytes = static_cast<size_t>(n_images) * 2 * plan_ints_per_axis(max_taps) * sizeof(int32_t);
+  int32_t* status = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_workspace) + plan_bytes);
+  int32_t* img_taps = status + 4;
+  IRP_CUDA_OK(cudaMemsetAsync(status, 0, 16 + static_cast<size_t>(n_images) * sizeof(int32_t), st));
+  resample_plan_kernel<<<n_images, 2 * kCrop, 0, st>>>(d_hw, n_images, max_taps, plan, status, img_taps);
   IRP_CUDA_OK(cudaGetLastError());
-  const size_t smem = resample_smem_bytes(max_taps, out_layout);
-  IRP_REQUIRE(smem <= 227 * 1024, "preprocess: max_taps %d needs %zu bytes of shared memory", max_taps, smem);
-  dim3 grid(kCrop / kBandRows, n_images);
-  if (out_layout == IRP_LAYOUT_NHWC4P) {
-    auto k = resample_kernel<IRP_LAYOUT_NHWC4P>;
-    if (smem > 48 * 1024) IRP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, static_cast<__nv_bfloat16*>(d_out));
-  } else {
-    auto k = resample_kernel<IRP_LAYOUT_NCHW>;
-    if (smem > 48 * 1024) IRP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, static_cast<__nv_bfloat16*>(d_out));
-  }
-  IRP_CUDA_OK(cudaGetLastError());
-  return IRP_OK;
+  if (out_layout == IRP_LAYOUT_NHWC4P)
+    return launch_resample<IRP_LAYOUT_NHWC4P>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps,
+                                              static_cast<__nv_bfloat16*>(d_out), st);
+  return launch_resample<IRP_LAYOUT_NCHW>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps,
+                                          static_cast<__nv_bfloat16*>(d_out), st);
 }
 
 /* Host-side view of the resize/crop geometry (used by the Python mirror to size max_taps and by tests). */
