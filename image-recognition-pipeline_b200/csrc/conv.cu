@@ -9,6 +9,7 @@
 
 #include "common.h"
 #include "conv_gemm.cuh"
+#include "stem_conv.cuh"
 
 namespace irp {
 
@@ -474,10 +475,12 @@ static const std::vector<ConvSpec>& specs() {
 }  // namespace
 
 struct irp_resnet50 {
+  StemParams stem2;                    // stem_mode 2: patch-resident no-swizzle stem kernel
+  __nv_bfloat16* stem2_w = nullptr;    // its weights (core-matrix order)
   int max_batch = 0;
   int micro = 0;  // images per pass through the trunk (activation arena size); inter-layer tensors of one
                   // micro-batch are meant to stay resident in the 126 MB L2
-  int stem_mode = 0;  // 0: overlapping TMA view, 1: explicit im2col + flat GEMM
+  int stem_mode = 2;  // 2: patch-resident kernel (stem_conv.cuh), 0: overlapping TMA view, 1: im2col + flat GEMM
   std::vector<ConvPlan> plans;
   std::vector<__nv_bfloat16*> weights;
   std::vector<float*> biases;
@@ -500,7 +503,21 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x) {
   const int B = net->micro;
   enum { A = 0, Bb = 1, T1 = 2, T2 = 3, DS = 4, STEM = 5 };
   // stem
-  if (net->stem_mode == 0) {
+  if (net->stem_mode == 2) {
+    StemParams& sp2 = net->stem2;
+    memset(&sp2, 0, sizeof(sp2));
+    constexpr uint64_t P = IRP_PAD_HW;
+    uint64_t idims[3] = {P * 4, P, static_cast<uint64_t>(net->max_batch)};
+    uint64_t istr[2] = {P * 8, P * P * 8};
+    uint32_t ibox[3] = {kStemPatchW * 4, kStemPatchH, 1};
+    IRP_TRY(encode_bf16_map(&sp2.tmIn, const_cast<void*>(d_x), 3, idims, istr, ibox, 0));
+    uint64_t odims[4] = {64, 112, 112, static_cast<uint64_t>(B)};
+    uint64_t ostr[3] = {128, 112 * 128, 112 * 112 * 128};
+    uint32_t obox[4] = {64, kStemTileW, kStemTileH, 1};
+    IRP_TRY(encode_bf16_map(&sp2.tmOut, net->buf[STEM], 4, odims, ostr, obox, 128));
+    sp2.weights = net->stem2_w;
+    sp2.bias = net->biases[0];
+  } else if (net->stem_mode == 0) {
     IRP_TRY(plan_stem_tma(&net->plans[0], d_x, net->weights[0], net->biases[0], net->buf[STEM], B, net->max_batch));
   } else {
     IRP_TRY(plan_conv(&net->plans[0], net->im2col, net->weights[0], net->biases[0], nullptr, net->buf[STEM], B, 112,
@@ -565,7 +582,8 @@ int irp_resnet50_create(irp_resnet50** out, int max_batch) {
     if (v > 0 && v < max_batch) net->micro = v;
   }
   const char* mode = getenv("IRP_STEM_MODE");
-  net->stem_mode = (mode && mode[0] == '1') ? 1 : 0;
+  net->stem_mode = mode ? atoi(mode) : 2;
+  if (net->stem_mode < 0 || net->stem_mode > 2) net->stem_mode = 2;
   net->plans.resize(sp.size());
   net->weights.assign(sp.size(), nullptr);
   net->biases.assign(sp.size(), nullptr);
@@ -583,6 +601,7 @@ int irp_resnet50_create(irp_resnet50** out, int max_batch) {
                    weight_elems(sp[i], net->stem_mode) * sizeof(__nv_bfloat16));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&net->biases[i]), sp[i].cout * sizeof(float));
   }
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&net->stem2_w), kStemWeightBytes);
   if (e != cudaSuccess) {
     set_last_error("irp_resnet50_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     irp_resnet50_destroy(net);
@@ -596,6 +615,7 @@ void irp_resnet50_destroy(irp_resnet50* net) {
   if (!net) return;
   for (auto& b : net->buf) cudaFree(b);
   cudaFree(net->im2col);
+  cudaFree(net->stem2_w);
   for (auto* w : net->weights) cudaFree(w);
   for (auto* b : net->biases) cudaFree(b);
   delete net;
@@ -608,6 +628,12 @@ int irp_resnet50_load_conv(irp_resnet50* net, int index, const float* d_weight_o
   const ConvSpec& s = sp[index];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int kw_pad = s.ksize, cin_pad = s.cin;
+  if (s.role == 0) {
+    stem_fold_kernel<<<grid_for(kStemWeightBytes / 2, 256), 256, 0, st>>>(d_weight_oihw, d_gamma, d_beta, d_mean,
+                                                                          d_var, eps, net->stem2_w, net->biases[0]);
+    IRP_CUDA_OK(cudaGetLastError());
+    if (net->stem_mode == 2) return IRP_OK;
+  }
   if (s.role == 0 && net->stem_mode == 0) {
     kw_pad = 8;
     cin_pad = 4;
@@ -660,7 +686,23 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
           mb);
       IRP_CUDA_OK(cudaGetLastError());
     }
-    IRP_TRY(launch_conv(net->plans[0], mb, st, s0));
+    if (net->stem_mode == 2) {
+      StemParams sp2 = net->stem2;
+      sp2.batch = mb;
+      sp2.n_base = s0;
+      sp2.num_tiles = mb * 98;
+      static bool stem_cfg = false;
+      if (!stem_cfg) {
+        IRP_CUDA_OK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kStemSmemBytes));
+        stem_cfg = true;
+      }
+      const int grid = sp2.num_tiles < num_sms() ? sp2.num_tiles : num_sms();
+      stem_conv_kernel<<<grid, kStemThreads, kStemSmemBytes, st>>>(sp2);
+      IRP_CUDA_OK(cudaGetLastError());
+    } else {
+      IRP_TRY(launch_conv(net->plans[0], mb, st, s0));
+    }
     IRP_TRY(capture(0));
     {
       const long long total = static_cast<long long>(mb) * 56 * 56 * (64 / 8);

@@ -160,7 +160,7 @@ def t_stem(lib):
     err = (cap.float() - ref).abs()
     rel = (err.max() / ref.abs().max()).item()
     nan = torch.isnan(cap.float()).sum().item()
-    print(f"[stem mode={os.environ.get('IRP_STEM_MODE', '0')}] max_err/max_ref={rel:.3e} nan={nan} "
+    print(f"[stem mode={os.environ.get('IRP_STEM_MODE', 'default')}] max_err/max_ref={rel:.3e} nan={nan} "
           f"{'OK' if rel < 2e-2 and nan == 0 else 'FAIL'}", flush=True)
     ok &= rel < 2e-2 and nan == 0
     if not ok:
