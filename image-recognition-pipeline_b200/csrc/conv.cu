@@ -9,6 +9,7 @@
 
 #include "common.h"
 #include "conv_gemm.cuh"
+#include "conv_gemm2.cuh"
 #include "stem_conv.cuh"
 
 namespace irp {
@@ -142,6 +143,7 @@ enum ConvKind { kConvFlat = 0, kConvSpatial = 1, kConvStem = 2 };
 struct ConvPlan {
   ConvParams p;
   int bn_tile = 128;  // BN of the kernel instance
+  int version = 2;    // 2: CTA-pair kernel (conv_gemm2.cuh), 1: single-CTA kernel (conv_gemm.cuh)
   ConvKind kind = kConvFlat;
   bool has_res = false;
   int H = 0, W = 0, Ho = 0, Wo = 0, cin = 0, cout = 0, ksize = 1, stride = 1;
@@ -197,6 +199,41 @@ static int encode_out_maps(ConvPlan* plan, void* out, const void* residual, int 
   return IRP_OK;
 }
 
+// Kernel generation: 2 (CTA pairs) unless IRP_CONV_V1=1 asks for the single-CTA kernel (A/B comparisons).
+static int conv_version() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("IRP_CONV_V1");
+    v = (e && atoi(e) != 0) ? 1 : 2;
+  }
+  return v;
+}
+
+// Tile width of the CTA-pair kernel for a conv with `pair_m_tiles` 256-row tiles: the operand stream per tile is
+// proportional to (256 + BN) bytes per unit of K and the tiles run in ceil(tiles / pairs) waves, so pick the BN
+// that minimises waves * (256 + BN); ties go to the wider tile (fewer operand bytes per FLOP).
+static int choose_bn2(int cout, long long pair_m_tiles) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("IRP_CONV_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  const int pairs = num_sms() / 2;
+  int best = 64;
+  long long best_cost = -1;
+  for (int bn = 64; bn <= 256; bn *= 2) {
+    if (cout % bn != 0) continue;
+    if (forced > 0 && bn != forced && cout % forced == 0) continue;
+    const long long tiles = pair_m_tiles * (cout / bn);
+    const long long cost = ceil_div64(tiles, pairs) * (256 + bn);
+    if (best_cost < 0 || cost <= best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
 // Builds tensor maps + static fields. x/w/out pointers are baked into the maps / params.
 static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* bias, const void* residual,
                      void* out, int max_batch, int H, int W, int Cin, int Cout, int ksize, int stride, int relu) {
@@ -217,6 +254,7 @@ static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* 
   plan->ksize = ksize;
   plan->stride = stride;
   plan->max_batch = max_batch;
+  plan->version = conv_version();
   plan->bn_tile = (Cout % 128 == 0) ? 128 : 64;
   constexpr int BK = 64;
   p.cin = Cin;
@@ -280,13 +318,23 @@ static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* 
     }
   }
   p.a_box_bytes = p.bw * p.bh * p.bn * BK * 2;
+  if (plan->version == 2) {
+    const long long rows = static_cast<long long>(max_batch) * Ho * Wo;
+    const long long m_tiles = plan->kind == kConvFlat
+                                  ? ceil_div64(rows, kTileM)
+                                  : static_cast<long long>(ceil_div(Wo, p.bw)) * ceil_div(Ho, p.bh) *
+                                        ceil_div(max_batch, p.bn);
+    plan->bn_tile = choose_bn2(Cout, (m_tiles + 1) / 2);
+    p.n_tiles_n = Cout / plan->bn_tile;
+  }
   IRP_TRY(encode_out_maps(plan, out, residual, max_batch));
   // weights: [Cout][taps*Cin]
   {
     const uint64_t K = static_cast<uint64_t>(p.ntaps) * Cin;
     uint64_t dims[2] = {K, static_cast<uint64_t>(Cout)};
     uint64_t strides[1] = {K * 2};
-    uint32_t box[2] = {BK, static_cast<uint32_t>(plan->bn_tile)};
+    // the CTA-pair kernel loads half of the tile's weight rows per CTA
+    uint32_t box[2] = {BK, static_cast<uint32_t>(plan->version == 2 ? plan->bn_tile / 2 : plan->bn_tile)};
     IRP_TRY(encode_bf16_map(&p.tmB, const_cast<void*>(w), 2, dims, strides, box, 128));
   }
   return IRP_OK;
@@ -359,6 +407,46 @@ static int launch_clustered(const ConvParams& p, int shape, cudaStream_t stream)
   }
 }
 
+template <int BN, bool RES>
+static int launch_instance2(const ConvParams& p, cudaStream_t stream) {
+  using S = Conv2Smem<BN, RES>;
+  static bool configured = false;
+  auto kernel = conv_gemm2_kernel<BN, RES>;
+  if (!configured) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
+    configured = true;
+  }
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int num_groups = ((m_tiles + 1) / 2) * p.n_tiles_n;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (num_groups < pairs ? num_groups : pairs);
+  if (grid <= 0) return IRP_OK;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kConv2Threads);
+  cfg.dynamicSmemBytes = S::kTotalBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IRP_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
+  return IRP_OK;
+}
+
+template <bool RES>
+static int launch_conv2(const ConvParams& p, int bn, cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch_instance2<256, RES>(p, stream);
+    case 128: return launch_instance2<128, RES>(p, stream);
+    default: return launch_instance2<64, RES>(p, stream);
+  }
+}
+
 // Launch a planned conv on `batch` images (batch <= plan->max_batch).
 static int launch_conv(const ConvPlan& plan, int batch, cudaStream_t stream, int n_base = 0) {
   ConvParams p = plan.p;
@@ -376,6 +464,8 @@ static int launch_conv(const ConvPlan& plan, int batch, cudaStream_t stream, int
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
   const int k_blocks = p.ntaps * p.kc_blocks;
   if (plan.kind == kConvStem) return launch_instance<64, 32, true, false, 2>(p, stream);
+  if (plan.version == 2)
+    return plan.has_res ? launch_conv2<true>(p, plan.bn_tile, stream) : launch_conv2<false>(p, plan.bn_tile, stream);
   if (plan.bn_tile == 128) {
     const int shape = cluster_policy(plan, k_blocks);
     if (plan.has_res) return launch_clustered<128, true, 3>(p, shape, stream);

@@ -61,7 +61,7 @@ struct ConvSmem {
   static constexpr int kBudget = 220 * 1024 - NB * kStgBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kBarrierBytes = 512;
+  static constexpr int kBarrierBytes = 1024;  // mbarriers + TMEM slot (256 B), then the tile's bias slice (fp32)
   static constexpr int kTotalBytes = kStages * kStageBytes + NB * kStgBytes + kBarrierBytes + 1024;
   static_assert(kStages >= 2, "not enough shared memory for a pipeline");
 };
@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* res_full = tempty_bar + 2;       // [NB] residual tile landed in staging buffer
   uint64_t* stg_empty = res_full + NB;       // [NB] staging buffer may be refilled by the producer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_empty + NB);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -250,8 +251,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint32_t acc_phase = 0;
     int j = 0;
     if (RES && leader) mbar_arrive(&stg_empty[0]);  // first use of buffer 0 needs no predecessor
+    // The tile's bias slice is staged in shared memory (no L1 is left beside ~200 KB of shared memory, so a
+    // global load inside the column loop is an exposed L2 round trip); it is fetched one tile ahead.
+    const int et = threadIdx.x - 64;  // 0..127
+    float bias_next = 0.f;
+    if (et < BN && cluster_id < num_groups) bias_next = __ldg(p.bias + ((cluster_id % groups_n) * CN + rn) * BN + et);
     for (int g = cluster_id; g < num_groups; g += num_clusters, ++j) {
       const int n_tile = (g % groups_n) * CN + rn;
+      // every thread is past the previous tile's named barrier 2, i.e. done reading the old slice
+      if (et < BN) sbias[et] = bias_next;
+      named_bar_sync(3, 128);
+      if (et < BN && g + num_clusters < num_groups)
+        bias_next = __ldg(p.bias + (((g + num_clusters) % groups_n) * CN + rn) * BN + et);
       int m_tile = (g / groups_n) * CM + rm;
       const int tw = m_tile % p.tiles_w;
       m_tile /= p.tiles_w;
@@ -288,12 +299,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           for (int i = 0; i < 4; ++i)
             rv[i] = *reinterpret_cast<const uint4*>(chunk + (((piece0 + i) ^ swz) << 4));
         }
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + c);
+        const float4* bp = reinterpret_cast<const float4*>(sbias + c);
         __syncwarp();
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 b0 = __ldg(bp + 2 * i), b1 = __ldg(bp + 2 * i + 1);
+          const float4 b0 = bp[2 * i], b1 = bp[2 * i + 1];
           float x[8];
           x[0] = __uint_as_float(v[8 * i + 0]) + b0.x;
           x[1] = __uint_as_float(v[8 * i + 1]) + b0.y;
