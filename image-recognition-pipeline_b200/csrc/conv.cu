@@ -10,6 +10,7 @@
 #include "common.h"
 #include "conv_gemm.cuh"
 #include "conv_gemm2.cuh"
+#include "conv3x3_c64.cuh"
 #include "stem_conv.cuh"
 
 namespace irp {
@@ -138,7 +139,7 @@ __global__ void stem_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 // ------------------------------------------------------------------------------------------------------------
 // conv planning
 // ------------------------------------------------------------------------------------------------------------
-enum ConvKind { kConvFlat = 0, kConvSpatial = 1, kConvStem = 2 };
+enum ConvKind { kConvFlat = 0, kConvSpatial = 1, kConvStem = 2, kConvPatch64 = 3 };
 
 struct ConvPlan {
   ConvParams p;
@@ -197,6 +198,15 @@ static int encode_out_maps(ConvPlan* plan, void* out, const void* residual, int 
   if (residual) IRP_TRY(encode_bf16_map(&p.tmRes, const_cast<void*>(residual), 4, dims, strides, box, 128));
   p.out_box_bytes = p.bw * p.bh * p.bn * 128;
   return IRP_OK;
+}
+
+static bool patch64_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IRP_NO_PATCH64");
+    v = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 // Kernel generation: 2 (CTA pairs) unless IRP_CONV_V1=1 asks for the single-CTA kernel (A/B comparisons).
@@ -265,6 +275,26 @@ static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* 
   p.n_tiles_n = Cout / plan->bn_tile;
 
   char* xb = static_cast<char*>(const_cast<void*>(x));
+  if (ksize == 3 && stride == 1 && Cin == 64 && Cout == 64 && residual == nullptr && patch64_enabled()) {
+    // patch-resident kernel (conv3x3_c64.cuh): 8 x 16 output tiles, 10 x 18 input patches, resident weights
+    plan->kind = kConvPatch64;
+    plan->version = 3;
+    plan->bn_tile = 64;
+    p.n_tiles_n = 1;
+    p.bw = kC64TileW;
+    p.bh = kC64TileH;
+    p.bn = 1;
+    uint64_t dims[4] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(max_batch)};
+    uint64_t strides[3] = {128, static_cast<uint64_t>(W) * 128, static_cast<uint64_t>(H) * W * 128};
+    uint32_t ibox[4] = {64, kC64PatchW, kC64PatchH, 1};
+    IRP_TRY(encode_bf16_map(&p.tmA[0], xb, 4, dims, strides, ibox, 128));
+    uint64_t wdims[2] = {576, 64};
+    uint64_t wstr[1] = {576 * 2};
+    uint32_t wbox[2] = {64, 64};
+    IRP_TRY(encode_bf16_map(&p.tmB, const_cast<void*>(w), 2, wdims, wstr, wbox, 128));
+    IRP_TRY(encode_out_maps(plan, out, nullptr, max_batch));
+    return IRP_OK;
+  }
   if (ksize == 1 && stride == 1) {
     // flattened: A is the plain [M, Cin] matrix, M = B*H*W
     plan->kind = kConvFlat;
@@ -464,6 +494,20 @@ static int launch_conv(const ConvPlan& plan, int batch, cudaStream_t stream, int
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
   const int k_blocks = p.ntaps * p.kc_blocks;
   if (plan.kind == kConvStem) return launch_instance<64, 32, true, false, 2>(p, stream);
+  if (plan.kind == kConvPatch64) {
+    static bool configured = false;
+    if (!configured) {
+      IRP_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kC64SmemBytes));
+      configured = true;
+    }
+    const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    if (grid <= 0) return IRP_OK;
+    conv3x3_c64_kernel<<<grid, kC64Threads, kC64SmemBytes, stream>>>(p);
+    IRP_CUDA_OK(cudaGetLastError());
+    return IRP_OK;
+  }
   if (plan.version == 2)
     return plan.has_res ? launch_conv2<true>(p, plan.bn_tile, stream) : launch_conv2<false>(p, plan.bn_tile, stream);
   if (plan.bn_tile == 128) {
