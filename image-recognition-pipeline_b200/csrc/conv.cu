@@ -609,12 +609,14 @@ static const std::vector<ConvSpec>& specs() {
 }  // namespace
 
 struct irp_resnet50 {
+  StemPoolParams stem3;                // stem_mode 3: stem + max pool fused (stem_pool_kernel)
   StemParams stem2;                    // stem_mode 2: patch-resident no-swizzle stem kernel
   __nv_bfloat16* stem2_w = nullptr;    // its weights (core-matrix order)
   int max_batch = 0;
   int micro = 0;  // images per pass through the trunk (activation arena size); inter-layer tensors of one
                   // micro-batch are meant to stay resident in the 126 MB L2
-  int stem_mode = 2;  // 2: patch-resident kernel (stem_conv.cuh), 0: overlapping TMA view, 1: im2col + flat GEMM
+  int stem_mode = 3;  // 3: stem + max pool fused, 2: patch-resident stem kernel (stem_conv.cuh), 0: overlapping
+                      // TMA view, 1: im2col + flat GEMM
   std::vector<ConvPlan> plans;
   std::vector<__nv_bfloat16*> weights;
   std::vector<float*> biases;
@@ -637,7 +639,19 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x) {
   const int B = net->micro;
   enum { A = 0, Bb = 1, T1 = 2, T2 = 3, DS = 4, STEM = 5 };
   // stem
-  if (net->stem_mode == 2) {
+  if (net->stem_mode == 3) {
+    StemPoolParams& sp3 = net->stem3;
+    memset(&sp3, 0, sizeof(sp3));
+    constexpr uint64_t P = IRP_PAD_HW;
+    uint64_t idims[3] = {P * 4, P, static_cast<uint64_t>(net->max_batch)};
+    uint64_t istr[2] = {P * 8, P * P * 8};
+    uint32_t ibox[3] = {kSpPatchW * 4, kSpPatchH, 1};
+    IRP_TRY(encode_bf16_map(&sp3.tmIn, const_cast<void*>(d_x), 3, idims, istr, ibox, 0));
+    sp3.weights = net->stem2_w;
+    sp3.bias = net->biases[0];
+    sp3.out = net->buf[A];
+  }
+  if (net->stem_mode >= 2) {
     StemParams& sp2 = net->stem2;
     memset(&sp2, 0, sizeof(sp2));
     constexpr uint64_t P = IRP_PAD_HW;
@@ -716,8 +730,8 @@ int irp_resnet50_create(irp_resnet50** out, int max_batch) {
     if (v > 0 && v < max_batch) net->micro = v;
   }
   const char* mode = getenv("IRP_STEM_MODE");
-  net->stem_mode = mode ? atoi(mode) : 2;
-  if (net->stem_mode < 0 || net->stem_mode > 2) net->stem_mode = 2;
+  net->stem_mode = mode ? atoi(mode) : 3;
+  if (net->stem_mode < 0 || net->stem_mode > 3) net->stem_mode = 3;
   net->plans.resize(sp.size());
   net->weights.assign(sp.size(), nullptr);
   net->biases.assign(sp.size(), nullptr);
@@ -766,7 +780,7 @@ int irp_resnet50_load_conv(irp_resnet50* net, int index, const float* d_weight_o
     stem_fold_kernel<<<grid_for(kStemWeightBytes / 2, 256), 256, 0, st>>>(d_weight_oihw, d_gamma, d_beta, d_mean,
                                                                           d_var, eps, net->stem2_w, net->biases[0]);
     IRP_CUDA_OK(cudaGetLastError());
-    if (net->stem_mode == 2) return IRP_OK;
+    if (net->stem_mode >= 2) return IRP_OK;
   }
   if (s.role == 0 && net->stem_mode == 0) {
     kw_pad = 8;
@@ -820,7 +834,21 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
           mb);
       IRP_CUDA_OK(cudaGetLastError());
     }
-    if (net->stem_mode == 2) {
+    // the fused stem + pool kernel never materialises the stem output: a capture of conv 0 takes the unfused path
+    const bool fused_pool = net->stem_mode == 3 && !(capture_index == 0 && d_capture != nullptr);
+    if (fused_pool) {
+      StemPoolParams sp3 = net->stem3;
+      sp3.n_base = s0;
+      sp3.num_tiles = mb * 64;
+      static bool sp_cfg = false;
+      if (!sp_cfg) {
+        IRP_CUDA_OK(cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmemBytes));
+        sp_cfg = true;
+      }
+      const int grid = sp3.num_tiles < num_sms() ? sp3.num_tiles : num_sms();
+      stem_pool_kernel<<<grid, kSpThreads, kSpSmemBytes, st>>>(sp3);
+      IRP_CUDA_OK(cudaGetLastError());
+    } else if (net->stem_mode >= 2) {
       StemParams sp2 = net->stem2;
       sp2.batch = mb;
       sp2.n_base = s0;
@@ -838,7 +866,7 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
       IRP_TRY(launch_conv(net->plans[0], mb, st, s0));
     }
     IRP_TRY(capture(0));
-    {
+    if (!fused_pool) {
       const long long total = static_cast<long long>(mb) * 56 * 56 * (64 / 8);
       maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(net->buf[STEM], net->buf[A], mb, 112, 112, 64, 56, 56);
       IRP_CUDA_OK(cudaGetLastError());
