@@ -236,7 +236,7 @@ class TimedBackend:
 def launches_per_step(n_images, batch, dim, multi_group=True):
     """Kernels of libirp_b200.so launched per step (counted from the launch sites in csrc/*.cu)."""
     batches = (n_images + batch - 1) // batch
-    per_batch = 2 + 55           # resample_plan + resample ; 53 convs + maxpool + avgpool
+    per_batch = 2 + 54           # resample_plan + resample ; stem+pool, 52 convs, avgpool
     cov = 3                      # split_transpose, add_count, cov_gemm
     fit = 1 + (dim - 1) + 5      # assemble, tridiag steps, bisect, inverse iteration, mgs, back-transform (+clip)
     fit += 1
@@ -360,7 +360,8 @@ def run_ours(args, rank, local_rank, world):
                    "parallelism": f"dp{world}: images sharded, one all-reduce of the PCA partial sums"},
         "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": conv_tflops / peaks["tflops_sustained"], "traffic": None,
-                     "kernel": "conv_gemm_kernel (53 launches per irp_resnet50_embed call, batch 256)",
+                     "kernel": "conv_gemm2_kernel / conv3x3_c64_kernel / stem_pool_kernel (53 conv launches per "
+                               "irp_resnet50_embed call, batch 256)",
                      "per_launch": f"{FLOPS_PER_IMAGE:.4e} FLOP/image x {BATCH} images per trunk call; "
                                    f"{calls} calls timed with CUDA events, mean {emb_ms / max(calls, 1):.3f} ms",
                      "peak_source": f"{peaks['source']} bf16_tflops_sustained"},
