@@ -149,8 +149,9 @@ __device__ __forceinline__ void list_insert(double* ld, int32_t* li, int K, doub
 __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restrict__ z,
                                                           const int32_t* __restrict__ order,
                                                           const int32_t* __restrict__ gstart, int n_groups, int dim,
-                                                          int k, const double* __restrict__ sq,
-                                                          double* __restrict__ knn_d, int32_t* __restrict__ knn_i) {
+                                                          int k, const double* __restrict__ sq, int part,
+                                                          int n_parts, double* __restrict__ knn_d,
+                                                          int32_t* __restrict__ knn_i, double* __restrict__ kdist) {
   extern __shared__ double shk[];
   double* Qs = shk;
   double* Cs = Qs + kKnnDChunk * kKnnTile;
@@ -158,6 +159,8 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
   double* ld = Dt + kKnnTile * (kKnnTile + 1);
   int32_t* li = reinterpret_cast<int32_t*>(ld + kKnnTile * k);
 
+  // query tiles are dealt round-robin to the parts (ranks); this launch only runs the tiles of `part`
+  if (static_cast<int>(blockIdx.x % n_parts) != part) return;
   // locate this CTA's (group, query tile)
   int tile = blockIdx.x;
   int g = 0, g0 = 0, g1 = 0;
@@ -256,8 +259,16 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
     if (q0 + ql < g1) {
       knn_d[static_cast<size_t>(q0 + ql) * k + s] = s < K ? sqrt(ld[ql * k + s]) : INFINITY;
       knn_i[static_cast<size_t>(q0 + ql) * k + s] = s < K ? li[ql * k + s] : -1;
+      if (s == K - 1) kdist[q0 + ql] = sqrt(ld[ql * k + s]);  // k-distance of the row (_lof.py:305)
     }
   }
+}
+
+// index of the k-NN CTA (query tile) that owns sorted row i: tiles are numbered group by group
+__device__ __forceinline__ int owner_tile(const int32_t* gstart, int g, int i) {
+  int t = 0;
+  for (int gg = 0; gg < g; ++gg) t += (gstart[gg + 1] - gstart[gg] + kKnnTile - 1) / kKnnTile;
+  return t + (i - gstart[g]) / kKnnTile;
 }
 
 // per-row group lookup in sorted order (binary search over gstart) -> K for that row
@@ -270,12 +281,17 @@ __device__ __forceinline__ int row_group(const int32_t* gstart, int n_groups, in
   return lo;
 }
 
+// rows owned by other parts are written as 0 so that a sum all-reduce assembles the full vector
 __global__ void lrd_kernel(const double* __restrict__ knn_d, const int32_t* __restrict__ knn_i,
-                           const int32_t* __restrict__ gstart, int n_groups, long long n, int k,
-                           double* __restrict__ lrd) {
+                           const double* __restrict__ kdist_all, const int32_t* __restrict__ gstart, int n_groups,
+                           long long n, int k, int part, int n_parts, double* __restrict__ lrd) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const int g = row_group(gstart, n_groups, static_cast<int>(i));
+  if (n_parts > 1 && owner_tile(gstart, g, static_cast<int>(i)) % n_parts != part) {
+    lrd[i] = 0.0;
+    return;
+  }
   const int ng = gstart[g + 1] - gstart[g];
   if (ng < 2) {
     lrd[i] = 1.0;
@@ -285,19 +301,21 @@ __global__ void lrd_kernel(const double* __restrict__ knn_d, const int32_t* __re
   double s = 0.0;
   for (int t = 0; t < K; ++t) {
     const int nb = knn_i[i * k + t];
-    const double dk = knn_d[static_cast<size_t>(nb) * k + (K - 1)];
-    s += fmax(knn_d[i * k + t], dk);
+    s += fmax(knn_d[i * k + t], kdist_all[nb]);  // reachability distance (_lof.py:519-521)
   }
   lrd[i] = 1.0 / (s / K + 1e-10);
 }
 
 __global__ void lof_score_kernel(const double* __restrict__ lrd, const int32_t* __restrict__ knn_i,
-                                 const int32_t* __restrict__ gstart, int n_groups, const int32_t* __restrict__ order,
-                                 long long n, int k, double* __restrict__ score_sorted,
-                                 double* __restrict__ score_out) {
+                                 const int32_t* __restrict__ gstart, int n_groups, long long n, int k, int part,
+                                 int n_parts, double* __restrict__ score_sorted) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const int g = row_group(gstart, n_groups, static_cast<int>(i));
+  if (n_parts > 1 && owner_tile(gstart, g, static_cast<int>(i)) % n_parts != part) {
+    score_sorted[i] = 0.0;
+    return;
+  }
   const int ng = gstart[g + 1] - gstart[g];
   double sc = -1.0;
   if (ng >= 2) {
@@ -308,7 +326,12 @@ __global__ void lof_score_kernel(const double* __restrict__ lrd, const int32_t* 
     sc = -(s / K);
   }
   score_sorted[i] = sc;
-  score_out[order[i]] = sc;
+}
+
+__global__ void unsort_kernel(const double* __restrict__ v_sorted, const int32_t* __restrict__ order, long long n,
+                              double* __restrict__ out) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) out[order[i]] = v_sorted[i];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -560,38 +583,72 @@ size_t irp_lof_workspace_bytes(int64_t n_rows, int dim, int k) {
   b += align_up(n * 8, 256);          // sq
   b += align_up(n * k * 8, 256);      // knn_d
   b += align_up(n * k * 4, 256);      // knn_i
-  b += align_up(n * 8, 256);          // lrd
-  b += align_up(n * 8, 256);          // score_sorted
+  b += 3 * align_up(n * 8, 256);      // kdist, lrd, score_sorted (single-part path)
   return b + 1024;
 }
 
-int irp_lof(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, int n_groups, int k,
-            double contamination, double* d_scores, double* d_offsets, uint8_t* d_flags, void* d_workspace,
-            size_t workspace_bytes, void* stream) {
-  IRP_REQUIRE(d_z && d_scores && d_offsets && d_flags && d_workspace, "lof: null argument");
-  IRP_REQUIRE(n_rows >= 2 && n_rows < (1ll << 31) && dim >= 1, "lof: n_rows %lld dim %d",
-              static_cast<long long>(n_rows), dim);
+namespace {
+
+// carve-up of the caller's workspace; identical for every phase of one (n_rows, k) problem
+struct LofWs {
+  SortedRows sr;
+  double* sq;
+  double* knn_d;
+  int32_t* knn_i;
+  double* kdist;
+  double* lrd;
+  double* score_sorted;
+};
+
+static LofWs lof_layout(void* d_workspace, size_t n, int k) {
+  LofWs w;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(d_workspace), 256));
+  w.sr.order = reinterpret_cast<int32_t*>(ws);
+  ws += align_up(n * 4, 256);
+  w.sr.gstart = reinterpret_cast<int32_t*>(ws);
+  ws += align_up(static_cast<size_t>(1024 + 1) * 4, 256);
+  w.sr.counts = reinterpret_cast<int32_t*>(ws);
+  ws += align_up(static_cast<size_t>(1024) * kSortThreads * 4, 256);
+  w.sq = reinterpret_cast<double*>(ws);
+  ws += align_up(n * 8, 256);
+  w.knn_d = reinterpret_cast<double*>(ws);
+  ws += align_up(n * k * 8, 256);
+  w.knn_i = reinterpret_cast<int32_t*>(ws);
+  ws += align_up(n * k * 4, 256);
+  w.kdist = reinterpret_cast<double*>(ws);
+  ws += align_up(n * 8, 256);
+  w.lrd = reinterpret_cast<double*>(ws);
+  ws += align_up(n * 8, 256);
+  w.score_sorted = reinterpret_cast<double*>(ws);
+  return w;
+}
+
+static int lof_check(int64_t n_rows, int k, int n_groups, int part, int n_parts, const void* ws, size_t ws_bytes) {
+  IRP_REQUIRE(ws != nullptr, "lof: null workspace");
+  IRP_REQUIRE(n_rows >= 2 && n_rows < (1ll << 31), "lof: n_rows %lld", static_cast<long long>(n_rows));
   IRP_REQUIRE(k >= 1 && k <= kMaxK, "lof: n_neighbors %d not in [1,%d]", k, kMaxK);
   IRP_REQUIRE(n_groups >= 1 && n_groups <= 1024, "lof: n_groups %d not in [1,1024]", n_groups);
-  IRP_REQUIRE(contamination > 0.0 && contamination <= 0.5, "lof: contamination %g not in (0,0.5]", contamination);
-  IRP_REQUIRE(workspace_bytes >= irp_lof_workspace_bytes(n_rows, dim, k), "lof: workspace too small");
+  IRP_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, "lof: part %d of %d", part, n_parts);
+  IRP_REQUIRE(ws_bytes >= irp_lof_workspace_bytes(n_rows, 1, k), "lof: workspace too small");
+  return IRP_OK;
+}
+
+}  // namespace
+
+int irp_lof_knn_part(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, int n_groups, int k, int part,
+                     int n_parts, double* d_kdist, void* d_workspace, size_t workspace_bytes, void* stream) {
+  IRP_REQUIRE(d_z && d_kdist && dim >= 1, "lof_knn_part: bad argument");
+  IRP_TRY(lof_check(n_rows, k, n_groups, part, n_parts, d_workspace, workspace_bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n = static_cast<size_t>(n_rows);
-  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(d_workspace), 256));
+  LofWs w = lof_layout(d_workspace, n, k);
+  uint8_t* cursor = reinterpret_cast<uint8_t*>(w.sr.order);
   SortedRows sr;
-  IRP_TRY(sort_rows(d_group, n_rows, n_groups, ws, &sr, st));
-  double* sq = reinterpret_cast<double*>(ws);
-  ws += align_up(n * 8, 256);
-  double* knn_d = reinterpret_cast<double*>(ws);
-  ws += align_up(n * k * 8, 256);
-  int32_t* knn_i = reinterpret_cast<int32_t*>(ws);
-  ws += align_up(n * k * 4, 256);
-  double* lrd = reinterpret_cast<double*>(ws);
-  ws += align_up(n * 8, 256);
-  double* score_sorted = reinterpret_cast<double*>(ws);
-
+  IRP_TRY(sort_rows(d_group, n_rows, n_groups, cursor, &sr, st));
+  w.sr = sr;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-  sqnorm_kernel<<<blocks, 256, 0, st>>>(d_z, sr.order, n_rows, dim, sq);
+  sqnorm_kernel<<<blocks, 256, 0, st>>>(d_z, w.sr.order, n_rows, dim, w.sq);
+  IRP_CUDA_OK(cudaMemsetAsync(d_kdist, 0, n * sizeof(double), st));  // rows of other parts stay 0
   const size_t smem = (2 * kKnnDChunk * kKnnTile + kKnnTile * (kKnnTile + 1) + static_cast<size_t>(kKnnTile) * k) * 8 +
                       static_cast<size_t>(kKnnTile) * k * 4;
   static size_t cfg = 0;
@@ -600,16 +657,73 @@ int irp_lof(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, i
     cfg = smem;
   }
   const unsigned knn_grid = static_cast<unsigned>((n + kKnnTile - 1) / kKnnTile + n_groups);
-  knn_kernel<<<knn_grid, kKnnThreads, smem, st>>>(d_z, sr.order, sr.gstart, n_groups, dim, k, sq, knn_d, knn_i);
-  lrd_kernel<<<blocks, 256, 0, st>>>(knn_d, knn_i, sr.gstart, n_groups, n_rows, k, lrd);
-  lof_score_kernel<<<blocks, 256, 0, st>>>(lrd, knn_i, sr.gstart, n_groups, sr.order, n_rows, k, score_sorted,
-                                           d_scores);
-  // sklearn passes 100*contamination to np.percentile, which divides by 100 again
-  const double q = (100.0 * contamination) / 100.0;
-  group_percentile_kernel<<<n_groups, 1024, 0, st>>>(score_sorted, sr.gstart, q, d_offsets);
-  flag_kernel<<<blocks, 256, 0, st>>>(score_sorted, sr.gstart, n_groups, sr.order, n_rows, d_offsets, 0, d_flags);
+  knn_kernel<<<knn_grid, kKnnThreads, smem, st>>>(d_z, w.sr.order, w.sr.gstart, n_groups, dim, k, w.sq, part, n_parts,
+                                                  w.knn_d, w.knn_i, d_kdist);
   IRP_CUDA_OK(cudaGetLastError());
   return IRP_OK;
+}
+
+int irp_lof_lrd_part(int64_t n_rows, int n_groups, int k, int part, int n_parts, const double* d_kdist_all,
+                     double* d_lrd, void* d_workspace, size_t workspace_bytes, void* stream) {
+  IRP_REQUIRE(d_kdist_all && d_lrd, "lof_lrd_part: null argument");
+  IRP_TRY(lof_check(n_rows, k, n_groups, part, n_parts, d_workspace, workspace_bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(n_rows);
+  LofWs w = lof_layout(d_workspace, n, k);
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  lrd_kernel<<<blocks, 256, 0, st>>>(w.knn_d, w.knn_i, d_kdist_all, w.sr.gstart, n_groups, n_rows, k, part, n_parts,
+                                     d_lrd);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+int irp_lof_score_part(int64_t n_rows, int n_groups, int k, int part, int n_parts, const double* d_lrd_all,
+                       double* d_score_sorted, void* d_workspace, size_t workspace_bytes, void* stream) {
+  IRP_REQUIRE(d_lrd_all && d_score_sorted, "lof_score_part: null argument");
+  IRP_TRY(lof_check(n_rows, k, n_groups, part, n_parts, d_workspace, workspace_bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(n_rows);
+  LofWs w = lof_layout(d_workspace, n, k);
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  lof_score_kernel<<<blocks, 256, 0, st>>>(d_lrd_all, w.knn_i, w.sr.gstart, n_groups, n_rows, k, part, n_parts,
+                                           d_score_sorted);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+int irp_lof_finish(int64_t n_rows, int n_groups, int k, double contamination, const double* d_score_sorted_all,
+                   double* d_scores, double* d_offsets, uint8_t* d_flags, void* d_workspace, size_t workspace_bytes,
+                   void* stream) {
+  IRP_REQUIRE(d_score_sorted_all && d_scores && d_offsets && d_flags, "lof_finish: null argument");
+  IRP_REQUIRE(contamination > 0.0 && contamination <= 0.5, "lof: contamination %g not in (0,0.5]", contamination);
+  IRP_TRY(lof_check(n_rows, k, n_groups, 0, 1, d_workspace, workspace_bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(n_rows);
+  LofWs w = lof_layout(d_workspace, n, k);
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  unsort_kernel<<<blocks, 256, 0, st>>>(d_score_sorted_all, w.sr.order, n_rows, d_scores);
+  // sklearn passes 100*contamination to np.percentile, which divides by 100 again
+  const double q = (100.0 * contamination) / 100.0;
+  group_percentile_kernel<<<n_groups, 1024, 0, st>>>(d_score_sorted_all, w.sr.gstart, q, d_offsets);
+  flag_kernel<<<blocks, 256, 0, st>>>(d_score_sorted_all, w.sr.gstart, n_groups, w.sr.order, n_rows, d_offsets, 0,
+                                      d_flags);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+int irp_lof(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, int n_groups, int k,
+            double contamination, double* d_scores, double* d_offsets, uint8_t* d_flags, void* d_workspace,
+            size_t workspace_bytes, void* stream) {
+  IRP_REQUIRE(d_z && d_scores && d_offsets && d_flags && d_workspace, "lof: null argument");
+  IRP_REQUIRE(dim >= 1, "lof: dim %d", dim);
+  IRP_REQUIRE(contamination > 0.0 && contamination <= 0.5, "lof: contamination %g not in (0,0.5]", contamination);
+  IRP_TRY(lof_check(n_rows, k, n_groups, 0, 1, d_workspace, workspace_bytes));
+  LofWs w = lof_layout(d_workspace, static_cast<size_t>(n_rows), k);
+  IRP_TRY(irp_lof_knn_part(d_z, n_rows, dim, d_group, n_groups, k, 0, 1, w.kdist, d_workspace, workspace_bytes, stream));
+  IRP_TRY(irp_lof_lrd_part(n_rows, n_groups, k, 0, 1, w.kdist, w.lrd, d_workspace, workspace_bytes, stream));
+  IRP_TRY(irp_lof_score_part(n_rows, n_groups, k, 0, 1, w.lrd, w.score_sorted, d_workspace, workspace_bytes, stream));
+  return irp_lof_finish(n_rows, n_groups, k, contamination, w.score_sorted, d_scores, d_offsets, d_flags, d_workspace,
+                        workspace_bytes, stream);
 }
 
 size_t irp_centroid_workspace_bytes(int64_t n_rows, int dim, int n_groups) {

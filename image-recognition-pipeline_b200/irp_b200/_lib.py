@@ -50,6 +50,10 @@ SIGNATURES = {
     "irp_pca_transform": (_i, [_vp, _i64, _i, _vp, _vp, _i, _vp, _vp]),
     "irp_lof_workspace_bytes": (_sz, [_i64, _i, _i]),
     "irp_lof": (_i, [_vp, _i64, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "irp_lof_knn_part": (_i, [_vp, _i64, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "irp_lof_lrd_part": (_i, [_i64, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "irp_lof_score_part": (_i, [_i64, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "irp_lof_finish": (_i, [_i64, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "irp_centroid_workspace_bytes": (_sz, [_i64, _i, _i]),
     "irp_centroid_zscore": (_i, [_vp, _i64, _i, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -158,6 +158,36 @@ def _(z, group, n_groups, n_neighbors, contamination):
             z.new_empty(n, dtype=torch.uint8))
 
 
+def lof_sharded(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: int, n_neighbors: int,
+                contamination: float, part: int, n_parts: int, all_reduce) -> Tuple[torch.Tensor, torch.Tensor,
+                                                                                   torch.Tensor]:
+    """irp_lof with the O(n^2) neighbour search sharded over `n_parts` ranks (irp_lof_knn_part / _lrd_part /
+    _score_part / _finish).  Every rank passes the same `z` / `group` (all rows); `all_reduce(t)` must sum the fp64
+    vector `t` in place over the ranks.  Returns the same (scores, offsets, flags) on every rank."""
+    lib = _lib_for(z)
+    assert z.dtype == torch.float32 and z.is_contiguous()
+    n, d = z.shape
+    k = int(n_neighbors)
+    ws_bytes = lib.irp_lof_workspace_bytes(n, d, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    vec = lambda: torch.empty(n, dtype=torch.float64, device=z.device)
+    kdist, lrd, score = vec(), vec(), vec()
+    _lib.check(lib.irp_lof_knn_part(_ptr(z), n, d, _ptr(group), n_groups, k, part, n_parts, _ptr(kdist), _ptr(ws),
+                                    ws_bytes, _stream()), "irp_lof_knn_part")
+    all_reduce(kdist)
+    _lib.check(lib.irp_lof_lrd_part(n, n_groups, k, part, n_parts, _ptr(kdist), _ptr(lrd), _ptr(ws), ws_bytes,
+                                    _stream()), "irp_lof_lrd_part")
+    all_reduce(lrd)
+    _lib.check(lib.irp_lof_score_part(n, n_groups, k, part, n_parts, _ptr(lrd), _ptr(score), _ptr(ws), ws_bytes,
+                                      _stream()), "irp_lof_score_part")
+    all_reduce(score)
+    scores, offsets, flags = vec(), torch.empty(n_groups, dtype=torch.float64, device=z.device), \
+        torch.empty(n, dtype=torch.uint8, device=z.device)
+    _lib.check(lib.irp_lof_finish(n, n_groups, k, C.c_double(contamination), _ptr(score), _ptr(scores), _ptr(offsets),
+                                  _ptr(flags), _ptr(ws), ws_bytes, _stream()), "irp_lof_finish")
+    return scores, offsets, flags
+
+
 @torch.library.custom_op("irp_b200::centroid_zscore", mutates_args=())
 def centroid_zscore(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: int,
                     contamination: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:

@@ -9,7 +9,8 @@
 Multi-GPU (one process per GPU, torch.distributed/NCCL): images shard across ranks with no data-path collective;
 the PCA needs ONE all-reduce of [count, sum, scatter] (plus an 8 KB broadcast of the shift vector so every rank
 accumulates about the same origin); scoring needs the projected rows of all ranks (one all-gather of N x k
-floats).
+floats), after which each rank runs the neighbour search for its share of the query tiles and three length-N fp64
+vectors (k-distance, lrd, score) are summed across ranks.
 """
 from __future__ import annotations
 
@@ -208,6 +209,7 @@ class CudaBackend:
     pca_fit = staticmethod(ops.pca_fit)
     pca_transform = staticmethod(ops.pca_transform)
     lof = staticmethod(ops.lof)
+    lof_sharded = staticmethod(ops.lof_sharded)
 
 
 class OutlierStage:
@@ -327,8 +329,22 @@ class OutlierStage:
         return torch.cat([o[:s] for o, s in zip(outs, sizes)], 0)
 
     def detect(self, z_all: torch.Tensor, class_ids_all: torch.Tensor, n_classes: int):
-        cs, _, cf = self.backend.lof(z_all, class_ids_all, n_classes, self.class_nn, self.class_cont)
-        gs, _, gf = self.backend.lof(z_all, None, 1, self.global_nn, self.global_cont)
+        """Per-class + global LOF over ALL rows.  On several ranks the O(n^2) neighbour search is sharded: rank r
+        searches the query tiles r, r+W, r+2W, ... and three length-n vectors are summed across ranks."""
+        dist = self._dist()
+        if dist is not None and self.world_size > 1 and hasattr(self.backend, "lof_sharded"):
+            rank, ws = dist.get_rank(self.pg), self.world_size
+
+            def all_reduce(t):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+
+            cs, _, cf = self.backend.lof_sharded(z_all, class_ids_all, n_classes, self.class_nn, self.class_cont,
+                                                 rank, ws, all_reduce)
+            gs, _, gf = self.backend.lof_sharded(z_all, None, 1, self.global_nn, self.global_cont, rank, ws,
+                                                 all_reduce)
+        else:
+            cs, _, cf = self.backend.lof(z_all, class_ids_all, n_classes, self.class_nn, self.class_cont)
+            gs, _, gf = self.backend.lof(z_all, None, 1, self.global_nn, self.global_cont)
         return cf.bool(), gf.bool(), cs, gs
 
     # ---- whole stage ----

@@ -146,6 +146,27 @@ int irp_lof(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, i
             double contamination, double* d_scores, double* d_offsets, uint8_t* d_flags, void* d_workspace,
             size_t workspace_bytes, void* stream);
 
+/* Multi-GPU form of irp_lof: every rank holds all rows (after the all-gather of the projected
+ * rows) and runs the O(n^2) neighbour search for 1/n_parts of the query tiles only; what the other ranks need are three
+ * length-n fp64 vectors, each exchanged with ONE sum all-reduce (rows a rank does not own are written as 0):
+ *
+ *   irp_lof_knn_part   -> d_kdist   [n]  k-distance of the rows this part owns          (all-reduce)
+ *   irp_lof_lrd_part   -> d_lrd     [n]  local reachability density of the owned rows   (all-reduce)
+ *   irp_lof_score_part -> d_score   [n]  negative_outlier_factor_ of the owned rows     (all-reduce)
+ *   irp_lof_finish     -> scores in input order, per-group np.percentile offset, flags  (every rank, O(n))
+ *
+ * All vectors are in the library's group-sorted row order; the SAME workspace (irp_lof_workspace_bytes) must be
+ * passed to the four calls of one problem.  irp_lof is these four calls with n_parts = 1. */
+int irp_lof_knn_part(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, int n_groups, int k, int part,
+                     int n_parts, double* d_kdist, void* d_workspace, size_t workspace_bytes, void* stream);
+int irp_lof_lrd_part(int64_t n_rows, int n_groups, int k, int part, int n_parts, const double* d_kdist_all,
+                     double* d_lrd, void* d_workspace, size_t workspace_bytes, void* stream);
+int irp_lof_score_part(int64_t n_rows, int n_groups, int k, int part, int n_parts, const double* d_lrd_all,
+                       double* d_score_sorted, void* d_workspace, size_t workspace_bytes, void* stream);
+int irp_lof_finish(int64_t n_rows, int n_groups, int k, double contamination, const double* d_score_sorted_all,
+                   double* d_scores, double* d_offsets, uint8_t* d_flags, void* d_workspace, size_t workspace_bytes,
+                   void* stream);
+
 size_t irp_centroid_workspace_bytes(int64_t n_rows, int dim, int n_groups);
 int irp_centroid_zscore(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, int n_groups,
                         double contamination, double* d_dist, double* d_zscore, double* d_thresholds,

@@ -428,6 +428,47 @@ def test_lof_duplicates_and_unsorted_groups(ops_mod):
     assert torch.isfinite(scores).all()
 
 
+@pytest.mark.parametrize("n_parts", [2, 3, 8])
+def test_lof_sharded_over_parts_is_bitwise_the_single_call(lib, ops_mod, n_parts):
+    """Multi-GPU form of irp_lof on ONE GPU: the parts (ranks) are run one after the other, their three fp64
+    vectors summed exactly as the all-reduce would; scores / offsets / flags must equal irp_lof bit for bit."""
+    from irp_b200 import _lib
+    z, y = synth.clustered_points(3000, 24, 6, seed=11)
+    zt = torch.from_numpy(z).cuda()
+    for ids, n_groups, k, cont in ((torch.from_numpy(y.astype(np.int32)).cuda(), 6, 30, 0.05), (None, 1, 75, 0.03)):
+        ref_scores, ref_offsets, ref_flags = ops_mod.lof(zt, ids, n_groups, k, cont)
+        n, d = zt.shape
+        ws_bytes = lib.irp_lof_workspace_bytes(n, d, k)
+        wss = [torch.empty(ws_bytes, dtype=torch.uint8, device="cuda") for _ in range(n_parts)]
+        vec = lambda: torch.zeros(n, dtype=torch.float64, device="cuda")
+        total = vec()
+        for p in range(n_parts):
+            t = vec()
+            _lib.check(lib.irp_lof_knn_part(_ptr(zt), n, d, _ptr(ids), n_groups, k, p, n_parts, _ptr(t), _ptr(wss[p]),
+                                            ws_bytes, _stream()), "knn_part")
+            total += t
+        kdist = total
+        total = vec()
+        for p in range(n_parts):
+            t = vec()
+            _lib.check(lib.irp_lof_lrd_part(n, n_groups, k, p, n_parts, _ptr(kdist), _ptr(t), _ptr(wss[p]), ws_bytes,
+                                            _stream()), "lrd_part")
+            total += t
+        lrd = total
+        total = vec()
+        for p in range(n_parts):
+            t = vec()
+            _lib.check(lib.irp_lof_score_part(n, n_groups, k, p, n_parts, _ptr(lrd), _ptr(t), _ptr(wss[p]), ws_bytes,
+                                              _stream()), "score_part")
+            total += t
+        scores, offsets = vec(), torch.empty(n_groups, dtype=torch.float64, device="cuda")
+        flags = torch.empty(n, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.irp_lof_finish(n, n_groups, k, C.c_double(cont), _ptr(total), _ptr(scores), _ptr(offsets),
+                                      _ptr(flags), _ptr(wss[0]), ws_bytes, _stream()), "finish")
+        torch.cuda.synchronize()
+        assert torch.equal(scores, ref_scores) and torch.equal(offsets, ref_offsets) and torch.equal(flags, ref_flags)
+
+
 def test_lof_full_size_properties(ops_mod):
     """BASELINE size (27 000 x 50): flag counts follow the contamination, flags are permutation-equivariant, and
     the per-class pass equals running each class alone."""
