@@ -10,6 +10,7 @@
 // tiles in registers, per-query sorted candidate lists in shared memory) -> lrd -> lof -> per-group radix select
 // of the two order statistics around the percentile -> flags.
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -260,6 +261,161 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
       knn_d[static_cast<size_t>(q0 + ql) * k + s] = s < K ? sqrt(ld[ql * k + s]) : INFINITY;
       knn_i[static_cast<size_t>(q0 + ql) * k + s] = s < K ? li[ql * k + s] : -1;
       if (s == K - 1) kdist[q0 + ql] = sqrt(ld[ql * k + s]);  // k-distance of the row (_lof.py:305)
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Fast path (dim <= kKnnMaxResidentDim): rows are first gathered into group-sorted order as fp64 [n][dpad] (zero
+// padded to a multiple of 8 features), so the search kernel reads contiguous rows without the order[] indirection;
+// the CTA's 64 query rows stay resident in shared memory for its whole life, candidate tiles are streamed with a
+// register prefetch of the next tile behind the 64 x 64 x dpad fp64 FMA block of the current one.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kKnnMaxResidentDim = 128;
+
+__global__ void gather_sorted_kernel(const float* __restrict__ z, const int32_t* __restrict__ order, long long n,
+                                     int dim, int dpad, double* __restrict__ zs) {
+  const long long total = n * dpad;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / dpad;
+    const int j = static_cast<int>(i - r * dpad);
+    zs[i] = j < dim ? static_cast<double>(z[static_cast<size_t>(order[r]) * dim + j]) : 0.0;
+  }
+}
+
+// dynamic smem: Qs[dpad][64], Cs[dpad][64], Dt[64][65], ld[64][k], li[64][k]
+__global__ void __launch_bounds__(kKnnThreads) knn_resident_kernel(const double* __restrict__ zs,
+                                                                   const int32_t* __restrict__ gstart, int n_groups,
+                                                                   int dpad, int k, const double* __restrict__ sq,
+                                                                   int part, int n_parts, double* __restrict__ knn_d,
+                                                                   int32_t* __restrict__ knn_i,
+                                                                   double* __restrict__ kdist) {
+  extern __shared__ double shk[];
+  double* Qs = shk;
+  double* Cs = Qs + dpad * kKnnTile;
+  double* Dt = Cs + dpad * kKnnTile;
+  double* ld = Dt + kKnnTile * (kKnnTile + 1);
+  int32_t* li = reinterpret_cast<int32_t*>(ld + kKnnTile * k);
+
+  if (static_cast<int>(blockIdx.x % n_parts) != part) return;
+  int tile = blockIdx.x;
+  int g = 0, g0 = 0, g1 = 0;
+  for (; g < n_groups; ++g) {
+    g0 = gstart[g];
+    g1 = gstart[g + 1];
+    const int tiles = (g1 - g0 + kKnnTile - 1) / kKnnTile;
+    if (tile < tiles) break;
+    tile -= tiles;
+  }
+  if (g >= n_groups) return;
+  const int ng = g1 - g0;
+  const int q0 = g0 + tile * kKnnTile;
+  const int K = max(1, min(k, ng - 1));  // _lof.py:293
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kKnnTile * k; i += kKnnThreads) {
+    ld[i] = INFINITY;
+    li[i] = -1;
+  }
+  // tile loads: thread (r = tid % 64, jp = tid / 64 + 4u) moves features 2jp, 2jp+1 of row r
+  const int lr = tid & 63, ljp = tid >> 6;
+  const int n_u = dpad >> 3;  // double2 loads per thread per tile (dpad is a multiple of 8)
+  constexpr int kMaxU = kKnnMaxResidentDim / 8;
+  {
+    const double* row = zs + static_cast<size_t>(min(q0 + lr, g1 - 1)) * dpad;
+    for (int u = 0; u < n_u; ++u) {
+      const int jp = ljp + 4 * u;
+      const double2 v = *reinterpret_cast<const double2*>(row + 2 * jp);
+      Qs[(2 * jp) * kKnnTile + lr] = v.x;
+      Qs[(2 * jp + 1) * kKnnTile + lr] = v.y;
+    }
+  }
+  double2 pre[kMaxU];
+  auto prefetch = [&](int c0) {
+    const double* row = zs + static_cast<size_t>(min(c0 + lr, g1 - 1)) * dpad;
+#pragma unroll
+    for (int u = 0; u < kMaxU; ++u)
+      if (u < n_u) pre[u] = __ldg(reinterpret_cast<const double2*>(row + 2 * (ljp + 4 * u)));
+  };
+  prefetch(g0);
+  const int ty = tid >> 4, tx = tid & 15;
+  double sqq[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) sqq[a] = sq[min(q0 + ty * 4 + a, g1 - 1)];
+
+  for (int c0 = g0; c0 < g1; c0 += kKnnTile) {
+    __syncthreads();  // the previous tile's selection is done with Dt, its FMA block with Cs
+#pragma unroll
+    for (int u = 0; u < kMaxU; ++u)
+      if (u < n_u) {
+        const int jp = ljp + 4 * u;
+        Cs[(2 * jp) * kKnnTile + lr] = pre[u].x;
+        Cs[(2 * jp + 1) * kKnnTile + lr] = pre[u].y;
+      }
+    __syncthreads();
+    if (c0 + kKnnTile < g1) prefetch(c0 + kKnnTile);
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 8
+    for (int jj = 0; jj < dpad; ++jj) {
+      const double2 qa = *reinterpret_cast<const double2*>(&Qs[jj * kKnnTile + ty * 4]);
+      const double2 qb = *reinterpret_cast<const double2*>(&Qs[jj * kKnnTile + ty * 4 + 2]);
+      const double2 ca = *reinterpret_cast<const double2*>(&Cs[jj * kKnnTile + tx * 4]);
+      const double2 cb = *reinterpret_cast<const double2*>(&Cs[jj * kKnnTile + tx * 4 + 2]);
+      const double q[4] = {qa.x, qa.y, qb.x, qb.y};
+      const double c[4] = {ca.x, ca.y, cb.x, cb.y};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(q[a], c[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int ci = c0 + tx * 4 + b;
+      const double sqc = ci < g1 ? sq[ci] : 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int qi = q0 + ty * 4 + a;
+        double d2 = INFINITY;
+        if (qi < g1 && ci < g1 && ci != qi) d2 = fmax(sqq[a] + sqc - 2.0 * acc[a][b], 0.0);
+        Dt[(ty * 4 + a) * (kKnnTile + 1) + tx * 4 + b] = d2;
+      }
+    }
+    __syncthreads();
+    // selection: warp w owns queries w*8 .. w*8+7
+    for (int qq = 0; qq < 8; ++qq) {
+      const int ql = warp * 8 + qq;
+      if (q0 + ql >= g1) break;
+      double* qld = ld + ql * k;
+      int32_t* qli = li + ql * k;
+      double tau = qld[K - 1];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const double dc = Dt[ql * (kKnnTile + 1) + half * 32 + lane];
+        unsigned pending = __ballot_sync(0xffffffffu, dc < tau);
+        while (pending) {
+          const int src = __ffs(pending) - 1;
+          pending &= pending - 1;
+          const double dv = __shfl_sync(0xffffffffu, dc, src);
+          if (dv < tau) {
+            list_insert(qld, qli, K, dv, c0 + half * 32 + src, lane);
+            tau = qld[K - 1];
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kKnnTile * k; i += kKnnThreads) {
+    const int ql = i / k, s = i % k;
+    if (q0 + ql < g1) {
+      knn_d[static_cast<size_t>(q0 + ql) * k + s] = s < K ? sqrt(ld[ql * k + s]) : INFINITY;
+      knn_i[static_cast<size_t>(q0 + ql) * k + s] = s < K ? li[ql * k + s] : -1;
+      if (s == K - 1) kdist[q0 + ql] = sqrt(ld[ql * k + s]);
     }
   }
 }
@@ -584,6 +740,7 @@ size_t irp_lof_workspace_bytes(int64_t n_rows, int dim, int k) {
   b += align_up(n * k * 8, 256);      // knn_d
   b += align_up(n * k * 4, 256);      // knn_i
   b += 3 * align_up(n * 8, 256);      // kdist, lrd, score_sorted (single-part path)
+  if (dim <= kKnnMaxResidentDim) b += align_up(n * static_cast<size_t>((dim + 7) / 8 * 8) * 8, 256);  // sorted fp64 rows
   return b + 1024;
 }
 
@@ -598,6 +755,7 @@ struct LofWs {
   double* kdist;
   double* lrd;
   double* score_sorted;
+  double* zs;  // [n][dpad] group-sorted fp64 rows (knn phase only; last, so the other offsets do not depend on dim)
 };
 
 static LofWs lof_layout(void* d_workspace, size_t n, int k) {
@@ -620,6 +778,8 @@ static LofWs lof_layout(void* d_workspace, size_t n, int k) {
   w.lrd = reinterpret_cast<double*>(ws);
   ws += align_up(n * 8, 256);
   w.score_sorted = reinterpret_cast<double*>(ws);
+  ws += align_up(n * 8, 256);
+  w.zs = reinterpret_cast<double*>(ws);
   return w;
 }
 
@@ -639,6 +799,7 @@ int irp_lof_knn_part(const float* d_z, int64_t n_rows, int dim, const int32_t* d
                      int n_parts, double* d_kdist, void* d_workspace, size_t workspace_bytes, void* stream) {
   IRP_REQUIRE(d_z && d_kdist && dim >= 1, "lof_knn_part: bad argument");
   IRP_TRY(lof_check(n_rows, k, n_groups, part, n_parts, d_workspace, workspace_bytes));
+  IRP_REQUIRE(workspace_bytes >= irp_lof_workspace_bytes(n_rows, dim, k), "lof: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n = static_cast<size_t>(n_rows);
   LofWs w = lof_layout(d_workspace, n, k);
@@ -649,16 +810,38 @@ int irp_lof_knn_part(const float* d_z, int64_t n_rows, int dim, const int32_t* d
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   sqnorm_kernel<<<blocks, 256, 0, st>>>(d_z, w.sr.order, n_rows, dim, w.sq);
   IRP_CUDA_OK(cudaMemsetAsync(d_kdist, 0, n * sizeof(double), st));  // rows of other parts stay 0
-  const size_t smem = (2 * kKnnDChunk * kKnnTile + kKnnTile * (kKnnTile + 1) + static_cast<size_t>(kKnnTile) * k) * 8 +
-                      static_cast<size_t>(kKnnTile) * k * 4;
-  static size_t cfg = 0;
-  if (smem > cfg) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    cfg = smem;
-  }
   const unsigned knn_grid = static_cast<unsigned>((n + kKnnTile - 1) / kKnnTile + n_groups);
-  knn_kernel<<<knn_grid, kKnnThreads, smem, st>>>(d_z, w.sr.order, w.sr.gstart, n_groups, dim, k, w.sq, part, n_parts,
-                                                  w.knn_d, w.knn_i, d_kdist);
+  static int force_generic = -1;
+  if (force_generic < 0) {
+    const char* e = getenv("IRP_KNN_GENERIC");
+    force_generic = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  if (dim <= kKnnMaxResidentDim && !force_generic) {
+    const int dpad = (dim + 7) / 8 * 8;
+    const long long total = static_cast<long long>(n) * dpad;
+    const unsigned gblocks = static_cast<unsigned>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
+    gather_sorted_kernel<<<gblocks, 256, 0, st>>>(d_z, w.sr.order, n_rows, dim, dpad, w.zs);
+    const size_t smem = (2 * static_cast<size_t>(dpad) * kKnnTile + kKnnTile * (kKnnTile + 1) +
+                         static_cast<size_t>(kKnnTile) * k) * 8 + static_cast<size_t>(kKnnTile) * k * 4;
+    static size_t cfg = 0;
+    if (smem > cfg) {
+      IRP_CUDA_OK(cudaFuncSetAttribute(knn_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+      cfg = smem;
+    }
+    knn_resident_kernel<<<knn_grid, kKnnThreads, smem, st>>>(w.zs, w.sr.gstart, n_groups, dpad, k, w.sq, part, n_parts,
+                                                             w.knn_d, w.knn_i, d_kdist);
+  } else {
+    const size_t smem = (2 * kKnnDChunk * kKnnTile + kKnnTile * (kKnnTile + 1) + static_cast<size_t>(kKnnTile) * k) * 8 +
+                        static_cast<size_t>(kKnnTile) * k * 4;
+    static size_t cfg = 0;
+    if (smem > cfg) {
+      IRP_CUDA_OK(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      cfg = smem;
+    }
+    knn_kernel<<<knn_grid, kKnnThreads, smem, st>>>(d_z, w.sr.order, w.sr.gstart, n_groups, dim, k, w.sq, part, n_parts,
+                                                    w.knn_d, w.knn_i, d_kdist);
+  }
   IRP_CUDA_OK(cudaGetLastError());
   return IRP_OK;
 }
