@@ -200,6 +200,16 @@ static int encode_out_maps(ConvPlan* plan, void* out, const void* residual, int 
   return IRP_OK;
 }
 
+// Programmatic dependent launch between consecutive trunk kernels (IRP_NO_PDL=1 turns it off).
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IRP_NO_PDL");
+    v = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool patch64_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -457,13 +467,15 @@ static int launch_instance2(const ConvParams& p, cudaStream_t stream) {
   cfg.blockDim = dim3(kConv2Threads);
   cfg.dynamicSmemBytes = S::kTotalBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   IRP_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
   return IRP_OK;
 }
@@ -504,8 +516,18 @@ static int launch_conv(const ConvPlan& plan, int batch, cudaStream_t stream, int
     const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     if (grid <= 0) return IRP_OK;
-    conv3x3_c64_kernel<<<grid, kC64Threads, kC64SmemBytes, stream>>>(p);
-    IRP_CUDA_OK(cudaGetLastError());
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kC64Threads);
+    cfg.dynamicSmemBytes = kC64SmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    IRP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3x3_c64_kernel, p));
     return IRP_OK;
   }
   if (plan.version == 2)

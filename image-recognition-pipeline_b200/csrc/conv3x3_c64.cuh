@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3x3_c64_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3x3_c64_kernel(const __gri
       mbar_arrive_expect_tx(wfull_bar, kC64WeightBytes);
 #pragma unroll 1
       for (int t = 0; t < 9; ++t) tma_load_2d(smem_w + t * 8192, &p.tmB, wfull_bar, t * 64, 0);
+      pdl_wait();  // weights are constants; the activations below come from the previous kernel
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {

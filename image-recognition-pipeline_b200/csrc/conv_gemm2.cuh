@@ -104,12 +104,14 @@ __global__ void __launch_bounds__(kConv2Threads, 1) conv_gemm2_kernel(const __gr
   cluster_sync_all();  // both CTAs' barriers are initialised before anyone signals across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // the next kernel in the stream may begin its own set-up
 
   const int k_blocks = p.ntaps * p.kc_blocks;
 
   if (warp == 0) {
     // ============================ TMA producer (both CTAs) ============================
     if (lane == 0) {
+      pdl_wait();  // everything this kernel reads from the previous one goes through these TMA loads
       int stage = 0;
       uint32_t phase = 0;
       int q = 0;  // residual chunk counter

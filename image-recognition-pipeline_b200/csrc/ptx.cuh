@@ -139,6 +139,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start (set up barriers, allocate TMEM, prefetch descriptors) while its predecessor in the stream is still
+// draining; pdl_wait() blocks until the predecessor has completed and its writes are visible, and must precede
+// the first read of anything the predecessor wrote.  pdl_trigger() lets the NEXT kernel start early.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, TMEM load, fences
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {

@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_pool_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {

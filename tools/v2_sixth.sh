@@ -1,0 +1,6 @@
+#!/bin/bash
+export IRP_B200_PARTIAL=1
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -x -q -m gpu -k "trunk or embedding or conv2d or model_callable" > gpurun_out/pytest_trunk.log 2>&1; echo "pytest rc=$?"; tail -n 4 gpurun_out/pytest_trunk.log
+timeout 300 python tools/trunk_once.py 256 8 2>&1 | tail -1
+IRP_NO_PDL=1 timeout 300 python tools/trunk_once.py 256 8 2>&1 | tail -1
