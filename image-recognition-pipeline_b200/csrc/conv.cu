@@ -11,6 +11,7 @@
 #include "conv_gemm.cuh"
 #include "conv_gemm2.cuh"
 #include "conv3x3_c64.cuh"
+#include "conv_chain.cuh"
 #include "stem_conv.cuh"
 
 namespace irp {
@@ -578,6 +579,90 @@ static int plan_stem_tma(ConvPlan* plan, const void* x_nhwc4p, const void* w, co
   return IRP_OK;
 }
 
+// conv3 of one bottleneck chained with conv1 of the next (conv_chain.cuh)
+struct ChainPlan {
+  ChainParams p;
+  int n2 = 0;
+  int rows_per_image = 0;
+  bool valid = false;
+};
+
+static bool chain_supported(int K1, int N1, int N2) {
+  return K1 % 64 == 0 && N1 % kChainBN1 == 0 && N1 <= kChainMaxN1 && (N2 == 64 || N2 == 128 || N2 == 256);
+}
+
+static int plan_chain(ChainPlan* plan, const void* t2, const void* w3, const float* b3, const void* residual, void* y,
+                      const void* w1, const float* b1, void* t1, long long max_rows, int rows_per_image, int K1,
+                      int N1, int N2) {
+  IRP_REQUIRE(chain_supported(K1, N1, N2), "conv chain: unsupported shape K1 %d N1 %d N2 %d", K1, N1, N2);
+  ChainParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  const uint64_t M = static_cast<uint64_t>(max_rows);
+  auto map2d = [&](CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_outer) -> int {
+    uint64_t dims[2] = {inner, outer};
+    uint64_t strides[1] = {inner * 2};
+    uint32_t box[2] = {64, box_outer};
+    return encode_bf16_map(m, const_cast<void*>(base), 2, dims, strides, box, 128);
+  };
+  IRP_TRY(map2d(&p.tmA, t2, K1, M, kTileM));
+  IRP_TRY(map2d(&p.tmB1, w3, K1, N1, kChainBN1 / 2));
+  IRP_TRY(map2d(&p.tmRes, residual, N1, M, kTileM));
+  IRP_TRY(map2d(&p.tmY, y, N1, M, kTileM));
+  IRP_TRY(map2d(&p.tmB2, w1, N1, N2, N2 / 2));
+  IRP_TRY(map2d(&p.tmOut2, t1, N2, M, kTileM));
+  p.bias1 = b3;
+  p.bias2 = b1;
+  p.k1_blocks = K1 / 64;
+  p.passes = N1 / kChainBN1;
+  p.n1 = N1;
+  plan->n2 = N2;
+  plan->rows_per_image = rows_per_image;
+  plan->valid = true;
+  return IRP_OK;
+}
+
+template <int N2>
+static int launch_chain_instance(const ChainParams& p, cudaStream_t stream) {
+  using S = ChainSmem<N2>;
+  static bool configured = false;
+  auto kernel = conv_chain_kernel<N2>;
+  if (!configured) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
+    configured = true;
+  }
+  const int pair_tiles = (p.m_tiles + 1) / 2;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (pair_tiles < pairs ? pair_tiles : pairs);
+  if (grid <= 0) return IRP_OK;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kChainThreads);
+  cfg.dynamicSmemBytes = S::kTotalBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  IRP_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
+  return IRP_OK;
+}
+
+static int launch_chain(const ChainPlan& plan, long long rows, cudaStream_t stream) {
+  ChainParams p = plan.p;
+  p.m_tiles = static_cast<int>(ceil_div64(rows, kTileM));
+  switch (plan.n2) {
+    case 64: return launch_chain_instance<64>(p, stream);
+    case 128: return launch_chain_instance<128>(p, stream);
+    default: return launch_chain_instance<256>(p, stream);
+  }
+}
+
 static int grid_for(long long total, int threads) {
   long long g = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -640,6 +725,8 @@ struct irp_resnet50 {
   int stem_mode = 3;  // 3: stem + max pool fused, 2: patch-resident stem kernel (stem_conv.cuh), 0: overlapping
                       // TMA view, 1: im2col + flat GEMM
   std::vector<ConvPlan> plans;
+  std::vector<ChainPlan> chains;  // indexed by the conv3 of the first block of a fused junction
+  int chain_level = 1;            // 0: off, 1: layer1 + layer2 junctions, 2: also layer3
   std::vector<__nv_bfloat16*> weights;
   std::vector<float*> biases;
   std::vector<int> out_buf;  // arena buffer id holding each conv's output
@@ -716,6 +803,19 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x) {
     IRP_TRY(plan_conv(&net->plans[i + 2], net->buf[T2], net->weights[i + 2], net->biases[i + 2], res,
                       net->buf[other], B, c3.H, c3.W, c3.cin, c3.cout, 1, 1, 1));
     net->out_buf[i + 2] = other;
+    {
+      // junction with the next bottleneck: its conv1 consumes this block's output at the same resolution
+      const size_t nxt = i + (has_ds ? 4 : 3);
+      net->chains[i + 2].valid = false;
+      const int max_n1 = net->chain_level >= 2 ? 1024 : 512;
+      if (net->chain_level > 0 && nxt < sp.size() && c3.cout <= max_n1 &&
+          chain_supported(c3.cin, c3.cout, sp[nxt].cout)) {
+        const ConvSpec& n1 = sp[nxt];
+        IRP_TRY(plan_chain(&net->chains[i + 2], net->buf[T2], net->weights[i + 2], net->biases[i + 2], res,
+                           net->buf[other], net->weights[nxt], net->biases[nxt], net->buf[T1],
+                           static_cast<long long>(B) * c3.H * c3.W, c3.H * c3.W, c3.cin, c3.cout, n1.cout));
+      }
+    }
     const int t = cur;
     cur = other;
     other = t;
@@ -755,6 +855,8 @@ int irp_resnet50_create(irp_resnet50** out, int max_batch) {
   net->stem_mode = mode ? atoi(mode) : 3;
   if (net->stem_mode < 0 || net->stem_mode > 3) net->stem_mode = 3;
   net->plans.resize(sp.size());
+  net->chains.resize(sp.size());
+  if (const char* cl = getenv("IRP_CHAIN")) net->chain_level = atoi(cl);
   net->weights.assign(sp.size(), nullptr);
   net->biases.assign(sp.size(), nullptr);
   net->out_buf.assign(sp.size(), -1);
@@ -895,9 +997,10 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
     }
     size_t i = 1;
     int last = 0;
+    bool conv1_done = false;  // this block's conv1 was already produced by the previous block's chained conv3
     while (i < sp.size()) {
       const bool has_ds = (i + 3 < sp.size()) && sp[i + 3].role == 4;
-      IRP_TRY(launch_conv(net->plans[i], mb, st));
+      if (!conv1_done) IRP_TRY(launch_conv(net->plans[i], mb, st));
       IRP_TRY(capture(static_cast<int>(i)));
       IRP_TRY(launch_conv(net->plans[i + 1], mb, st));
       IRP_TRY(capture(static_cast<int>(i + 1)));
@@ -905,7 +1008,14 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
         IRP_TRY(launch_conv(net->plans[i + 3], mb, st));
         IRP_TRY(capture(static_cast<int>(i + 3)));
       }
-      IRP_TRY(launch_conv(net->plans[i + 2], mb, st));
+      const ChainPlan& ch = net->chains[i + 2];
+      if (ch.valid) {
+        IRP_TRY(launch_chain(ch, static_cast<long long>(mb) * ch.rows_per_image, st));
+        conv1_done = true;
+      } else {
+        IRP_TRY(launch_conv(net->plans[i + 2], mb, st));
+        conv1_done = false;
+      }
       IRP_TRY(capture(static_cast<int>(i + 2)));
       last = static_cast<int>(i + 2);
       i += has_ds ? 4 : 3;
@@ -928,6 +1038,15 @@ int irp_resnet50_embed_capture(irp_resnet50* net, const void* d_x_nhwc4p, int ba
                                int capture_index, void* d_capture_bf16, size_t capacity_elems, void* stream) {
   return resnet50_forward(net, d_x_nhwc4p, batch, d_embed, capture_index, d_capture_bf16, capacity_elems,
                           static_cast<cudaStream_t>(stream));
+}
+
+int irp_conv1x1_chain(const void* d_t2, const void* d_w3, const float* d_b3, const void* d_residual, void* d_y,
+                      const void* d_w1, const float* d_b1, void* d_t1, int64_t rows, int K1, int N1, int N2,
+                      void* stream) {
+  IRP_REQUIRE(d_t2 && d_w3 && d_b3 && d_residual && d_y && d_w1 && d_b1 && d_t1 && rows > 0, "conv chain: bad argument");
+  ChainPlan plan;
+  IRP_TRY(plan_chain(&plan, d_t2, d_w3, d_b3, d_residual, d_y, d_w1, d_b1, d_t1, rows, 1, K1, N1, N2));
+  return launch_chain(plan, rows, static_cast<cudaStream_t>(stream));
 }
 
 int irp_conv2d_nhwc(const void* d_x, const void* d_w, const float* d_bias, const void* d_residual, void* d_out,

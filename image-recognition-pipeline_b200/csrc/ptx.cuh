@@ -51,11 +51,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Spin on the barrier phase.  A wait that never completes is a protocol bug; trap after ~seconds instead of
-// hanging the GPU (the launch then fails with an error the host reports through irp_last_error()).
+// hanging the GPU (the launch then fails with an error the host reports through irp_last_error()).  A legitimate
+// wait lasts microseconds; 2^22 polls of a suspending try_wait are seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 22)) __trap();
   }
 }
 

@@ -101,6 +101,15 @@ int irp_resnet50_embed_capture(irp_resnet50* net, const void* d_x_nhwc4p, int ba
 int irp_conv2d_nhwc(const void* d_x, const void* d_w, const float* d_bias, const void* d_residual, void* d_out,
                     int B, int H, int W, int Cin, int Cout, int ksize, int stride, int relu, void* stream);
 
+/* Two chained 1x1 convolutions (a bottleneck's conv3 + residual + ReLU, then the next bottleneck's conv1 + ReLU),
+ * the fused form the trunk uses at the layer1 / layer2 block junctions; exposed for parity tests.
+ *   y  [rows,N1] = relu(t2 [rows,K1] . w3[N1,K1]^T + b3 + residual [rows,N1])
+ *   t1 [rows,N2] = relu(y . w1[N2,N1]^T + b1)
+ * all bf16 row-major, biases fp32.  K1 % 64 == 0, N1 % 128 == 0, N1 <= 1024, N2 in {64,128,256}. */
+int irp_conv1x1_chain(const void* d_t2, const void* d_w3, const float* d_b3, const void* d_residual, void* d_y,
+                      const void* d_w1, const float* d_b1, void* d_t1, int64_t rows, int K1, int N1, int N2,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * A3  PCA  --  replaces PCA(n_components).fit_transform at functions/data_curation.py:700-701 with the exact
  * covariance route (sklearn/decomposition/_pca.py:587-640 covariance_eigh, _base.py:151-159 transform,

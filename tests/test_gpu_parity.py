@@ -164,6 +164,39 @@ def test_conv2d_matches_torch(lib, B, H, Cin, Cout, k, stride, relu, residual):
     assert ((out.float() - ref).abs().max() / ref.abs().max()).item() < 6e-3
 
 
+@pytest.mark.parametrize("rows,K1,N1,N2", [
+    (128, 64, 128, 64),          # one tile, one pass
+    (300, 64, 128, 64),          # 3 M tiles: ragged last tile + a phantom tile in the last CTA pair
+    (1000, 64, 256, 64),         # layer1 junction, ragged
+    (2 * 3136, 64, 256, 128),    # layer1 -> layer2 junction
+    (3 * 784, 128, 512, 128),    # layer2 junction
+    (2 * 784, 128, 512, 256),    # layer2 -> layer3 junction
+    (5 * 196, 256, 1024, 256),   # layer3 junction (8 passes)
+    (40000, 64, 256, 64),        # many tiles per CTA pair: ring / accumulator recycling
+])
+def test_conv1x1_chain_matches_torch(lib, rows, K1, N1, N2):
+    """conv3 + residual + ReLU chained with the next block's conv1 + ReLU (conv_chain.cuh) against fp32 torch, with
+    the intermediate rounded to bf16 exactly where the kernel rounds it."""
+    from irp_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(rows + K1 + N1 + N2)
+    t2 = torch.randn(rows, K1, device="cuda", generator=g).bfloat16()
+    w3 = (torch.randn(N1, K1, device="cuda", generator=g) / K1 ** 0.5).bfloat16()
+    b3 = torch.randn(N1, device="cuda", generator=g)
+    res = torch.randn(rows, N1, device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn(N2, N1, device="cuda", generator=g) / N1 ** 0.5).bfloat16()
+    b1 = torch.randn(N2, device="cuda", generator=g)
+    y = torch.full((rows, N1), float("nan"), device="cuda").bfloat16()
+    t1 = torch.full((rows, N2), float("nan"), device="cuda").bfloat16()
+    _lib.check(lib.irp_conv1x1_chain(_ptr(t2), _ptr(w3), _ptr(b3), _ptr(res), _ptr(y), _ptr(w1), _ptr(b1), _ptr(t1),
+                                     rows, K1, N1, N2, _stream()), "irp_conv1x1_chain")
+    torch.cuda.synchronize()
+    y_ref = (t2.float() @ w3.float().t() + b3 + res.float()).relu()
+    assert not torch.isnan(y.float()).any() and not torch.isnan(t1.float()).any()
+    assert ((y.float() - y_ref).abs().max() / y_ref.abs().max()).item() < 6e-3
+    t1_ref = (y.float() @ w1.float().t() + b1).relu()       # from the kernel's own bf16 intermediate
+    assert ((t1.float() - t1_ref).abs().max() / t1_ref.abs().max()).item() < 6e-3
+
+
 def test_conv2d_rejects_unsupported_shapes(lib):
     x = torch.zeros(1, 8, 8, 48, device="cuda", dtype=torch.bfloat16)
     st = lib.irp_conv2d_nhwc(_ptr(x), _ptr(x), _ptr(x), None, _ptr(x), 1, 8, 8, 48, 64, 1, 1, 0, _stream())
