@@ -273,7 +273,8 @@ def run_ours(args, rank, local_rank, world):
     def step(from_host=False, src=None):
         res = stage.run(src if src is not None else packed, ids, N_CLASSES, from_host=from_host)
         if from_host:  # what process_image_directory / detect_outliers hand back to the host
-            out = (res.features.cpu(), res.z[: len(packed)].cpu(), res.class_outliers.cpu(), res.global_outliers.cpu())
+            out = (stage.to_host(res.features, "features"), stage.to_host(res.z[: len(packed)], "z"),
+                   stage.to_host(res.class_outliers, "class_flags"), stage.to_host(res.global_outliers, "global_flags"))
             return res, out
         return res, None
 

@@ -120,7 +120,7 @@ def process_image_directory(root_dir, device, transform, batch_size=32, model=No
                 feats = stage.embed_packed(pack_images(pend_imgs), from_host=True)
             else:
                 feats = model.trunk.embed_nchw(torch.stack(pend_imgs))
-            features.append(feats.cpu().numpy())
+            features.append(np.array(stage.to_host(feats, "batch").numpy()))  # pinned staging buffer, then an owned copy
             labels.extend(pend_labels)
             paths.extend(pend_paths)
         except Exception as e:  # keep the reference's skip-and-continue contract at batch granularity

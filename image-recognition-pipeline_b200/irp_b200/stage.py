@@ -234,6 +234,26 @@ class OutlierStage:
         self.global_nn, self.global_cont = int(global_n_neighbors), float(global_contamination)
         self.pg = process_group
         self.copy_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._pinned = {}
+
+    # ---- device -> host ----
+    def to_host(self, t: torch.Tensor, slot: str = "default") -> torch.Tensor:
+        """Copy a device tensor into a reusable PINNED host buffer (one per `slot`) and return the host view.
+
+        `tensor.cpu()` lands in pageable memory and runs at ~2 GB/s (100 ms for the 221 MB feature matrix of 27k
+        images); a pinned destination makes the same copy a single ~5 ms DMA.  The view is valid until the next call
+        with the same slot."""
+        if not t.is_cuda:
+            return t
+        n = t.numel() * t.element_size()
+        buf = self._pinned.get(slot)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True)
+            self._pinned[slot] = buf
+        host = buf[:n].view(t.dtype).view(t.shape)
+        host.copy_(t.contiguous(), non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return host
 
     # ---- distributed helpers ----
     def _dist(self):
