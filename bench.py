@@ -233,16 +233,23 @@ class TimedBackend:
         return out
 
 
-def launches_per_step(n_images, batch, dim, multi_group=True):
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the 50 kernels of ONE irp_resnet50_embed call at batch 256,
+# from the ncu pass committed as profiles/r01_ncu_trunk_traffic_v4.csv (6 645 MB read + 4 513 MB written).
+TRUNK_DRAM_BYTES_PER_CALL = 11.158e9
+
+
+def launches_per_step(n_images, batch, dim, max_taps):
     """Kernels of libirp_b200.so launched per step (counted from the launch sites in csrc/*.cu)."""
     batches = (n_images + batch - 1) // batch
-    per_batch = 2 + 54           # resample_plan + resample ; stem+pool, 52 convs, avgpool
+    pre = 2 + (1 if max_taps > 6 else 0)  # resample_plan + fast path (+ generic many-tap path)
+    trunk = 50                   # stem+pool, 16 3x3, 4 downsample, 9 conv1, 9 conv3, 7 chained conv3+conv1, avgpool
+    per_batch = pre + trunk
     cov = 3                      # split_transpose, add_count, cov_gemm
     fit = 1 + (dim - 1) + 5      # assemble, tridiag steps, bisect, inverse iteration, mgs, back-transform (+clip)
     fit += 1
     transform = 1
-    lof_grouped = 3 + 6          # count/scan/scatter + sqnorm, knn, lrd, score, percentile, flag
-    lof_global = 1 + 6
+    lof_grouped = 3 + 9          # count/scan/scatter + sqnorm, gather, knn, lrd, score, unsort, percentile, flag
+    lof_global = 1 + 9
     return batches * per_batch + cov + fit + transform + lof_grouped + lof_global
 
 
@@ -360,9 +367,11 @@ def run_ours(args, rank, local_rank, world):
                          "no explicit flush",
                    "parallelism": f"dp{world}: images sharded, one all-reduce of the PCA partial sums"},
         "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": conv_tflops / peaks["tflops_sustained"], "traffic": None,
-                     "kernel": "conv_gemm2_kernel / conv3x3_c64_kernel / stem_pool_kernel (53 conv launches per "
-                               "irp_resnet50_embed call, batch 256)",
+                     "frac": conv_tflops / peaks["tflops_sustained"], "traffic": TRUNK_DRAM_BYTES_PER_CALL,
+                     "traffic_source": "ncu dram__bytes_read+write over the 50 kernels of one trunk call, "
+                                       "profiles/r01_ncu_trunk_traffic_v4.csv",
+                     "kernel": "conv_gemm2_kernel / conv_chain_kernel / conv3x3_c64_kernel / stem_pool_kernel (the 53 "
+                               "convolutions of one irp_resnet50_embed call, batch 256)",
                      "per_launch": f"{FLOPS_PER_IMAGE:.4e} FLOP/image x {BATCH} images per trunk call; "
                                    f"{calls} calls timed with CUDA events, mean {emb_ms / max(calls, 1):.3f} ms",
                      "peak_source": f"{peaks['source']} bf16_tflops_sustained"},
@@ -373,7 +382,7 @@ def run_ours(args, rank, local_rank, world):
         "stage_ms": {"preprocess": pre_ms / args.steps, "trunk": emb_ms / args.steps,
                      "pca_lof_other": ms_step - (pre_ms + emb_ms) / args.steps},
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": launches_per_step(N_IMAGES, BATCH, 2048) * args.steps,
+        "gpu_launches": launches_per_step(N_IMAGES, BATCH, 2048, packed.max_taps) * args.steps,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
