@@ -16,6 +16,8 @@
 //                          registers, LUT normalise, staged in shared memory and written with 16-byte stores.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.h"
 
 namespace irp {
@@ -475,7 +477,7 @@ __device__ __forceinline__ void resample_fast_body(uint8_t* smem, const uint8_t*
 }
 
 template <int LAYOUT, int TH>
-__global__ void __launch_bounds__(kThreads, 3) resample_fast_kernel(const uint8_t* __restrict__ pixels,
+__global__ void __launch_bounds__(kThreads, (TH <= 8 ? 3 : (TH <= 16 ? 2 : 1))) resample_fast_kernel(const uint8_t* __restrict__ pixels,
                                                                     const int64_t* __restrict__ offsets,
                                                                     const int32_t* __restrict__ hw, int max_taps,
                                                                     const int32_t* __restrict__ plan,
@@ -514,36 +516,104 @@ static size_t resample_smem_bytes(int max_taps, int layout) {
 
 using namespace irp;
 
+template <int LAYOUT, int TH>
+static int launch_fast(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
+                       int max_taps, const int32_t* plan, const int32_t* img_taps, __nv_bfloat16* out,
+                       cudaStream_t st) {
+  const size_t smem = fast_smem_bytes<TH>(LAYOUT);
+  auto k = resample_fast_kernel<LAYOUT, TH>;
+  static bool cfg = false;
+  if (!cfg) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cfg = true;
+  }
+  dim3 grid(kCrop / TH, n_images);
+  k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, img_taps, out);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+// output rows per CTA of the fast path (IRP_PRE_TH = 8 | 16 | 32)
+static int fast_band_rows() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("IRP_PRE_TH");
+    v = e ? atoi(e) : 8;
+    if (v != 8 && v != 16 && v != 32) v = 8;
+  }
+  return v;
+}
+
 template <int LAYOUT>
 static int launch_resample(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
                            int max_taps, const int32_t* plan, const int32_t* img_taps, __nv_bfloat16* out,
                            cudaStream_t st) {
-  constexpr int TH = 8;
-  {
-    const size_t smem = fast_smem_bytes<TH>(LAYOUT);
-    auto k = resample_fast_kernel<LAYOUT, TH>;
-    static bool cfg = false;
-    if (!cfg) {
-      IRP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      cfg = true;
-    }
-    dim3 grid(kCrop / TH, n_images);
-    k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, img_taps, out);
-    IRP_CUDA_OK(cudaGetLastError());
+  switch (fast_band_rows()) {
+    default: IRP_TRY((launch_fast<LAYOUT, 8>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st))); break;
+    case 32: IRP_TRY((launch_fast<LAYOUT, 32>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st))); break;
+    case 16: IRP_TRY((launch_fast<LAYOUT, 16>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st))); break;
   }
-  if (max_taps > kFastTaps) {  // some image may need the generic many-tap path
-    const size_t smem = resample_smem_bytes(max_taps, LAYOUT);
-    IRP_REQUIRE(smem <= 227 * 1024, "preprocess: max_taps %d needs %zu bytes of shared memory", max_taps, smem);
-    auto k = resample_kernel<LAYOUT>;
-    static size_t cfg = 0;
-    if (smem > 48 * 1024 && smem > cfg) {
-      IRP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      cfg = smem;
-    }
-    dim3 grid(kCrop / kBandRows, n_images);
-    k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, img_taps, out);
-    IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+// The rare images that need more than kFastTaps taps (downscale > 2.5x) run through the generic kernel: a few
+// long CTAs per image.  After the fast path they would be a pure tail (112 us for one 1200x1200 image against
+// 158 us for the other 255 images of a batch), so they run CONCURRENTLY on a side stream: fork after the plan
+// kernel, join after the fast path.  The two kernels write disjoint images.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int side_stream(SideStream** out) {
+  static SideStream per_device[64];
+  int dev = 0;
+  IRP_CUDA_OK(cudaGetDevice(&dev));
+  IRP_REQUIRE(dev >= 0 && dev < 64, "preprocess: device index %d", dev);
+  SideStream& s = per_device[dev];
+  if (s.stream == nullptr) {
+    // highest priority: its few long CTAs must get SM slots while the fast path's thousands of CTAs are queued
+    int least = 0, greatest = 0;
+    IRP_CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    IRP_CUDA_OK(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, greatest));
+    IRP_CUDA_OK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    IRP_CUDA_OK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
   }
+  *out = &s;
+  return IRP_OK;
+}
+
+template <int LAYOUT>
+static int launch_generic(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
+                          int max_taps, const int32_t* plan, const int32_t* img_taps, __nv_bfloat16* out,
+                          cudaStream_t st) {
+  const size_t smem = resample_smem_bytes(max_taps, LAYOUT);
+  IRP_REQUIRE(smem <= 227 * 1024, "preprocess: max_taps %d needs %zu bytes of shared memory", max_taps, smem);
+  auto k = resample_kernel<LAYOUT>;
+  static size_t cfg = 0;
+  if (smem > 48 * 1024 && smem > cfg) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cfg = smem;
+  }
+  dim3 grid(kCrop / kBandRows, n_images);
+  k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, img_taps, out);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+template <int LAYOUT>
+static int launch_both(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
+                       int max_taps, const int32_t* plan, const int32_t* img_taps, __nv_bfloat16* out,
+                       cudaStream_t st) {
+  if (max_taps <= kFastTaps)  // no image can need the generic path
+    return launch_resample<LAYOUT>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st);
+  SideStream* side = nullptr;
+  IRP_TRY(side_stream(&side));
+  IRP_CUDA_OK(cudaEventRecord(side->fork, st));  // the plan kernel (and the caller's earlier work) precede both
+  IRP_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  IRP_TRY(launch_generic<LAYOUT>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, side->stream));
+  IRP_CUDA_OK(cudaEventRecord(side->join, side->stream));
+  IRP_TRY(launch_resample<LAYOUT>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st));
+  IRP_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
   return IRP_OK;
 }
 
@@ -576,10 +646,10 @@ int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int3
   resample_plan_kernel<<<n_images, 2 * kCrop, 0, st>>>(d_hw, n_images, max_taps, plan, status, img_taps);
   IRP_CUDA_OK(cudaGetLastError());
   if (out_layout == IRP_LAYOUT_NHWC4P)
-    return launch_resample<IRP_LAYOUT_NHWC4P>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps,
-                                              static_cast<__nv_bfloat16*>(d_out), st);
-  return launch_resample<IRP_LAYOUT_NCHW>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps,
+    return launch_both<IRP_LAYOUT_NHWC4P>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps,
                                           static_cast<__nv_bfloat16*>(d_out), st);
+  return launch_both<IRP_LAYOUT_NCHW>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps,
+                                      static_cast<__nv_bfloat16*>(d_out), st);
 }
 
 /* Host-side view of the resize/crop geometry (used by the Python mirror to size max_taps and by tests). */
