@@ -116,7 +116,8 @@ __device__ __forceinline__ void list_insert(double* ld, int32_t* li, int K, doub
   int pos = 0;
   for (int s0 = 0; s0 < K; s0 += 32) {
     const int s = s0 + lane;
-    const bool le = (s < K) && (ld[s] <= dc);
+    // position by (distance, candidate index): the result does not depend on the order candidates arrive in
+    const bool le = (s < K) && (ld[s] < dc || (ld[s] == dc && li[s] < jc));
     pos += __popc(__ballot_sync(0xffffffffu, le));
   }
   // shift [pos, K-2] -> [pos+1, K-1]
@@ -274,13 +275,296 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restric
 constexpr int kKnnMaxResidentDim = 128;
 
 __global__ void gather_sorted_kernel(const float* __restrict__ z, const int32_t* __restrict__ order, long long n,
-                                     int dim, int dpad, double* __restrict__ zs) {
+                                     int dim, int dpad, double* __restrict__ zs, float* __restrict__ zs32) {
   const long long total = n * dpad;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / dpad;
     const int j = static_cast<int>(i - r * dpad);
-    zs[i] = j < dim ? static_cast<double>(z[static_cast<size_t>(order[r]) * dim + j]) : 0.0;
+    const float v = j < dim ? z[static_cast<size_t>(order[r]) * dim + j] : 0.f;
+    zs[i] = static_cast<double>(v);
+    zs32[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Filtered search (default): the 64 x 128 x dpad distance block is evaluated in fp32 (FFMA, 4 x 8 register tiles)
+// and used only as a CONSERVATIVE FILTER: a candidate is re-evaluated in fp64 -- with exactly the arithmetic of
+// knn_resident_kernel, so results are bit-identical -- iff  d2_fp32 <= tau + E (|q|^2 + |c|^2), where tau is the
+// query's current k-th best squared distance and E bounds the fp32 evaluation error of |q|^2 + |c|^2 - 2 q.c
+// (inputs are exact: the rows ARE float32; the dot product contributes at most dpad 2^-24 sum|q_j c_j| <=
+// dpad 2^-25 (|q|^2+|c|^2), the norms and the final three operations a few ulps of |q|^2+|c|^2; E = 4 (dpad+8)
+// 2^-24 leaves a factor > 4).  Every true neighbour passes (its exact d2 <= final tau <= current tau), so the
+// k-NN lists equal those of the exhaustive fp64 search; after the first tile only ~k ln(n/k) candidates per query
+// take the fp64 path.
+// dynamic smem: Qs[dpad][64] f32, Cs[dpad][128] f32, csq[128] f32, tauf[64] f32, wl[8][512] u16, wlc[8] i32,
+//               ld[64][k] f64, li[64][k] i32
+// ------------------------------------------------------------------------------------------------------------
+// k-best set kept UNSORTED with its maximum tracked: an accepted candidate overwrites the maximum and the new
+// maximum is found by the whole warp (k/32 elements per lane + 5 shuffle steps).  Order is (distance, index).
+struct KBestTop {
+  double d;
+  int32_t idx;
+  int32_t pos;
+};
+__device__ __forceinline__ bool kb_greater(double d0, int32_t i0, double d1, int32_t i1) {
+  return d0 > d1 || (d0 == d1 && i0 > i1);
+}
+__device__ __forceinline__ void kbest_replace_max(double* ld, int32_t* li, int K, double dv, int32_t jc, int lane,
+                                                  KBestTop* top) {
+  if (lane == 0) {
+    ld[top->pos] = dv;
+    li[top->pos] = jc;
+  }
+  __syncwarp();
+  double md = -1.0;  // squared distances are >= 0
+  int32_t mi = -2, mp = 0;
+  for (int s = lane; s < K; s += 32) {
+    const double d = ld[s];
+    const int32_t i = li[s];
+    if (kb_greater(d, i, md, mi)) {
+      md = d;
+      mi = i;
+      mp = s;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, md, o);
+    const int32_t oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    const int32_t op = __shfl_xor_sync(0xffffffffu, mp, o);
+    if (kb_greater(od, oi, md, mi) || (od == md && oi == mi && op < mp)) {
+      md = od;
+      mi = oi;
+      mp = op;
+    }
+  }
+  if (lane == 0) {
+    top->d = md;
+    top->idx = mi;
+    top->pos = mp;
+  }
+  __syncwarp();
+}
+
+constexpr int kFltCand = 128;   // candidates per step
+constexpr int kFltCap = 256;    // worklist entries per warp
+
+__global__ void __launch_bounds__(kKnnThreads, 2) knn_filter_kernel(const double* __restrict__ zs,
+                                                                 const float* __restrict__ zs32,
+                                                                 const int32_t* __restrict__ gstart, int n_groups,
+                                                                 int dpad, int k, const double* __restrict__ sq,
+                                                                 int part, int n_parts, double* __restrict__ knn_d,
+                                                                 int32_t* __restrict__ knn_i,
+                                                                 double* __restrict__ kdist) {
+  extern __shared__ double shk[];
+  double* ld = shk;                                          // [64][k]
+  int32_t* li = reinterpret_cast<int32_t*>(ld + kKnnTile * k);  // [64][k]
+  float* Qs = reinterpret_cast<float*>(li + kKnnTile * k + ((kKnnTile * k) & 1));  // 8-byte aligned
+  float* Cs = Qs + dpad * kKnnTile;
+  float* csq = Cs + dpad * kFltCand;
+  float* tauf = csq + kFltCand;
+  uint16_t* wl = reinterpret_cast<uint16_t*>(tauf + kKnnTile);
+  int* wlc = reinterpret_cast<int*>(wl + 8 * kFltCap);
+  KBestTop* tops = reinterpret_cast<KBestTop*>(wlc + 8);  // [64], 16-byte entries
+
+  if (static_cast<int>(blockIdx.x % n_parts) != part) return;
+  int tile = blockIdx.x;
+  int g = 0, g0 = 0, g1 = 0;
+  for (; g < n_groups; ++g) {
+    g0 = gstart[g];
+    g1 = gstart[g + 1];
+    const int tiles = (g1 - g0 + kKnnTile - 1) / kKnnTile;
+    if (tile < tiles) break;
+    tile -= tiles;
+  }
+  if (g >= n_groups) return;
+  const int ng = g1 - g0;
+  const int q0 = g0 + tile * kKnnTile;
+  const int K = max(1, min(k, ng - 1));  // _lof.py:293
+  const float E = 4.0f * static_cast<float>(dpad + 8) * 5.9604645e-8f;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kKnnTile * k; i += kKnnThreads) {
+    ld[i] = INFINITY;
+    li[i] = -1;
+  }
+  if (tid < kKnnTile) {
+    tauf[tid] = INFINITY;
+    tops[tid].d = INFINITY;
+    tops[tid].idx = -1;
+    tops[tid].pos = 0;
+  }
+  if (tid < 8) wlc[tid] = 0;
+  // query tile, transposed: thread (r = tid % 64, h = tid / 64) moves float4 index h + 4u of row r
+  const int n4 = dpad >> 2;
+  {
+    const int r = tid & 63, h = tid >> 6;
+    const float* row = zs32 + static_cast<size_t>(min(q0 + r, g1 - 1)) * dpad;
+    for (int jq = h; jq < n4; jq += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(row + 4 * jq);
+      Qs[(4 * jq + 0) * kKnnTile + r] = v.x;
+      Qs[(4 * jq + 1) * kKnnTile + r] = v.y;
+      Qs[(4 * jq + 2) * kKnnTile + r] = v.z;
+      Qs[(4 * jq + 3) * kKnnTile + r] = v.w;
+    }
+  }
+  // candidate tiles: thread (r = tid % 128, h = tid / 128) moves float4 index h + 2u of row r
+  constexpr int kMaxU = kKnnMaxResidentDim / 8;
+  const int cr = tid & 127, ch = tid >> 7;
+  const int n_u = dpad >> 3;
+  float4 pre[kMaxU];
+  float pre_sq = 0.f;
+  auto prefetch = [&](int c0) {
+    const int rowi = min(c0 + cr, g1 - 1);
+    const float* row = zs32 + static_cast<size_t>(rowi) * dpad;
+#pragma unroll
+    for (int u = 0; u < kMaxU; ++u)
+      if (u < n_u) pre[u] = __ldg(reinterpret_cast<const float4*>(row + 4 * (ch + 2 * u)));
+    if (ch == 0) pre_sq = static_cast<float>(sq[rowi]);
+  };
+  prefetch(g0);
+  const int ty = tid >> 4, tx = tid & 15;  // 4 queries x 8 candidates per thread
+  float sqq[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) sqq[a] = static_cast<float>(sq[min(q0 + ty * 4 + a, g1 - 1)]);
+
+  for (int c0 = g0; c0 < g1; c0 += kFltCand) {
+    __syncthreads();  // previous tile: FMA block done with Cs, selection done with tauf / worklists
+#pragma unroll
+    for (int u = 0; u < kMaxU; ++u)
+      if (u < n_u) {
+        const int jq = ch + 2 * u;
+        Cs[(4 * jq + 0) * kFltCand + cr] = pre[u].x;
+        Cs[(4 * jq + 1) * kFltCand + cr] = pre[u].y;
+        Cs[(4 * jq + 2) * kFltCand + cr] = pre[u].z;
+        Cs[(4 * jq + 3) * kFltCand + cr] = pre[u].w;
+      }
+    if (ch == 0) csq[cr] = pre_sq;
+    __syncthreads();
+    if (c0 + kFltCand < g1) prefetch(c0 + kFltCand);
+    const bool dense = (c0 == g0);  // lists are empty: everything passes, skip the filter
+    if (!dense) {
+      float acc[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+      for (int jj = 0; jj < dpad; ++jj) {
+        const float4 qv = *reinterpret_cast<const float4*>(&Qs[jj * kKnnTile + ty * 4]);
+        const float4 ca = *reinterpret_cast<const float4*>(&Cs[jj * kFltCand + tx * 8]);
+        const float4 cb = *reinterpret_cast<const float4*>(&Cs[jj * kFltCand + tx * 8 + 4]);
+        const float q[4] = {qv.x, qv.y, qv.z, qv.w};
+        const float c[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(q[a], c[b], acc[a][b]);
+      }
+      // filter -> per-warp worklists (the warp that owns query ql is ql / 8)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int ql = ty * 4 + a;
+        const int qi = q0 + ql;
+        if (qi >= g1) continue;
+        const float t = tauf[ql];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int cl = tx * 8 + b;
+          const int ci = c0 + cl;
+          const float s = sqq[a] + csq[cl];
+          const float d2 = s - 2.0f * acc[a][b];
+          if (ci < g1 && ci != qi && d2 <= t + E * s) {
+            const int w = ql >> 3;
+            const int idx = atomicAdd(&wlc[w], 1);
+            if (idx < kFltCap) wl[w * kFltCap + idx] = static_cast<uint16_t>((ql << 7) | cl);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- exact fp64 evaluation + insertion: warp w owns queries 8w .. 8w+7 ----
+    {
+      const int cnt = dense ? 0 : wlc[warp];
+      const bool all_pairs = dense || cnt > kFltCap;  // overflow: fall back to every pair of this warp's queries
+      const int total = all_pairs ? 8 * kFltCand : cnt;
+      for (int base = 0; base < total; base += 32) {
+        const int e = base + lane;
+        int ql = -1, cl = 0;
+        if (e < total) {
+          if (all_pairs) {
+            ql = warp * 8 + (e >> 7);
+            cl = e & 127;
+          } else {
+            const int ent = wl[warp * kFltCap + e];
+            ql = ent >> 7;
+            cl = ent & 127;
+          }
+        }
+        double dc = INFINITY;
+        const int qi = q0 + ql, ci = c0 + cl;
+        if (ql >= 0 && qi < g1 && ci < g1 && ci != qi) {
+          // same arithmetic as knn_resident_kernel: sequential fma over the (zero padded) features.  The rows are
+          // float32 values, so the fp32 tiles already in shared memory convert to the fp64 operands exactly.
+          double acc = 0.0;
+#pragma unroll 4
+          for (int jj = 0; jj < dpad; ++jj)
+            acc = fma(static_cast<double>(Qs[jj * kKnnTile + ql]), static_cast<double>(Cs[jj * kFltCand + cl]), acc);
+          dc = fmax(sq[qi] + sq[ci] - 2.0 * acc, 0.0);
+        }
+        // worklist entries arrive in no particular order: a candidate is accepted iff it precedes the heap root in
+        // (distance, candidate index) order, so the final set is the k smallest such pairs whatever the arrival
+        // order -- the same neighbours the in-order exhaustive kernels find.
+        bool cand = false;
+        if (dc < INFINITY) {  // lane-local pre-check against the query's current k-th best (it only ever tightens)
+          const KBestTop t = tops[ql];
+          cand = dc < t.d || (dc == t.d && ci < t.idx);
+        }
+        unsigned pending = __ballot_sync(0xffffffffu, cand);
+        while (pending) {
+          const int src = __ffs(pending) - 1;
+          pending &= pending - 1;
+          const double dv = __shfl_sync(0xffffffffu, dc, src);
+          const int sq_l = __shfl_sync(0xffffffffu, ql, src);
+          const int jc = c0 + __shfl_sync(0xffffffffu, cl, src);
+          KBestTop* top = &tops[sq_l];
+          if (dv < top->d || (dv == top->d && jc < top->idx))
+            kbest_replace_max(ld + sq_l * k, li + sq_l * k, K, dv, jc, lane, top);
+        }
+      }
+      __syncwarp();
+      if (lane < 8) {
+        const double t = tops[warp * 8 + lane].d;
+        float tf = static_cast<float>(t);
+        if (static_cast<double>(tf) < t) tf = nextafterf(tf, INFINITY);  // round up: the filter must not tighten tau
+        tauf[warp * 8 + lane] = tf;
+      }
+      if (lane == 0) wlc[warp] = 0;
+    }
+  }
+  __syncthreads();
+  // write out in ascending (distance, index) order: rank of an element = number of smaller elements
+  for (int qq = 0; qq < 8; ++qq) {
+    const int ql = warp * 8 + qq;
+    if (q0 + ql >= g1) break;
+    const double* qld = ld + ql * k;
+    const int32_t* qli = li + ql * k;
+    const size_t out = static_cast<size_t>(q0 + ql) * k;
+    for (int s = lane; s < k; s += 32) {
+      if (s >= K) {
+        knn_d[out + s] = INFINITY;
+        knn_i[out + s] = -1;
+        continue;
+      }
+      const double d = qld[s];
+      const int32_t ix = qli[s];
+      int rank = 0;
+      for (int t = 0; t < K; ++t) rank += kb_greater(d, ix, qld[t], qli[t]) ? 1 : 0;
+      knn_d[out + rank] = sqrt(d);
+      knn_i[out + rank] = ix;
+      if (rank == K - 1) kdist[q0 + ql] = sqrt(d);
+    }
   }
 }
 
@@ -740,7 +1024,7 @@ size_t irp_lof_workspace_bytes(int64_t n_rows, int dim, int k) {
   b += align_up(n * k * 8, 256);      // knn_d
   b += align_up(n * k * 4, 256);      // knn_i
   b += 3 * align_up(n * 8, 256);      // kdist, lrd, score_sorted (single-part path)
-  if (dim <= kKnnMaxResidentDim) b += align_up(n * static_cast<size_t>((dim + 7) / 8 * 8) * 8, 256);  // sorted fp64 rows
+  if (dim <= kKnnMaxResidentDim) b += align_up(n * static_cast<size_t>((dim + 7) / 8 * 8) * 12, 256);  // sorted fp64 + fp32 rows
   return b + 1024;
 }
 
@@ -820,17 +1104,37 @@ int irp_lof_knn_part(const float* d_z, int64_t n_rows, int dim, const int32_t* d
     const int dpad = (dim + 7) / 8 * 8;
     const long long total = static_cast<long long>(n) * dpad;
     const unsigned gblocks = static_cast<unsigned>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
-    gather_sorted_kernel<<<gblocks, 256, 0, st>>>(d_z, w.sr.order, n_rows, dim, dpad, w.zs);
-    const size_t smem = (2 * static_cast<size_t>(dpad) * kKnnTile + kKnnTile * (kKnnTile + 1) +
-                         static_cast<size_t>(kKnnTile) * k) * 8 + static_cast<size_t>(kKnnTile) * k * 4;
-    static size_t cfg = 0;
-    if (smem > cfg) {
-      IRP_CUDA_OK(cudaFuncSetAttribute(knn_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-      cfg = smem;
+    float* zs32 = reinterpret_cast<float*>(w.zs + n * dpad);
+    gather_sorted_kernel<<<gblocks, 256, 0, st>>>(d_z, w.sr.order, n_rows, dim, dpad, w.zs, zs32);
+    static int exhaustive = -1;  // IRP_KNN_EXHAUSTIVE=1: fp64 evaluation of every pair (A/B runs)
+    if (exhaustive < 0) {
+      const char* e = getenv("IRP_KNN_EXHAUSTIVE");
+      exhaustive = (e && atoi(e) != 0) ? 1 : 0;
     }
-    knn_resident_kernel<<<knn_grid, kKnnThreads, smem, st>>>(w.zs, w.sr.gstart, n_groups, dpad, k, w.sq, part, n_parts,
-                                                             w.knn_d, w.knn_i, d_kdist);
+    if (exhaustive) {
+      const size_t smem = (2 * static_cast<size_t>(dpad) * kKnnTile + kKnnTile * (kKnnTile + 1) +
+                           static_cast<size_t>(kKnnTile) * k) * 8 + static_cast<size_t>(kKnnTile) * k * 4;
+      static size_t cfg = 0;
+      if (smem > cfg) {
+        IRP_CUDA_OK(cudaFuncSetAttribute(knn_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+        cfg = smem;
+      }
+      knn_resident_kernel<<<knn_grid, kKnnThreads, smem, st>>>(w.zs, w.sr.gstart, n_groups, dpad, k, w.sq, part,
+                                                               n_parts, w.knn_d, w.knn_i, d_kdist);
+    } else {
+      const size_t lists = static_cast<size_t>(kKnnTile) * k * 12 + 8;
+      const size_t smem = lists + (static_cast<size_t>(dpad) * (kKnnTile + kFltCand) + kFltCand + kKnnTile) * 4 +
+                          8 * kFltCap * 2 + 64 + kKnnTile * 16;
+      static size_t cfg = 0;
+      if (smem > cfg) {
+        IRP_CUDA_OK(cudaFuncSetAttribute(knn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+        cfg = smem;
+      }
+      knn_filter_kernel<<<knn_grid, kKnnThreads, smem, st>>>(w.zs, zs32, w.sr.gstart, n_groups, dpad, k, w.sq, part,
+                                                             n_parts, w.knn_d, w.knn_i, d_kdist);
+    }
   } else {
     const size_t smem = (2 * kKnnDChunk * kKnnTile + kKnnTile * (kKnnTile + 1) + static_cast<size_t>(kKnnTile) * k) * 8 +
                         static_cast<size_t>(kKnnTile) * k * 4;
