@@ -12,6 +12,7 @@
 #include "conv_gemm2.cuh"
 #include "conv3x3_c64.cuh"
 #include "conv_chain.cuh"
+#include "l1_block.cuh"
 #include "stem_conv.cuh"
 
 namespace irp {
@@ -663,6 +664,100 @@ static int launch_chain(const ChainPlan& plan, long long rows, cudaStream_t stre
   }
 }
 
+// conv2 + conv3 + next conv1 of a layer1 bottleneck in one launch (l1_block.cuh)
+struct L1Plan {
+  L1BlockParams p;
+  int n2 = 0;
+  bool valid = false;
+};
+
+static int plan_l1_block(L1Plan* plan, const void* t1_in, const void* w2, const float* b2, const void* w3,
+                         const float* b3, const void* residual, void* y, const void* w1, const float* b1, void* t1_out,
+                         int max_batch, int H, int W, int N2) {
+  IRP_REQUIRE(N2 == 64 || N2 == 128, "l1 block: N2 %d", N2);
+  L1BlockParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  auto act_map = [&](CUtensorMap* m, const void* base, uint64_t C, uint32_t bw, uint32_t bh) -> int {
+    uint64_t dims[4] = {C, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(max_batch)};
+    uint64_t strides[3] = {C * 2, static_cast<uint64_t>(W) * C * 2, static_cast<uint64_t>(H) * W * C * 2};
+    uint32_t box[4] = {64, bw, bh, 1};
+    return encode_bf16_map(m, const_cast<void*>(base), 4, dims, strides, box, 128);
+  };
+  auto w_map = [&](CUtensorMap* m, const void* base, uint64_t K, uint64_t N, uint32_t box_n) -> int {
+    uint64_t dims[2] = {K, N};
+    uint64_t strides[1] = {K * 2};
+    uint32_t box[2] = {64, box_n};
+    return encode_bf16_map(m, const_cast<void*>(base), 2, dims, strides, box, 128);
+  };
+  IRP_TRY(act_map(&p.tmIn, t1_in, 64, kC64PatchW, kC64PatchH));
+  IRP_TRY(w_map(&p.tmW2, w2, 576, 64, 32));
+  IRP_TRY(w_map(&p.tmW3, w3, 64, kL1N1, 64));
+  IRP_TRY(w_map(&p.tmW1, w1, kL1N1, N2, N2 / 2));
+  IRP_TRY(act_map(&p.tmRes, residual, kL1N1, kC64TileW, kC64TileH));
+  IRP_TRY(act_map(&p.tmY, y, kL1N1, kC64TileW, kC64TileH));
+  IRP_TRY(act_map(&p.tmOut2, t1_out, N2, kC64TileW, kC64TileH));
+  p.bias2 = b2;
+  p.bias3 = b3;
+  p.bias1 = b1;
+  p.tiles_w = ceil_div(W, kC64TileW);
+  p.tiles_h = ceil_div(H, kC64TileH);
+  plan->n2 = N2;
+  plan->valid = true;
+  return IRP_OK;
+}
+
+// mapped host memory the device writes a record into when an mbarrier wait times out (ptx.cuh mbar_wait_dbg)
+static uint32_t* g_trap_host = nullptr;
+static int ensure_trap_record() {
+  if (g_trap_host != nullptr) return IRP_OK;
+  IRP_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&g_trap_host), 64, cudaHostAllocMapped));
+  memset(g_trap_host, 0, 64);
+  uint32_t* dptr = nullptr;
+  IRP_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_trap_host, 0));
+  IRP_CUDA_OK(cudaMemcpyToSymbol(g_irp_trap_rec, &dptr, sizeof(dptr)));
+  return IRP_OK;
+}
+
+template <int N2>
+static int launch_l1_instance(const L1BlockParams& p, cudaStream_t stream) {
+  using S = L1Smem<N2>;
+  static bool configured = false;
+  auto kernel = l1_block_kernel<N2>;
+  IRP_TRY(ensure_trap_record());
+  if (!configured) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
+    configured = true;
+  }
+  const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int pair_tiles = (tiles + 1) / 2;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (pair_tiles < pairs ? pair_tiles : pairs);
+  if (grid <= 0) return IRP_OK;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kL1Threads);
+  cfg.dynamicSmemBytes = S::kTotalBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  IRP_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
+  return IRP_OK;
+}
+
+static int launch_l1_block(const L1Plan& plan, int batch, cudaStream_t stream) {
+  L1BlockParams p = plan.p;
+  p.tiles_n = batch;
+  return plan.n2 == 64 ? launch_l1_instance<64>(p, stream) : launch_l1_instance<128>(p, stream);
+}
+
 static int grid_for(long long total, int threads) {
   long long g = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -726,12 +821,17 @@ struct irp_resnet50 {
                       // TMA view, 1: im2col + flat GEMM
   std::vector<ConvPlan> plans;
   std::vector<ChainPlan> chains;  // indexed by the conv3 of the first block of a fused junction
+  std::vector<L1Plan> l1blocks;   // indexed by the conv2 of a layer1 block whose conv2+conv3+next conv1 are fused
+  int l1_level = 0;               // IRP_L1_FUSE=1: layer1 blocks through l1_block.cuh.  Off by default: measured 346 us
+                                  // against 81 + 218 us for conv3x3_c64 + conv_chain -- with everything on one SM the
+                                  // kernel is shared-memory-bandwidth bound (~700 KB of smem traffic per 128-pixel tile)
+  int planned_l1 = -1;            // l1 mode the current plans were built for
   int chain_level = 1;            // 0: off, 1: layer1 + layer2 junctions, 2: also layer3
   std::vector<__nv_bfloat16*> weights;
   std::vector<float*> biases;
   std::vector<int> out_buf;  // arena buffer id holding each conv's output
   // arena
-  __nv_bfloat16* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // A, B, T1, T2, DS, STEM
+  __nv_bfloat16* buf[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // A, B, T1, T2, DS, STEM, T1B
   __nv_bfloat16* im2col = nullptr;
   const void* planned_input = nullptr;
   ConvPlan stem_plan_tma;
@@ -743,10 +843,11 @@ static size_t weight_elems(const ConvSpec& s, int stem_mode) {
   return static_cast<size_t>(s.cout) * s.ksize * s.ksize * s.cin;
 }
 
-static int resnet50_plan(irp_resnet50* net, const void* d_x) {
+static int resnet50_plan(irp_resnet50* net, const void* d_x, int l1_mode) {
   const auto& sp = specs();
   const int B = net->micro;
-  enum { A = 0, Bb = 1, T1 = 2, T2 = 3, DS = 4, STEM = 5 };
+  enum { A = 0, Bb = 1, T1 = 2, T2 = 3, DS = 4, STEM = 5, T1B = 6 };
+  int t1_in = T1;  // buffer holding the current block's conv1 output
   // stem
   if (net->stem_mode == 3) {
     StemPoolParams& sp3 = net->stem3;
@@ -788,10 +889,12 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x) {
     const ConvSpec &c1 = sp[i], &c2 = sp[i + 1], &c3 = sp[i + 2];
     IRP_TRY(plan_conv(&net->plans[i], net->buf[cur], net->weights[i], net->biases[i], nullptr, net->buf[T1], B, c1.H,
                       c1.W, c1.cin, c1.cout, 1, 1, 1));
-    net->out_buf[i] = T1;
-    IRP_TRY(plan_conv(&net->plans[i + 1], net->buf[T1], net->weights[i + 1], net->biases[i + 1], nullptr,
+    net->out_buf[i] = t1_in;  // T1 unless the previous block's fused kernel wrote this conv1 output elsewhere
+    IRP_TRY(plan_conv(&net->plans[i + 1], net->buf[t1_in], net->weights[i + 1], net->biases[i + 1], nullptr,
                       net->buf[T2], B, c2.H, c2.W, c2.cin, c2.cout, 3, c2.stride, 1));
     net->out_buf[i + 1] = T2;
+    const int t1_this = t1_in;
+    t1_in = T1;
     const __nv_bfloat16* res = net->buf[cur];
     if (has_ds) {
       const ConvSpec& d = sp[i + 3];
@@ -815,6 +918,17 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x) {
                            net->buf[other], net->weights[nxt], net->biases[nxt], net->buf[T1],
                            static_cast<long long>(B) * c3.H * c3.W, c3.H * c3.W, c3.cin, c3.cout, n1.cout));
       }
+      // layer1 blocks: conv2 + conv3 + next conv1 in one kernel; T1' ping-pongs between T1 and T1B because the
+      // kernel reads its own conv1 input (with halo) while it writes the next one
+      net->l1blocks[i + 1].valid = false;
+      if (l1_mode > 0 && nxt < sp.size() && c2.cin == 64 && c2.cout == 64 && c2.ksize == 3 && c2.stride == 1 &&
+          c3.cout == kL1N1 && (sp[nxt].cout == 64 || sp[nxt].cout == 128)) {
+        const int alt = t1_this == T1 ? T1B : T1;
+        IRP_TRY(plan_l1_block(&net->l1blocks[i + 1], net->buf[t1_this], net->weights[i + 1], net->biases[i + 1],
+                              net->weights[i + 2], net->biases[i + 2], res, net->buf[other], net->weights[nxt],
+                              net->biases[nxt], net->buf[alt], B, c2.H, c2.W, sp[nxt].cout));
+        t1_in = alt;
+      }
     }
     const int t = cur;
     cur = other;
@@ -823,6 +937,7 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x) {
   }
   net->planned_input = d_x;
   net->planned = true;
+  net->planned_l1 = l1_mode;
   return IRP_OK;
 }
 
@@ -856,14 +971,16 @@ int irp_resnet50_create(irp_resnet50** out, int max_batch) {
   if (net->stem_mode < 0 || net->stem_mode > 3) net->stem_mode = 3;
   net->plans.resize(sp.size());
   net->chains.resize(sp.size());
+  net->l1blocks.resize(sp.size());
+  if (const char* lf = getenv("IRP_L1_FUSE")) net->l1_level = atoi(lf);
   if (const char* cl = getenv("IRP_CHAIN")) net->chain_level = atoi(cl);
   net->weights.assign(sp.size(), nullptr);
   net->biases.assign(sp.size(), nullptr);
   net->out_buf.assign(sp.size(), -1);
-  const size_t per_img[6] = {56 * 56 * 256, 56 * 56 * 256, 56 * 56 * 128, 56 * 56 * 64, 56 * 56 * 256,
-                             112 * 112 * 64};
+  const size_t per_img[7] = {56 * 56 * 256, 56 * 56 * 256, 56 * 56 * 128, 56 * 56 * 64, 56 * 56 * 256,
+                             112 * 112 * 64, 56 * 56 * 128};
   cudaError_t e = cudaSuccess;
-  for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+  for (int i = 0; i < 7 && e == cudaSuccess; ++i)
     e = cudaMalloc(reinterpret_cast<void**>(&net->buf[i]), per_img[i] * net->micro * sizeof(__nv_bfloat16));
   if (e == cudaSuccess && net->stem_mode == 1)
     e = cudaMalloc(reinterpret_cast<void**>(&net->im2col),
@@ -936,7 +1053,13 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
                             void* d_capture, size_t capture_capacity, cudaStream_t st) {
   IRP_REQUIRE(net != nullptr && d_x != nullptr && d_embed != nullptr, "embed: null argument");
   IRP_REQUIRE(batch > 0 && batch <= net->max_batch, "embed: batch %d not in [1,%d]", batch, net->max_batch);
-  if (!net->planned || net->planned_input != d_x) IRP_TRY(resnet50_plan(net, d_x));
+  // the fused layer1 kernel never materialises conv2's output: a capture of one of those layers runs unfused
+  int l1_mode = net->l1_level;
+  if (d_capture != nullptr && capture_index >= 0 && capture_index < static_cast<int>(specs().size()) &&
+      specs()[capture_index].role == 2 && specs()[capture_index].cin == 64)
+    l1_mode = 0;
+  if (!net->planned || net->planned_input != d_x || net->planned_l1 != l1_mode)
+    IRP_TRY(resnet50_plan(net, d_x, l1_mode));
   const auto& sp = specs();
   enum { A = 0, STEM = 5 };
   for (int s0 = 0; s0 < batch; s0 += net->micro) {
@@ -1002,14 +1125,20 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
       const bool has_ds = (i + 3 < sp.size()) && sp[i + 3].role == 4;
       if (!conv1_done) IRP_TRY(launch_conv(net->plans[i], mb, st));
       IRP_TRY(capture(static_cast<int>(i)));
-      IRP_TRY(launch_conv(net->plans[i + 1], mb, st));
-      IRP_TRY(capture(static_cast<int>(i + 1)));
+      const L1Plan& l1 = net->l1blocks[i + 1];
+      if (!l1.valid) {
+        IRP_TRY(launch_conv(net->plans[i + 1], mb, st));
+        IRP_TRY(capture(static_cast<int>(i + 1)));
+      }
       if (has_ds) {
         IRP_TRY(launch_conv(net->plans[i + 3], mb, st));
         IRP_TRY(capture(static_cast<int>(i + 3)));
       }
       const ChainPlan& ch = net->chains[i + 2];
-      if (ch.valid) {
+      if (l1.valid) {
+        IRP_TRY(launch_l1_block(l1, mb, st));
+        conv1_done = true;
+      } else if (ch.valid) {
         IRP_TRY(launch_chain(ch, static_cast<long long>(mb) * ch.rows_per_image, st));
         conv1_done = true;
       } else {
@@ -1047,6 +1176,24 @@ int irp_conv1x1_chain(const void* d_t2, const void* d_w3, const float* d_b3, con
   ChainPlan plan;
   IRP_TRY(plan_chain(&plan, d_t2, d_w3, d_b3, d_residual, d_y, d_w1, d_b1, d_t1, rows, 1, K1, N1, N2));
   return launch_chain(plan, rows, static_cast<cudaStream_t>(stream));
+}
+
+int irp_debug_trap_record(uint32_t* out5) {
+  IRP_REQUIRE(out5 != nullptr, "debug_trap_record: null argument");
+  for (int i = 0; i < 5; ++i) out5[i] = g_trap_host ? g_trap_host[i] : 0u;
+  return IRP_OK;
+}
+
+int irp_l1_block(const void* d_t1, const void* d_w2, const float* d_b2, const void* d_w3, const float* d_b3,
+                 const void* d_residual, void* d_y, const void* d_w1, const float* d_b1, void* d_t1_next, int B, int H,
+                 int W, int N2, void* stream) {
+  IRP_REQUIRE(d_t1 && d_w2 && d_b2 && d_w3 && d_b3 && d_residual && d_y && d_w1 && d_b1 && d_t1_next && B > 0 &&
+                  H > 0 && W > 0,
+              "l1 block: bad argument");
+  IRP_REQUIRE(d_t1 != d_t1_next, "l1 block: the next conv1 output must not alias the conv1 input");
+  L1Plan plan;
+  IRP_TRY(plan_l1_block(&plan, d_t1, d_w2, d_b2, d_w3, d_b3, d_residual, d_y, d_w1, d_b1, d_t1_next, B, H, W, N2));
+  return launch_l1_block(plan, B, static_cast<cudaStream_t>(stream));
 }
 
 int irp_conv2d_nhwc(const void* d_x, const void* d_w, const float* d_bias, const void* d_residual, void* d_out,

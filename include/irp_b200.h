@@ -110,6 +110,18 @@ int irp_conv1x1_chain(const void* d_t2, const void* d_w3, const float* d_b3, con
                       const void* d_w1, const float* d_b1, void* d_t1, int64_t rows, int K1, int N1, int N2,
                       void* stream);
 
+/* The fused tail of a layer1 bottleneck + head of the next one (l1_block.cuh), exposed for parity tests:
+ *   t2 = relu(conv3x3(t1 [B,H,W,64], w2 [64,3,3,64]) + b2)      (kept on chip)
+ *   y  [B,H,W,256] = relu(t2 . w3[256,64]^T + b3 + residual [B,H,W,256])
+ *   t1_next [B,H,W,N2] = relu(y . w1[N2,256]^T + b1),  N2 in {64,128};  t1_next must not alias t1. */
+int irp_l1_block(const void* d_t1, const void* d_w2, const float* d_b2, const void* d_w3, const float* d_b3,
+                 const void* d_residual, void* d_y, const void* d_w1, const float* d_b1, void* d_t1_next, int B, int H,
+                 int W, int N2, void* stream);
+
+/* Debugging aid: {source line, blockIdx.x, threadIdx.x, parity, user} of the first mbarrier wait that timed out in
+ * an instrumented kernel (zeros if none).  Host call, valid even after the launch failure it explains. */
+int irp_debug_trap_record(uint32_t* out5);
+
 /* ------------------------------------------------------------------------------------------------------------
  * A3  PCA  --  replaces PCA(n_components).fit_transform at functions/data_curation.py:700-701 with the exact
  * covariance route (sklearn/decomposition/_pca.py:587-640 covariance_eigh, _base.py:151-159 transform,
