@@ -13,6 +13,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.h"
 
 namespace irp {
@@ -96,7 +98,7 @@ __global__ void iota_kernel(int32_t* order, long long n, int32_t* gstart) {
 
 // squared norms in sorted order (fp64)
 __global__ void sqnorm_kernel(const float* __restrict__ z, const int32_t* __restrict__ order, long long n, int dim,
-                              double* __restrict__ sq) {
+                              double* __restrict__ sq, unsigned long long* __restrict__ max_sq_bits) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const float* r = z + static_cast<size_t>(order[i]) * dim;
@@ -106,6 +108,21 @@ __global__ void sqnorm_kernel(const float* __restrict__ z, const int32_t* __rest
     s += v * v;
   }
   sq[i] = s;
+  // non-negative doubles order like their bit patterns
+  if (max_sq_bits != nullptr) atomicMax(max_sq_bits, static_cast<unsigned long long>(__double_as_longlong(s)));
+}
+
+// sort key of a row: (group, first coordinate) -- rows of a group end up ordered by z[.,0], which lets the search
+// stop scanning once the gap in that coordinate alone exceeds the current k-th distance
+__global__ void sort_key_kernel(const float* __restrict__ z, const int32_t* __restrict__ group, long long n, int dim,
+                                unsigned long long* __restrict__ keys, int32_t* __restrict__ vals) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  uint32_t u = __float_as_uint(z[static_cast<size_t>(i) * dim]);
+  u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;  // order-preserving map of float to uint32
+  const unsigned long long g = group ? static_cast<unsigned long long>(static_cast<uint32_t>(group[i])) : 0ull;
+  keys[i] = (g << 32) | u;
+  vals[i] = static_cast<int32_t>(i);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -354,7 +371,8 @@ __global__ void __launch_bounds__(kKnnThreads, 2) knn_filter_kernel(const double
                                                                  const float* __restrict__ zs32,
                                                                  const int32_t* __restrict__ gstart, int n_groups,
                                                                  int dpad, int k, const double* __restrict__ sq,
-                                                                 int part, int n_parts, double* __restrict__ knn_d,
+                                                                 const double* __restrict__ max_sq, int part,
+                                                                 int n_parts, double* __restrict__ knn_d,
                                                                  int32_t* __restrict__ knn_i,
                                                                  double* __restrict__ kdist) {
   extern __shared__ double shk[];
@@ -367,6 +385,7 @@ __global__ void __launch_bounds__(kKnnThreads, 2) knn_filter_kernel(const double
   uint16_t* wl = reinterpret_cast<uint16_t*>(tauf + kKnnTile);
   int* wlc = reinterpret_cast<int*>(wl + 8 * kFltCap);
   KBestTop* tops = reinterpret_cast<KBestTop*>(wlc + 8);  // [64], 16-byte entries
+  double* wmax = reinterpret_cast<double*>(tops + kKnnTile);  // [8] per-warp max of the current k-th distances
 
   if (static_cast<int>(blockIdx.x % n_parts) != part) return;
   int tile = blockIdx.x;
@@ -423,14 +442,52 @@ __global__ void __launch_bounds__(kKnnThreads, 2) knn_filter_kernel(const double
       if (u < n_u) pre[u] = __ldg(reinterpret_cast<const float4*>(row + 4 * (ch + 2 * u)));
     if (ch == 0) pre_sq = static_cast<float>(sq[rowi]);
   };
-  prefetch(g0);
   const int ty = tid >> 4, tx = tid & 15;  // 4 queries x 8 candidates per thread
   float sqq[4];
 #pragma unroll
   for (int a = 0; a < 4; ++a) sqq[a] = static_cast<float>(sq[min(q0 + ty * 4 + a, g1 - 1)]);
 
-  for (int c0 = g0; c0 < g1; c0 += kFltCand) {
-    __syncthreads();  // previous tile: FMA block done with Cs, selection done with tauf / worklists
+  // Rows of a group are sorted by their first coordinate z0, and d^2 >= (z0_q - z0_c)^2.  Candidate tiles are
+  // visited outward from the tile that holds the queries, alternating right / left; a side is finished for good as
+  // soon as the z0 gap between its next tile and the query range exceeds the largest current k-th distance of the
+  // tile's queries (with a margin far above the rounding error of the evaluated distances).  On PCA scores z0 is
+  // the max-variance direction, so most of the O(n^2) work disappears -- and what remains does not grow with n.
+  const int n_ctiles = (ng + kFltCand - 1) / kFltCand;
+  const int tq = (q0 - g0) / kFltCand;
+  const int q_last = min(q0 + kKnnTile, g1) - 1;
+  const double z_lo = zs[static_cast<size_t>(q0) * dpad], z_hi = zs[static_cast<size_t>(q_last) * dpad];
+  const double abs_margin = 1e-9 * (4.0 * max_sq[0] + 1.0);
+  if (tid < 8) wmax[tid] = INFINITY;
+  int t_left = tq, t_right = tq;       // tiles [t_left, t_right] have been visited
+  bool go_right = true;                // side to try first at the next step
+  bool left_done = (tq == 0), right_done = (tq == n_ctiles - 1);
+  // next tile to visit given the pruning threshold, or -1
+  auto next_tile = [&](double tau_max) {
+    const double thr = tau_max * (1.0 + 1e-6) + abs_margin;
+    if (!right_done) {
+      const double gap = zs[static_cast<size_t>(g0 + (t_right + 1) * kFltCand) * dpad] - z_hi;
+      if (gap > 0.0 && gap * gap > thr) right_done = true;
+    }
+    if (!left_done) {
+      const double gap = z_lo - zs[static_cast<size_t>(g0 + t_left * kFltCand - 1) * dpad];
+      if (gap > 0.0 && gap * gap > thr) left_done = true;
+    }
+    int t = -1;
+    if (go_right ? !right_done : left_done && !right_done) t = ++t_right;
+    else if (!left_done) t = --t_left;
+    if (t >= 0) {
+      go_right = !go_right;
+      if (t_right == n_ctiles - 1) right_done = true;
+      if (t_left == 0) left_done = true;
+    }
+    return t;
+  };
+  int cur = tq;
+  prefetch(g0 + cur * kFltCand);
+  bool first = true;
+  while (cur >= 0) {
+    const int c0 = g0 + cur * kFltCand;
+    __syncthreads();  // previous tile: FMA block done with Cs, selection done with tauf / worklists / wmax
 #pragma unroll
     for (int u = 0; u < kMaxU; ++u)
       if (u < n_u) {
@@ -442,8 +499,15 @@ __global__ void __launch_bounds__(kKnnThreads, 2) knn_filter_kernel(const double
       }
     if (ch == 0) csq[cr] = pre_sq;
     __syncthreads();
-    if (c0 + kFltCand < g1) prefetch(c0 + kFltCand);
-    const bool dense = (c0 == g0);  // lists are empty: everything passes, skip the filter
+    // the next tile is chosen with the k-th distances as of the END of the previous step (one step stale, i.e.
+    // conservative), so that its rows can be prefetched behind this tile's arithmetic
+    double tau_max = 0.0;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) tau_max = fmax(tau_max, wmax[w8]);
+    const int nxt = next_tile(tau_max);
+    if (nxt >= 0) prefetch(g0 + nxt * kFltCand);
+    const bool dense = first;  // lists are empty: everything passes, skip the filter
+    first = false;
     if (!dense) {
       float acc[4][8];
 #pragma unroll
@@ -534,14 +598,23 @@ __global__ void __launch_bounds__(kKnnThreads, 2) knn_filter_kernel(const double
         }
       }
       __syncwarp();
+      double t = 0.0;
       if (lane < 8) {
-        const double t = tops[warp * 8 + lane].d;
+        t = tops[warp * 8 + lane].d;
         float tf = static_cast<float>(t);
         if (static_cast<double>(tf) < t) tf = nextafterf(tf, INFINITY);  // round up: the filter must not tighten tau
         tauf[warp * 8 + lane] = tf;
+        if (q0 + warp * 8 + lane >= g1) t = 0.0;  // rows past the group do not hold the scan open
       }
-      if (lane == 0) wlc[warp] = 0;
+      t = fmax(t, __shfl_xor_sync(0xffffffffu, t, 4));
+      t = fmax(t, __shfl_xor_sync(0xffffffffu, t, 2));
+      t = fmax(t, __shfl_xor_sync(0xffffffffu, t, 1));
+      if (lane == 0) {
+        wmax[warp] = t;
+        wlc[warp] = 0;
+      }
     }
+    cur = nxt;
   }
   __syncthreads();
   // write out in ascending (distance, index) order: rank of an element = number of smaller elements
@@ -1016,6 +1089,9 @@ using namespace irp;
 
 extern "C" {
 
+// scratch reserved for cub::DeviceRadixSort (histograms / look-back state; far below this bound for 64-bit keys)
+static size_t lof_sort_tmp_bytes(size_t n) { return (4u << 20) + n * 4; }
+
 size_t irp_lof_workspace_bytes(int64_t n_rows, int dim, int k) {
   if (n_rows <= 0 || dim <= 0 || k <= 0) return 0;
   const size_t n = static_cast<size_t>(n_rows);
@@ -1024,7 +1100,10 @@ size_t irp_lof_workspace_bytes(int64_t n_rows, int dim, int k) {
   b += align_up(n * k * 8, 256);      // knn_d
   b += align_up(n * k * 4, 256);      // knn_i
   b += 3 * align_up(n * 8, 256);      // kdist, lrd, score_sorted (single-part path)
-  if (dim <= kKnnMaxResidentDim) b += align_up(n * static_cast<size_t>((dim + 7) / 8 * 8) * 12, 256);  // sorted fp64 + fp32 rows
+  if (dim <= kKnnMaxResidentDim) {
+    b += align_up(n * static_cast<size_t>((dim + 7) / 8 * 8) * 12, 256);  // sorted fp64 + fp32 rows
+    b += 256 + n * 16 + align_up(n * 4, 256) + lof_sort_tmp_bytes(n);      // max norm, sort keys x2, values, cub scratch
+  }
   return b + 1024;
 }
 
@@ -1092,7 +1171,31 @@ int irp_lof_knn_part(const float* d_z, int64_t n_rows, int dim, const int32_t* d
   IRP_TRY(sort_rows(d_group, n_rows, n_groups, cursor, &sr, st));
   w.sr = sr;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-  sqnorm_kernel<<<blocks, 256, 0, st>>>(d_z, w.sr.order, n_rows, dim, w.sq);
+  const bool resident = dim <= kKnnMaxResidentDim;
+  double* max_sq = nullptr;
+  if (resident) {
+    // re-order the rows of every group by their first coordinate (stable radix sort of (group, z0) keys); the
+    // group boundaries computed above stay valid.  Scratch lives behind the fp64 / fp32 row copies.
+    const size_t dpad = static_cast<size_t>((dim + 7) / 8 * 8);
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(w.zs) + align_up(n * dpad * 12, 256);
+    max_sq = reinterpret_cast<double*>(scratch);
+    unsigned long long* keys_in = reinterpret_cast<unsigned long long*>(scratch + 256);
+    unsigned long long* keys_out = keys_in + n;
+    int32_t* vals_in = reinterpret_cast<int32_t*>(keys_out + n);
+    void* cub_tmp = reinterpret_cast<uint8_t*>(vals_in) + align_up(n * 4, 256);
+    size_t cub_bytes = 0;
+    int end_bit = 32;
+    for (int gmax = n_groups - 1; gmax > 0; gmax >>= 1) ++end_bit;
+    IRP_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys_in, keys_out, vals_in, w.sr.order,
+                                                static_cast<long long>(n), 0, end_bit, st));
+    IRP_REQUIRE(cub_bytes <= lof_sort_tmp_bytes(n), "lof: radix sort needs %zu bytes of scratch", cub_bytes);
+    sort_key_kernel<<<blocks, 256, 0, st>>>(d_z, n_groups > 1 ? d_group : nullptr, n_rows, dim, keys_in, vals_in);
+    IRP_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, vals_in, w.sr.order,
+                                                static_cast<long long>(n), 0, end_bit, st));
+    IRP_CUDA_OK(cudaMemsetAsync(max_sq, 0, sizeof(double), st));
+  }
+  sqnorm_kernel<<<blocks, 256, 0, st>>>(d_z, w.sr.order, n_rows, dim, w.sq,
+                                        reinterpret_cast<unsigned long long*>(max_sq));
   IRP_CUDA_OK(cudaMemsetAsync(d_kdist, 0, n * sizeof(double), st));  // rows of other parts stay 0
   const unsigned knn_grid = static_cast<unsigned>((n + kKnnTile - 1) / kKnnTile + n_groups);
   static int force_generic = -1;
@@ -1125,15 +1228,15 @@ int irp_lof_knn_part(const float* d_z, int64_t n_rows, int dim, const int32_t* d
     } else {
       const size_t lists = static_cast<size_t>(kKnnTile) * k * 12 + 8;
       const size_t smem = lists + (static_cast<size_t>(dpad) * (kKnnTile + kFltCand) + kFltCand + kKnnTile) * 4 +
-                          8 * kFltCap * 2 + 64 + kKnnTile * 16;
+                          8 * kFltCap * 2 + 64 + kKnnTile * 16 + 64;
       static size_t cfg = 0;
       if (smem > cfg) {
         IRP_CUDA_OK(cudaFuncSetAttribute(knn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
         cfg = smem;
       }
-      knn_filter_kernel<<<knn_grid, kKnnThreads, smem, st>>>(w.zs, zs32, w.sr.gstart, n_groups, dpad, k, w.sq, part,
-                                                             n_parts, w.knn_d, w.knn_i, d_kdist);
+      knn_filter_kernel<<<knn_grid, kKnnThreads, smem, st>>>(w.zs, zs32, w.sr.gstart, n_groups, dpad, k, w.sq, max_sq,
+                                                             part, n_parts, w.knn_d, w.knn_i, d_kdist);
     }
   } else {
     const size_t smem = (2 * kKnnDChunk * kKnnTile + kKnnTile * (kKnnTile + 1) + static_cast<size_t>(kKnnTile) * k) * 8 +
