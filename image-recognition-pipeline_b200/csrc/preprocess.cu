@@ -65,9 +65,19 @@ __host__ __device__ inline Geometry compute_geometry(int h, int w) {
 
 __global__ void resample_plan_kernel(const int32_t* __restrict__ hw, int n_images, int max_taps,
                                      int32_t* __restrict__ plan, int32_t* __restrict__ status,
-                                     int32_t* __restrict__ img_taps) {
+                                     int32_t* __restrict__ img_taps, __nv_bfloat16* __restrict__ lut) {
   const int img = blockIdx.x;
   const int j = threadIdx.x;
+  if (img == 0 && lut != nullptr) {
+    // normalisation table for the two-pass path: lut[c*256 + v] = bf16(((v / 255) - mean_c) / std_c)
+    for (int i = j; i < 768; i += blockDim.x) {
+      const int c = i >> 8, v = i & 255;
+      const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+      const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+      const float f = __fdiv_rn(static_cast<float>(v), 255.0f);
+      lut[i] = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(f, mean), stdv));
+    }
+  }
   if (img >= n_images || j >= 2 * kCrop) return;
   const int axis = j / kCrop;  // 0: horizontal (x), 1: vertical (y)
   const int o = j % kCrop;
@@ -493,6 +503,118 @@ __global__ void __launch_bounds__(kThreads, (TH <= 8 ? 3 : (TH <= 16 ? 2 : 1))) 
   else resample_fast_body<LAYOUT, TH, 6>(smem, pixels, offsets, hw, max_taps, plan, out);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Two-pass path (default for images with <= kFastTaps taps): no shared memory, no barriers, full occupancy.
+//   hpass_kernel : one thread per (source row inside the crop window, output column): the horizontal filter is
+//                  applied ONCE per source row (the band kernels recompute the rows shared by adjacent bands) and
+//                  its rounded uint8 result goes to an intermediate [image][row][224*3] that stays in L2;
+//   vpass_kernel : one thread per padded output pixel: vertical filter over the intermediate rows, Pillow's
+//                  rounding, LUT normalisation, and one 8-byte store of the (R, G, B, 0) bf16 pixel (NHWC4P) or
+//                  three 2-byte stores (NCHW); the threads of the 3-pixel border write zeros.
+// The arithmetic is the band kernels' (and Pillow's): acc = 2^21 + sum src * coef, clip8(acc >> 22), twice.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kTwoPassMaxRows = 576;  // >= 224 * 2.5 + 2 * 3 + 2: source rows the crop window of a fast image can need
+constexpr int kHRowsPerCta = 16;
+constexpr int kVRowsPerCta = 8;  // (padded) output rows per CTA of the vertical pass
+
+__global__ void __launch_bounds__(kCrop) hpass_kernel(const uint8_t* __restrict__ pixels,
+                                                     const int64_t* __restrict__ offsets,
+                                                     const int32_t* __restrict__ hw, int max_taps,
+                                                     const int32_t* __restrict__ plan,
+                                                     const int32_t* __restrict__ img_taps,
+                                                     uint8_t* __restrict__ inter) {
+  const int img = blockIdx.y;
+  const int nt = img_taps[img];
+  if (nt > kFastTaps) return;  // the generic kernel handles this image
+  const int T = max_taps;
+  const int32_t* plan_h = plan + (static_cast<size_t>(img) * 2 + 0) * plan_ints_per_axis(T);
+  const int32_t* plan_v = plan + (static_cast<size_t>(img) * 2 + 1) * plan_ints_per_axis(T);
+  const int row_lo = plan_v[0];
+  const int row_hi = plan_v[kCrop - 1] + plan_v[2 * kCrop - 1];  // first + count of the last output row
+  const int r0 = row_lo + blockIdx.x * kHRowsPerCta;
+  if (r0 >= row_hi) return;
+  const int x = threadIdx.x;
+  const int first = plan_h[x], n = plan_h[kCrop + x];
+  int cf[kFastTaps];
+#pragma unroll
+  for (int t = 0; t < kFastTaps; ++t) cf[t] = t < n ? plan_h[2 * kCrop + static_cast<size_t>(x) * T + t] : 0;
+  const int w = hw[2 * img + 1];
+  const size_t row_bytes = static_cast<size_t>(w) * 3;
+  const uint8_t* src = pixels + offsets[img] + static_cast<size_t>(first) * 3;
+  uint8_t* dst = inter + (static_cast<size_t>(img) * kTwoPassMaxRows) * kRowElems + x * 3;
+#pragma unroll 4
+  for (int rr = 0; rr < kHRowsPerCta; ++rr) {
+    const int r = r0 + rr;
+    if (r >= row_hi) break;
+    const uint8_t* sp = src + static_cast<size_t>(r) * row_bytes;
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+#pragma unroll
+    for (int t = 0; t < kFastTaps; ++t) {
+      if (t < n) {  // taps past this column's own count would read past its window: skipped, not zero-weighted
+        a0 += static_cast<int>(__ldg(sp + 3 * t + 0)) * cf[t];
+        a1 += static_cast<int>(__ldg(sp + 3 * t + 1)) * cf[t];
+        a2 += static_cast<int>(__ldg(sp + 3 * t + 2)) * cf[t];
+      }
+    }
+    uint8_t* d = dst + static_cast<size_t>(r - row_lo) * kRowElems;
+    d[0] = static_cast<uint8_t>(clip8_fixed(a0));
+    d[1] = static_cast<uint8_t>(clip8_fixed(a1));
+    d[2] = static_cast<uint8_t>(clip8_fixed(a2));
+  }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) vpass_kernel(const int32_t* __restrict__ plan, int max_taps,
+                                                    const int32_t* __restrict__ img_taps,
+                                                    const uint8_t* __restrict__ inter,
+                                                    const __nv_bfloat16* __restrict__ lut,
+                                                    __nv_bfloat16* __restrict__ out) {
+  const int img = blockIdx.y;
+  if (img_taps[img] > kFastTaps) return;
+  const int T = max_taps;
+  const int32_t* plan_v = plan + (static_cast<size_t>(img) * 2 + 1) * plan_ints_per_axis(T);
+  constexpr int kSide = LAYOUT == IRP_LAYOUT_NHWC4P ? kPad : kCrop;  // rows / columns this launch covers
+  constexpr int kBorder = LAYOUT == IRP_LAYOUT_NHWC4P ? 3 : 0;
+  const int px = threadIdx.x;          // (padded) output column
+  if (px >= kSide) return;
+  const int x = px - kBorder;
+  const int row_lo = plan_v[0];
+  const uint16_t* l16 = reinterpret_cast<const uint16_t*>(lut);
+#pragma unroll 2
+  for (int py = blockIdx.x * kVRowsPerCta; py < min(kSide, (static_cast<int>(blockIdx.x) + 1) * kVRowsPerCta); ++py) {
+  const int y = py - kBorder;          // (padded) output row py
+  const bool inside = y >= 0 && y < kCrop && x >= 0 && x < kCrop;
+  uint32_t rgb[3] = {0u, 0u, 0u};  // bf16 bit patterns
+  if (inside) {
+    const int vf = plan_v[y], vn = plan_v[kCrop + y];
+    const int32_t* vc = plan_v + 2 * kCrop + static_cast<size_t>(y) * T;
+    const uint8_t* ip = inter + (static_cast<size_t>(img) * kTwoPassMaxRows + (vf - row_lo)) * kRowElems + x * 3;
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+    for (int t = 0; t < vn; ++t) {
+      const int c = vc[t];
+      const uint8_t* rp = ip + static_cast<size_t>(t) * kRowElems;
+      a0 += static_cast<int>(rp[0]) * c;
+      a1 += static_cast<int>(rp[1]) * c;
+      a2 += static_cast<int>(rp[2]) * c;
+    }
+    rgb[0] = __ldg(l16 + clip8_fixed(a0));
+    rgb[1] = __ldg(l16 + 256 + clip8_fixed(a1));
+    rgb[2] = __ldg(l16 + 512 + clip8_fixed(a2));
+  }
+  if (LAYOUT == IRP_LAYOUT_NHWC4P) {
+    uint2 o;
+    o.x = rgb[0] | (rgb[1] << 16);
+    o.y = rgb[2];
+    reinterpret_cast<uint2*>(out)[(static_cast<size_t>(img) * kPad + py) * kPad + px] = o;
+  } else {
+    uint16_t* o16 = reinterpret_cast<uint16_t*>(out);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      o16[((static_cast<size_t>(img) * 3 + c) * kCrop + py) * kCrop + px] = static_cast<uint16_t>(rgb[c]);
+  }
+  }
+}
+
 template <int TH>
 static size_t fast_smem_bytes(int layout) {
   size_t b = (static_cast<size_t>(TH) * (2 + kFastTaps) + kFastRows) * 4 + 768 * 2;
@@ -544,10 +666,29 @@ static int fast_band_rows() {
   return v;
 }
 
+// IRP_PRE_BANDS=1 selects the single-kernel band path (A/B runs)
+static bool two_pass_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IRP_PRE_BANDS");
+    v = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int LAYOUT>
 static int launch_resample(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
                            int max_taps, const int32_t* plan, const int32_t* img_taps, __nv_bfloat16* out,
-                           cudaStream_t st) {
+                           cudaStream_t st, uint8_t* inter, const __nv_bfloat16* lut) {
+  if (two_pass_enabled()) {
+    dim3 hgrid((kTwoPassMaxRows + kHRowsPerCta - 1) / kHRowsPerCta, n_images);
+    hpass_kernel<<<hgrid, kCrop, 0, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, img_taps, inter);
+    constexpr int kSide = LAYOUT == IRP_LAYOUT_NHWC4P ? kPad : kCrop;
+    dim3 vgrid((kSide + kVRowsPerCta - 1) / kVRowsPerCta, n_images);
+    vpass_kernel<LAYOUT><<<vgrid, 256, 0, st>>>(plan, max_taps, img_taps, inter, lut, out);
+    IRP_CUDA_OK(cudaGetLastError());
+    return IRP_OK;
+  }
   switch (fast_band_rows()) {
     default: IRP_TRY((launch_fast<LAYOUT, 8>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st))); break;
     case 32: IRP_TRY((launch_fast<LAYOUT, 32>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st))); break;
@@ -603,16 +744,16 @@ static int launch_generic(const uint8_t* d_pixels, const int64_t* d_offsets, con
 template <int LAYOUT>
 static int launch_both(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
                        int max_taps, const int32_t* plan, const int32_t* img_taps, __nv_bfloat16* out,
-                       cudaStream_t st) {
+                       cudaStream_t st, uint8_t* inter, const __nv_bfloat16* lut) {
   if (max_taps <= kFastTaps)  // no image can need the generic path
-    return launch_resample<LAYOUT>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st);
+    return launch_resample<LAYOUT>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st, inter, lut);
   SideStream* side = nullptr;
   IRP_TRY(side_stream(&side));
   IRP_CUDA_OK(cudaEventRecord(side->fork, st));  // the plan kernel (and the caller's earlier work) precede both
   IRP_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
   IRP_TRY(launch_generic<LAYOUT>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, side->stream));
   IRP_CUDA_OK(cudaEventRecord(side->join, side->stream));
-  IRP_TRY(launch_resample<LAYOUT>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st));
+  IRP_TRY(launch_resample<LAYOUT>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st, inter, lut));
   IRP_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
   return IRP_OK;
 }
@@ -621,8 +762,12 @@ extern "C" {
 
 size_t irp_preprocess_workspace_bytes(int n_images, int max_taps) {
   if (n_images <= 0 || max_taps <= 0) return 0;
-  return static_cast<size_t>(n_images) * 2 * plan_ints_per_axis(max_taps) * sizeof(int32_t) + 16 +
-         static_cast<size_t>(n_images) * sizeof(int32_t);
+  size_t b = static_cast<size_t>(n_images) * 2 * plan_ints_per_axis(max_taps) * sizeof(int32_t) + 16 +
+             static_cast<size_t>(n_images) * sizeof(int32_t);
+  b = (b + 255) & ~static_cast<size_t>(255);
+  b += 2048;                                                              // normalisation LUT (768 bf16)
+  b += static_cast<size_t>(n_images) * kTwoPassMaxRows * kRowElems;       // horizontally filtered rows (uint8)
+  return b;
 }
 
 int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
@@ -642,14 +787,18 @@ int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int3
   const size_t plan_bytes = static_cast<size_t>(n_images) * 2 * plan_ints_per_axis(max_taps) * sizeof(int32_t);
   int32_t* status = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_workspace) + plan_bytes);
   int32_t* img_taps = status + 4;
+  size_t head = plan_bytes + 16 + static_cast<size_t>(n_images) * sizeof(int32_t);
+  head = (head + 255) & ~static_cast<size_t>(255);
+  __nv_bfloat16* lut = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(d_workspace) + head);
+  uint8_t* inter = static_cast<uint8_t*>(d_workspace) + head + 2048;
   IRP_CUDA_OK(cudaMemsetAsync(status, 0, 16 + static_cast<size_t>(n_images) * sizeof(int32_t), st));
-  resample_plan_kernel<<<n_images, 2 * kCrop, 0, st>>>(d_hw, n_images, max_taps, plan, status, img_taps);
+  resample_plan_kernel<<<n_images, 2 * kCrop, 0, st>>>(d_hw, n_images, max_taps, plan, status, img_taps, lut);
   IRP_CUDA_OK(cudaGetLastError());
   if (out_layout == IRP_LAYOUT_NHWC4P)
     return launch_both<IRP_LAYOUT_NHWC4P>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps,
-                                          static_cast<__nv_bfloat16*>(d_out), st);
+                                          static_cast<__nv_bfloat16*>(d_out), st, inter, lut);
   return launch_both<IRP_LAYOUT_NCHW>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps,
-                                      static_cast<__nv_bfloat16*>(d_out), st);
+                                      static_cast<__nv_bfloat16*>(d_out), st, inter, lut);
 }
 
 /* Host-side view of the resize/crop geometry (used by the Python mirror to size max_taps and by tests). */
