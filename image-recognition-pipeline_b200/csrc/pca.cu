@@ -385,6 +385,238 @@ __global__ void __launch_bounds__(kTriThreads) tridiag_step_kernel(double* __res
 }
 
 // ============================================================================================================
+// 4b. Lanczos with full re-orthogonalisation: only the top-k eigenpairs of the covariance are needed, and the
+//     Krylov space of a generic start vector captures them after a few hundred steps, while the Householder
+//     reduction above always pays for all n columns (n^3/3 * 16 bytes of matrix traffic and n launches).
+//       step j:  w = C q_j;  h1 = Q^T w; w -= Q h1;  h2 = Q^T w; w -= Q h2   (classical Gram-Schmidt, twice)
+//                alpha_j = h1[j] + h2[j];  beta_j = ||w||;  q_{j+1} = w / beta_j
+//     T_m = tridiag(alpha, beta) goes through the same bisection / inverse-iteration kernels; a Ritz pair
+//     (theta, Q s) has residual |beta_{m-1} s_{m-1}|, which the host checks after m steps (more steps if needed;
+//     at m = n the recurrence IS the exact tridiagonalisation, and the caller falls back to section 4 long before).
+// ============================================================================================================
+__global__ void lz_start_kernel(double* __restrict__ q0, int n) {
+  __shared__ double red[32];
+  pdl_trigger();
+  pdl_wait();
+  double part = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    uint32_t h = static_cast<uint32_t>(i) * 2654435761u + 0x9E3779B9u;  // fixed pseudo-random start vector
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    const double v = static_cast<double>(h) * (1.0 / 4294967296.0) - 0.5;
+    q0[i] = v;
+    part += v * v;
+  }
+  const double nrm = sqrt(block_sum(part, red));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) q0[i] /= nrm;
+}
+
+// All Lanczos kernels are launched with programmatic stream serialisation: the step is a chain of five short
+// dependent kernels, and letting each one become resident while its predecessor drains removes most of the
+// launch gap.  pdl_wait() precedes the first access to anything a predecessor wrote.
+//
+// Step j:  matvec   q_j = v / ||v||  (v = the previous step's orthogonalised vector; every CTA normalises its own
+//                   shared-memory copy, CTA 0 stores q_j, alpha_{j-1}, beta_{j-1});  w0 = C q_j
+//          dots     h1 = Q^T w0            (one CTA per basis vector)
+//          axpy     w1 = w0 - Q h1         (32 columns x 8 row shares per CTA, shares combined in a fixed order)
+//          dots     h2 = Q^T w1
+//          axpy     w2 = w1 - Q h2  -> v of step j+1
+
+// normalise v into shared memory; returns ||v||
+__device__ __forceinline__ double lz_normalise(const double* __restrict__ v, int n, double* sh_q, double* red) {
+  double part = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double x = v[i];
+    sh_q[i] = x;
+    part += x * x;
+  }
+  const double beta = sqrt(block_sum(part, red));
+  const double inv = beta > 0.0 ? 1.0 / beta : 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sh_q[i] *= inv;  // own elements
+  return beta;
+}
+
+__device__ __forceinline__ void lz_store_basis(const double* sh_q, int n, int j, double beta,
+                                               const double* __restrict__ h1, const double* __restrict__ h2,
+                                               double* __restrict__ Q, double* __restrict__ diag,
+                                               double* __restrict__ off) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) Q[static_cast<size_t>(j) * n + i] = sh_q[i];
+  if (threadIdx.x == 0 && j > 0) {
+    diag[j - 1] = h1[j - 1] + h2[j - 1];
+    off[j - 1] = beta;
+  }
+}
+
+__global__ void __launch_bounds__(256) lz_matvec_kernel(const double* __restrict__ C, const double* __restrict__ v,
+                                                        int n, int j, const double* __restrict__ h1,
+                                                        const double* __restrict__ h2, double* __restrict__ Q,
+                                                        double* __restrict__ diag, double* __restrict__ off,
+                                                        double* __restrict__ w) {
+  extern __shared__ double sh_q[];  // [n]
+  __shared__ double red[32];
+  pdl_trigger();
+  pdl_wait();
+  const double beta = lz_normalise(v, n, sh_q, red);
+  if (blockIdx.x == 0) lz_store_basis(sh_q, n, j, beta, h1, h2, Q, diag, off);
+  __syncthreads();
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double2* c2 = reinterpret_cast<const double2*>(C + static_cast<size_t>(row) * n);
+  const double2* q2 = reinterpret_cast<const double2*>(sh_q);
+  double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 8
+  for (int i = lane; i < (n >> 1); i += 32) {
+    const double2 a = c2[i], b = q2[i];
+    acc0 = fma(a.x, b.x, acc0);
+    acc1 = fma(a.y, b.y, acc1);
+  }
+  double acc = acc0 + acc1;
+  if ((n & 1) && lane == 0) acc = fma(C[static_cast<size_t>(row) * n + n - 1], sh_q[n - 1], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) w[row] = acc;
+}
+
+// closes a batch of steps: q_m, alpha_{m-1}, beta_{m-1} (the next batch's first matvec recomputes the same values)
+__global__ void __launch_bounds__(256) lz_close_kernel(const double* __restrict__ v, int n, int j,
+                                                       const double* __restrict__ h1, const double* __restrict__ h2,
+                                                       double* __restrict__ Q, double* __restrict__ diag,
+                                                       double* __restrict__ off) {
+  extern __shared__ double sh_q[];
+  __shared__ double red[32];
+  pdl_trigger();
+  pdl_wait();
+  const double beta = lz_normalise(v, n, sh_q, red);
+  lz_store_basis(sh_q, n, j, beta, h1, h2, Q, diag, off);
+}
+
+// h[r] = Q[r] . w, one CTA per basis vector
+__global__ void __launch_bounds__(256) lz_dots_kernel(const double* __restrict__ Q, const double* __restrict__ w,
+                                                      int n, double* __restrict__ h) {
+  __shared__ double red[32];
+  pdl_trigger();
+  pdl_wait();
+  const double* qr = Q + static_cast<size_t>(blockIdx.x) * n;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int i = threadIdx.x; i < n; i += 256) acc = fma(qr[i], w[i], acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) h[blockIdx.x] = acc;
+}
+
+// w_out = w_in - sum_{r < cnt} h[r] Q[r]: 32 columns per CTA, the basis rows dealt round-robin to 8 shares
+// (thread = share * 32 + column) and the shares combined in a fixed order: deterministic, no atomics.
+__global__ void __launch_bounds__(256) lz_axpy_kernel(const double* __restrict__ Q, const double* __restrict__ h,
+                                                      const double* __restrict__ w_in, int n, int cnt,
+                                                      double* __restrict__ w_out) {
+  __shared__ double sh_part[8][33];
+  pdl_trigger();
+  pdl_wait();
+  const int col = threadIdx.x & 31, share = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + col;
+  double acc = 0.0;
+  if (i < n) {
+#pragma unroll 8
+    for (int r = share; r < cnt; r += 8) acc = fma(h[r], Q[static_cast<size_t>(r) * n + i], acc);
+  }
+  sh_part[share][col] = acc;
+  __syncthreads();
+  if (share == 0 && i < n) {
+    double sum = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) sum += sh_part[y][col];
+    w_out[i] = w_in[i] - sum;
+  }
+}
+
+// convergence data for the host: out[0] = max_i |beta_{m-1} S[i][m-1]|, out[1] = min_j beta_j (j < m-1), out[2] = ||T||
+__global__ void lz_residual_kernel(const double* __restrict__ Z, const double* __restrict__ off, int m, int k,
+                                   const double* __restrict__ tnorm, double* __restrict__ out) {
+  double r = 0.0, bmin = INFINITY;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) r = fmax(r, fabs(off[m - 1] * Z[static_cast<size_t>(i) * m + m - 1]));
+  for (int j = threadIdx.x; j < m - 1; j += blockDim.x) bmin = fmin(bmin, off[j]);
+  __shared__ double sr[256], sb[256];
+  sr[threadIdx.x] = r;
+  sb[threadIdx.x] = bmin;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int t = 1; t < blockDim.x; ++t) {
+      r = fmax(r, sr[t]);
+      bmin = fmin(bmin, sb[t]);
+    }
+    out[0] = r;
+    out[1] = bmin;
+    out[2] = tnorm[0];
+  }
+}
+
+// Ritz vectors comps[which] = sum_j S[which][j] Q[j] (grid: component x 256-column block), then sklearn's sign
+// convention (entry of largest magnitude positive, first occurrence on ties) in a second kernel
+__global__ void __launch_bounds__(256) lz_ritz_kernel(const double* __restrict__ Q, const double* __restrict__ S,
+                                                      int n, int m, double* __restrict__ comps) {
+  extern __shared__ double sh_s[];  // S row [m]
+  const int which = blockIdx.x;
+  for (int j = threadIdx.x; j < m; j += 256) sh_s[j] = S[static_cast<size_t>(which) * m + j];
+  __syncthreads();
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= n) return;
+  double acc0 = 0.0, acc1 = 0.0;
+  int j = 0;
+#pragma unroll 4
+  for (; j + 1 < m; j += 2) {
+    acc0 = fma(sh_s[j], Q[static_cast<size_t>(j) * n + c], acc0);
+    acc1 = fma(sh_s[j + 1], Q[static_cast<size_t>(j + 1) * n + c], acc1);
+  }
+  if (j < m) acc0 = fma(sh_s[j], Q[static_cast<size_t>(j) * n + c], acc0);
+  comps[static_cast<size_t>(which) * n + c] = acc0 + acc1;
+}
+
+__global__ void __launch_bounds__(256) lz_sign_kernel(double* __restrict__ comps, int n) {
+  __shared__ double wb[8];
+  __shared__ int wi[8];
+  __shared__ double s_sign;
+  double* row = comps + static_cast<size_t>(blockIdx.x) * n;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double best = -1.0;
+  int bidx = n;
+  for (int c = tid; c < n; c += 256) {
+    const double a = fabs(row[c]);
+    if (a > best) {  // c ascends per thread: first occurrence kept on ties
+      best = a;
+      bidx = c;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ob > best || (ob == best && oi < bidx)) {
+      best = ob;
+      bidx = oi;
+    }
+  }
+  if (lane == 0) {
+    wb[warp] = best;
+    wi[warp] = bidx;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double bb = wb[0];
+    int bi = wi[0];
+    for (int i = 1; i < 8; ++i)
+      if (wb[i] > bb || (wb[i] == bb && wi[i] < bi)) {
+        bb = wb[i];
+        bi = wi[i];
+      }
+    s_sign = row[bi] < 0.0 ? -1.0 : 1.0;
+  }
+  __syncthreads();
+  if (s_sign < 0.0)
+    for (int c = tid; c < n; c += 256) row[c] = -row[c];
+}
+
+// ============================================================================================================
 // 5. top-k eigenvalues of the tridiagonal by multisection: one CTA per eigenvalue, one shift per thread and round.
 //    Sturm count = sign changes of the leading-minor polynomials p_i(x) (three-term recurrence, division free,
 //    rescaled every 8 steps; a zero takes the sign opposite to its predecessor -- Wilkinson).  The matrix is scaled
@@ -864,6 +1096,122 @@ int irp_cov_accumulate(const float* d_x, int64_t n_rows, int dim, const float* d
   return IRP_OK;
 }
 
+}  // extern "C"
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+static bool lanczos_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IRP_PCA_HOUSEHOLDER");
+    v = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Top-k eigenpairs by Lanczos (section 4b).  *done = false asks the caller for the exact Householder path
+// (breakdown, or no convergence within dim/2 steps).  Synchronises the stream once per convergence check.
+static int lanczos_topk(const double* A, int n, int k, double* Q, double* diag, double* off, double* tnorm,
+                        double* work, double* Z, double* d_eigenvalues, double* d_components, cudaStream_t st,
+                        bool* done) {
+  *done = false;
+  double* w0 = work;
+  double* w1 = w0 + n;
+  double* w2 = w1 + n;
+  double* h1 = w2 + n;
+  double* h2 = h1 + n;
+  double* out = h2 + n;
+  const double *cQ = Q, *cw0 = w0, *cw1 = w1, *cw2 = w2, *ch1 = h1, *ch2 = h2;
+  int m_target = 3 * k + 10 > 96 ? 3 * k + 10 : 96;
+  if (const char* e = getenv("IRP_PCA_LANCZOS_M0")) m_target = atoi(e) > k ? atoi(e) : m_target;
+  const int m_cap = n / 2;
+  if (m_target > m_cap) m_target = m_cap;
+  int m = 0;
+  IRP_CUDA_OK(launch_pdl(lz_start_kernel, dim3(1), dim3(1024), 0, st, w2, n));
+  const size_t vec_smem = static_cast<size_t>(n) * sizeof(double);
+  static size_t bis_cfg = 0, ii_cfg = 0, ritz_cfg = 0, vec_cfg = 0;
+  if (vec_smem > 32 * 1024 && vec_smem > vec_cfg) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(lz_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(vec_smem)));
+    IRP_CUDA_OK(cudaFuncSetAttribute(lz_close_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(vec_smem)));
+    vec_cfg = vec_smem;
+  }
+  const dim3 axpy_grid(ceil_div(n, 32));
+  int checks = 0;
+  for (;;) {
+    for (int j = m; j < m_target; ++j) {
+      IRP_CUDA_OK(launch_pdl(lz_matvec_kernel, dim3(ceil_div(n, 8)), dim3(256), vec_smem, st, A, cw2, n, j, ch1, ch2, Q,
+                             diag, off, w0));
+      IRP_CUDA_OK(launch_pdl(lz_dots_kernel, dim3(j + 1), dim3(256), 0, st, cQ, cw0, n, h1));
+      IRP_CUDA_OK(launch_pdl(lz_axpy_kernel, axpy_grid, dim3(256), 0, st, cQ, ch1, cw0, n, j + 1, w1));
+      IRP_CUDA_OK(launch_pdl(lz_dots_kernel, dim3(j + 1), dim3(256), 0, st, cQ, cw1, n, h2));
+      IRP_CUDA_OK(launch_pdl(lz_axpy_kernel, axpy_grid, dim3(256), 0, st, cQ, ch2, cw1, n, j + 1, w2));
+    }
+    IRP_CUDA_OK(launch_pdl(lz_close_kernel, dim3(1), dim3(256), vec_smem, st, cw2, n, m_target, ch1, ch2, Q, diag, off));
+    IRP_CUDA_OK(cudaGetLastError());
+    m = m_target;
+    const size_t bis_smem = 2 * static_cast<size_t>(m) * sizeof(double);
+    if (bis_smem > 32 * 1024 && bis_smem > bis_cfg) {
+      IRP_CUDA_OK(cudaFuncSetAttribute(bisect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(bis_smem)));
+      bis_cfg = bis_smem;
+    }
+    bisect_topk_kernel<<<k, kBisThreads, bis_smem, st>>>(diag, off, m, k, d_eigenvalues, tnorm);
+    const size_t ii_smem = 6 * static_cast<size_t>(m) * sizeof(double) + static_cast<size_t>(m) + 16;
+    if (ii_smem > 32 * 1024 && ii_smem > ii_cfg) {
+      IRP_CUDA_OK(cudaFuncSetAttribute(inverse_iteration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(ii_smem)));
+      ii_cfg = ii_smem;
+    }
+    inverse_iteration_kernel<<<k, 32, ii_smem, st>>>(diag, off, m, k, d_eigenvalues, tnorm, Z);
+    cluster_mgs_kernel<<<1, 256, 0, st>>>(Z, m, k, d_eigenvalues, tnorm);
+    lz_residual_kernel<<<1, 256, 0, st>>>(Z, off, m, k, tnorm, out);
+    IRP_CUDA_OK(cudaGetLastError());
+    double host[3] = {0.0, 0.0, 0.0};
+    IRP_CUDA_OK(cudaMemcpyAsync(host, out, sizeof(host), cudaMemcpyDeviceToHost, st));
+    IRP_CUDA_OK(cudaStreamSynchronize(st));
+    const double tn = host[2] > 0.0 ? host[2] : 1.0;
+    ++checks;
+    if (getenv("IRP_PCA_DEBUG"))
+      fprintf(stderr, "[irp] lanczos n=%d k=%d m=%d check %d: residual %.3e, min beta %.3e (||T|| %.3e)\n", n, k, m,
+              checks, host[0], host[1], tn);
+    if (!(host[1] > 1e-10 * tn) || !(host[0] == host[0])) return IRP_OK;  // breakdown (invariant subspace) or NaN
+    if (host[0] <= 1e-12 * tn) {
+      const size_t ritz_smem = static_cast<size_t>(m) * sizeof(double);
+      if (ritz_smem > 32 * 1024 && ritz_smem > ritz_cfg) {
+        IRP_CUDA_OK(cudaFuncSetAttribute(lz_ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(ritz_smem)));
+        ritz_cfg = ritz_smem;
+      }
+      lz_ritz_kernel<<<dim3(k, ceil_div(n, 256)), 256, ritz_smem, st>>>(Q, Z, n, m, d_components);
+      lz_sign_kernel<<<k, 256, 0, st>>>(d_components, n);
+      IRP_CUDA_OK(cudaGetLastError());
+      *done = true;
+      return IRP_OK;
+    }
+    if (m >= m_cap) return IRP_OK;
+    m_target = m + 64 < m_cap ? m + 64 : m_cap;
+  }
+}
+
+extern "C" {
+
 size_t irp_pca_fit_workspace_bytes(int dim, int k) {
   if (dim <= 0 || k <= 0) return 0;
   const size_t n = static_cast<size_t>(dim);
@@ -901,6 +1249,10 @@ int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scat
   assemble_cov_kernel<<<num_sms() * 4, 256, 0, st>>>(d_count, d_sum, d_scatter, d_shift, n, d_mean, A, scal);
   IRP_CUDA_OK(cudaGetLastError());
 
+  bool done = false;
+  if (lanczos_enabled() && n >= 512 && k * 8 <= n && k >= 5)
+    IRP_TRY(lanczos_topk(A, n, k, V, diag, off, scal + 1, work, Z, d_eigenvalues, d_components, st, &done));
+  if (!done) {
   // ---- tridiagonalisation: launches j = -1 .. n-3 ----
   const size_t tri_smem = 3 * static_cast<size_t>(n) * sizeof(double);
   static size_t tri_cfg = 0;
@@ -949,6 +1301,7 @@ int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scat
   // ---- back-transform + sign ----
   back_transform_kernel<<<k, kBtThreads, 0, st>>>(V, tau, n, Z, d_components);
   IRP_CUDA_OK(cudaGetLastError());
+  }
   clip_evals_kernel<<<ceil_div(k, 128), 128, 0, st>>>(d_eigenvalues, k);
   IRP_CUDA_OK(cudaGetLastError());
   // total variance (trace of C) is returned right after the k eigenvalues

@@ -130,8 +130,9 @@ int irp_debug_trap_record(uint32_t* out5);
  *   irp_cov_accumulate : adds this shard's  n, sum(x - s), sum (x-s)(x-s)^T  into fp64 accumulators
  *                        (split-bf16 tensor-core GEMM, fp32 per-chunk accumulate, fp64 combine).  Multi-GPU:
  *                        all-reduce the three accumulators (that is the stage's only collective), then
- *   irp_pca_fit        : mean, covariance, fp64 symmetric eigensolve (Householder tridiagonalisation, bisection,
- *                        inverse iteration), top-k components with sklearn's sign convention;
+ *   irp_pca_fit        : mean, covariance, fp64 symmetric eigensolve of the top k pairs (Lanczos with full
+ *                        re-orthogonalisation, or Householder tridiagonalisation for small / rank-deficient
+ *                        problems; bisection + inverse iteration on the tridiagonal), sklearn's sign convention;
  *   irp_pca_transform  : Z = (X - mean) V^T.
  * ---------------------------------------------------------------------------------------------------------- */
 size_t irp_cov_workspace_bytes(int64_t n_rows, int dim);
@@ -141,7 +142,8 @@ int irp_cov_accumulate(const float* d_x, int64_t n_rows, int dim, const float* d
 size_t irp_pca_fit_workspace_bytes(int dim, int k);
 /* Outputs (device): mean fp64[dim]; components fp64[k,dim] (row-major, sklearn sign convention); eigenvalues
  * fp64[k+1]: the k largest eigenvalues of the covariance in descending order (explained_variance_) followed by
- * the total variance trace(C) (denominator of explained_variance_ratio_). Work is enqueued on `stream`. */
+ * the total variance trace(C) (denominator of explained_variance_ratio_). Work is enqueued on `stream`; the call
+ * may synchronise `stream` (convergence check of the Lanczos iteration) and must not be stream-captured. */
 int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scatter, const float* d_shift,
                 int dim, int k, double* d_mean, double* d_components, double* d_eigenvalues, void* d_workspace,
                 size_t workspace_bytes, void* stream);

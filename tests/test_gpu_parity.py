@@ -23,6 +23,7 @@ pytestmark = pytest.mark.gpu
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 COS_MIN = 0.999
 LINF_REL_MAX = 2e-2
 ANGLE_MAX = 1e-3
@@ -429,6 +430,60 @@ def test_pca_full_size_properties(ops_mod):
     zref = (x64 - mu) @ comps.T
     assert (z.double() - zref).abs().max().item() < 1e-3 * zref.abs().max().item()
     np.testing.assert_allclose(z.double().var(0, unbiased=True).cpu().numpy(), ev.cpu().numpy(), rtol=1e-3)
+
+
+def test_pca_lanczos_extends_until_converged_and_matches_eigh(ops_mod, monkeypatch, capfd):
+    """Power-law spectrum (lambda_i ~ 1/i, 2 % gaps around the 50th) with the first convergence check forced too
+    early (56 steps for 50 pairs): the Krylov iteration must extend itself, and the result must still agree with a
+    dense fp64 eigendecomposition; bitwise repeatable."""
+    rng = np.random.default_rng(77)
+    d, n, k = 2048, 6000, 50
+    scale = (np.arange(1, d + 1, dtype=np.float64) ** -0.5).astype(np.float32)
+    x = (rng.standard_normal((n, d), dtype=np.float32) * scale)[:, rng.permutation(d)].copy()
+    monkeypatch.setenv("IRP_PCA_DEBUG", "1")
+    monkeypatch.setenv("IRP_PCA_LANCZOS_M0", "56")
+    mean, comps, evals, _ = _gpu_pca(ops_mod, x, k)
+    err = capfd.readouterr().err
+    monkeypatch.delenv("IRP_PCA_DEBUG")
+    assert "lanczos" in err and "check 2" in err, err
+    ref = pca_ref.pca_fit(x, k)
+    assert pca_ref.subspace_angle(comps, ref.components) <= ANGLE_MAX
+    assert np.abs(comps @ comps.T - np.eye(k)).max() < 1e-9
+    np.testing.assert_allclose(evals[:k], ref.explained_variance, rtol=2e-4)
+    mean2, comps2, evals2, _ = _gpu_pca(ops_mod, x, k)
+    assert np.array_equal(comps, comps2) and np.array_equal(evals, evals2)
+
+
+def test_pca_lanczos_and_householder_agree(ops_mod):
+    """The Krylov path and the exact Householder path (taken for small / rank-deficient problems) on one input."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from irp_b200 import ops
+        from oracle import synth
+        x = torch.from_numpy(synth.embedding_like(1200, 2048, seed=3)).cuda()
+        d = 2048
+        shift = x[:256].mean(0).contiguous()
+        acc = torch.zeros(1 + d + d * d, dtype=torch.float64, device="cuda")
+        ops.cov_accumulate(x, shift, acc[:1], acc[1:1 + d], acc[1 + d:].view(d, d))
+        mean, comps, ev = ops.pca_fit(acc[:1], acc[1:1 + d], acc[1 + d:].view(d, d), shift, 50)
+        np.savez(sys.argv[1], comps=comps.cpu().numpy(), ev=ev.cpu().numpy())
+    """) % (os.path.join(ROOT, "image-recognition-pipeline_b200"), ROOT)
+    import tempfile
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for mode in ("lanczos", "householder"):
+            env = dict(os.environ)
+            if mode == "householder":
+                env["IRP_PCA_HOUSEHOLDER"] = "1"
+            path = os.path.join(tmp, mode + ".npz")
+            subprocess.run([sys.executable, "-c", code, path], env=env, check=True, timeout=300)
+            out[mode] = dict(np.load(path))
+    a, b = out["lanczos"], out["householder"]
+    np.testing.assert_allclose(a["ev"], b["ev"], rtol=1e-10)
+    assert (np.abs((a["comps"] * b["comps"]).sum(1)) > 1 - 1e-10).all()
+    assert ((a["comps"] * b["comps"]).sum(1) > 0).all()  # same sign convention
 
 
 # =============================================================================================== A4 scoring
