@@ -46,6 +46,12 @@ __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restr
   }
 }
 
+__global__ void add_bias_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
 // 3x3 / stride 2 / pad 1 max pooling, NHWC bf16, 8 channels (16 bytes) per thread.
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
                                     int W, int C, int Ho, int Wo) {
@@ -592,10 +598,15 @@ static bool chain_supported(int K1, int N1, int N2) {
   return K1 % 64 == 0 && N1 % kChainBN1 == 0 && N1 <= kChainMaxN1 && (N2 == 64 || N2 == 128 || N2 == 256);
 }
 
+// x2 / K2: optional second GEMM1 operand (stride-1 1x1 shortcut convolution of x2 folded into the same accumulator);
+// then w3 is [N1][K1 + K2] (conv3 and shortcut weights concatenated along K), b3 the sum of both biases, and
+// `residual` must be null.
 static int plan_chain(ChainPlan* plan, const void* t2, const void* w3, const float* b3, const void* residual, void* y,
                       const void* w1, const float* b1, void* t1, long long max_rows, int rows_per_image, int K1,
-                      int N1, int N2) {
+                      int N1, int N2, const void* x2 = nullptr, int K2 = 0) {
   IRP_REQUIRE(chain_supported(K1, N1, N2), "conv chain: unsupported shape K1 %d N1 %d N2 %d", K1, N1, N2);
+  IRP_REQUIRE((x2 == nullptr) == (K2 == 0) && K2 % 64 == 0 && (x2 == nullptr) != (residual == nullptr),
+              "conv chain: either a residual or a second operand (K2 %d)", K2);
   ChainParams& p = plan->p;
   memset(&p, 0, sizeof(p));
   const uint64_t M = static_cast<uint64_t>(max_rows);
@@ -606,8 +617,11 @@ static int plan_chain(ChainPlan* plan, const void* t2, const void* w3, const flo
     return encode_bf16_map(m, const_cast<void*>(base), 2, dims, strides, box, 128);
   };
   IRP_TRY(map2d(&p.tmA, t2, K1, M, kTileM));
-  IRP_TRY(map2d(&p.tmB1, w3, K1, N1, kChainBN1 / 2));
-  IRP_TRY(map2d(&p.tmRes, residual, N1, M, kTileM));
+  IRP_TRY(map2d(&p.tmB1, w3, K1 + K2, N1, kChainBN1 / 2));
+  IRP_TRY(map2d(&p.tmRes, residual ? residual : y, N1, M, kTileM));
+  IRP_TRY(map2d(&p.tmA2, x2 ? x2 : t2, x2 ? K2 : K1, M, kTileM));
+  p.k2_blocks = K2 / 64;
+  p.has_res = residual != nullptr ? 1 : 0;
   IRP_TRY(map2d(&p.tmY, y, N1, M, kTileM));
   IRP_TRY(map2d(&p.tmB2, w1, N1, N2, N2 / 2));
   IRP_TRY(map2d(&p.tmOut2, t1, N2, M, kTileM));
@@ -821,6 +835,11 @@ struct irp_resnet50 {
                       // TMA view, 1: im2col + flat GEMM
   std::vector<ConvPlan> plans;
   std::vector<ChainPlan> chains;  // indexed by the conv3 of the first block of a fused junction
+  std::vector<ChainPlan> chains_ds;  // same junction with the block's stride-1 shortcut conv folded into GEMM1
+  int cat_c3 = -1, cat_ds = -1;      // conv3 / shortcut conv whose folded weights are also kept concatenated along K
+  __nv_bfloat16* wcat = nullptr;     // [cout][cin_c3 + cin_ds]
+  float* bcat = nullptr;             // bias_c3 + bias_ds
+  bool ds_fuse = true;               // IRP_NO_DS_FUSE=1: keep the shortcut conv of layer1's first block separate
   std::vector<L1Plan> l1blocks;   // indexed by the conv2 of a layer1 block whose conv2+conv3+next conv1 are fused
   int l1_level = 0;               // IRP_L1_FUSE=1: layer1 blocks through l1_block.cuh.  Off by default: measured 346 us
                                   // against 81 + 218 us for conv3x3_c64 + conv_chain -- with everything on one SM the
@@ -918,6 +937,15 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x, int l1_mode) {
                            net->buf[other], net->weights[nxt], net->biases[nxt], net->buf[T1],
                            static_cast<long long>(B) * c3.H * c3.W, c3.H * c3.W, c3.cin, c3.cout, n1.cout));
       }
+      // the same junction with the stride-1 shortcut conv computed inside GEMM1 (no DS tensor, no residual read)
+      net->chains_ds[i + 2].valid = false;
+      if (net->ds_fuse && net->chains[i + 2].valid && has_ds && static_cast<int>(i + 3) == net->cat_ds &&
+          sp[i + 3].cin % 64 == 0) {
+        IRP_TRY(plan_chain(&net->chains_ds[i + 2], net->buf[T2], net->wcat, net->bcat, nullptr, net->buf[other],
+                           net->weights[nxt], net->biases[nxt], net->buf[T1],
+                           static_cast<long long>(B) * c3.H * c3.W, c3.H * c3.W, c3.cin, c3.cout, sp[nxt].cout,
+                           net->buf[cur], sp[i + 3].cin));
+      }
       // layer1 blocks: conv2 + conv3 + next conv1 in one kernel; T1' ping-pongs between T1 and T1B because the
       // kernel reads its own conv1 input (with halo) while it writes the next one
       net->l1blocks[i + 1].valid = false;
@@ -972,6 +1000,13 @@ int irp_resnet50_create(irp_resnet50** out, int max_batch) {
   net->plans.resize(sp.size());
   net->chains.resize(sp.size());
   net->l1blocks.resize(sp.size());
+  net->chains_ds.resize(sp.size());
+  if (const char* nf = getenv("IRP_NO_DS_FUSE")) net->ds_fuse = atoi(nf) == 0;
+  for (size_t i = 0; i < sp.size(); ++i)
+    if (sp[i].role == 4 && sp[i].stride == 1 && net->cat_ds < 0) {  // conv order in a block: conv1, conv2, conv3, ds
+      net->cat_ds = static_cast<int>(i);
+      net->cat_c3 = static_cast<int>(i) - 1;
+    }
   if (const char* lf = getenv("IRP_L1_FUSE")) net->l1_level = atoi(lf);
   if (const char* cl = getenv("IRP_CHAIN")) net->chain_level = atoi(cl);
   net->weights.assign(sp.size(), nullptr);
@@ -991,6 +1026,14 @@ int irp_resnet50_create(irp_resnet50** out, int max_batch) {
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&net->biases[i]), sp[i].cout * sizeof(float));
   }
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&net->stem2_w), kStemWeightBytes);
+  if (e == cudaSuccess && net->cat_ds >= 0) {
+    const ConvSpec &c3 = sp[net->cat_c3], &d = sp[net->cat_ds];
+    e = cudaMalloc(reinterpret_cast<void**>(&net->wcat),
+                   static_cast<size_t>(c3.cout) * (c3.cin + d.cin) * sizeof(__nv_bfloat16));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&net->bcat), c3.cout * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(net->biases[net->cat_c3], 0, c3.cout * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(net->biases[net->cat_ds], 0, d.cout * sizeof(float));
+  }
   if (e != cudaSuccess) {
     set_last_error("irp_resnet50_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     irp_resnet50_destroy(net);
@@ -1005,6 +1048,8 @@ void irp_resnet50_destroy(irp_resnet50* net) {
   for (auto& b : net->buf) cudaFree(b);
   cudaFree(net->im2col);
   cudaFree(net->stem2_w);
+  cudaFree(net->wcat);
+  cudaFree(net->bcat);
   for (auto* w : net->weights) cudaFree(w);
   for (auto* b : net->biases) cudaFree(b);
   delete net;
@@ -1046,6 +1091,17 @@ int irp_resnet50_load_conv(irp_resnet50* net, int index, const float* d_weight_o
                                                        s.cin, s.ksize, s.ksize, kw_pad, cin_pad, net->weights[index],
                                                        net->biases[index]);
   IRP_CUDA_OK(cudaGetLastError());
+  if (index == net->cat_c3 || index == net->cat_ds) {
+    // keep [W3 | Wds] and b3 + bds current for the junction kernel that folds the shortcut conv into its GEMM1
+    const ConvSpec &c3 = sp[net->cat_c3], &d = sp[net->cat_ds];
+    const size_t pitch = static_cast<size_t>(c3.cin + d.cin) * sizeof(__nv_bfloat16);
+    const size_t col0 = index == net->cat_c3 ? 0 : static_cast<size_t>(c3.cin);
+    IRP_CUDA_OK(cudaMemcpy2DAsync(net->wcat + col0, pitch, net->weights[index], s.cin * sizeof(__nv_bfloat16),
+                                  s.cin * sizeof(__nv_bfloat16), s.cout, cudaMemcpyDeviceToDevice, st));
+    add_bias_kernel<<<grid_for(c3.cout, 256), 256, 0, st>>>(net->biases[net->cat_c3], net->biases[net->cat_ds],
+                                                           net->bcat, c3.cout);
+    IRP_CUDA_OK(cudaGetLastError());
+  }
   return IRP_OK;
 }
 
@@ -1121,7 +1177,11 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
     size_t i = 1;
     int last = 0;
     bool conv1_done = false;  // this block's conv1 was already produced by the previous block's chained conv3
+    int blocks_left = -1;     // debugging: run only the first IRP_TRUNK_BLOCKS bottleneck blocks (timing experiments)
+    if (const char* e = getenv("IRP_TRUNK_BLOCKS")) blocks_left = atoi(e);
     while (i < sp.size()) {
+      if (blocks_left == 0) break;
+      if (blocks_left > 0) --blocks_left;
       const bool has_ds = (i + 3 < sp.size()) && sp[i + 3].role == 4;
       if (!conv1_done) IRP_TRY(launch_conv(net->plans[i], mb, st));
       IRP_TRY(capture(static_cast<int>(i)));
@@ -1130,11 +1190,14 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
         IRP_TRY(launch_conv(net->plans[i + 1], mb, st));
         IRP_TRY(capture(static_cast<int>(i + 1)));
       }
-      if (has_ds) {
+      // shortcut conv folded into the junction kernel (not when a layer output is being captured: the DS tensor
+      // does not exist then, and the per-layer parity test wants every conv on its own)
+      const bool ds_folded = has_ds && !l1.valid && net->chains_ds[i + 2].valid && d_capture == nullptr;
+      if (has_ds && !ds_folded) {
         IRP_TRY(launch_conv(net->plans[i + 3], mb, st));
         IRP_TRY(capture(static_cast<int>(i + 3)));
       }
-      const ChainPlan& ch = net->chains[i + 2];
+      const ChainPlan& ch = ds_folded ? net->chains_ds[i + 2] : net->chains[i + 2];
       if (l1.valid) {
         IRP_TRY(launch_l1_block(l1, mb, st));
         conv1_done = true;
@@ -1149,7 +1212,7 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
       last = static_cast<int>(i + 2);
       i += has_ds ? 4 : 3;
     }
-    {
+    if (blocks_left < 0) {
       const long long total = static_cast<long long>(mb) * (2048 / 2);
       avgpool_kernel<<<grid_for(total, 128), 128, 0, st>>>(net->buf[net->out_buf[last]],
                                                           d_embed + static_cast<size_t>(s0) * 2048, mb, 49, 2048);
@@ -1175,6 +1238,16 @@ int irp_conv1x1_chain(const void* d_t2, const void* d_w3, const float* d_b3, con
   IRP_REQUIRE(d_t2 && d_w3 && d_b3 && d_residual && d_y && d_w1 && d_b1 && d_t1 && rows > 0, "conv chain: bad argument");
   ChainPlan plan;
   IRP_TRY(plan_chain(&plan, d_t2, d_w3, d_b3, d_residual, d_y, d_w1, d_b1, d_t1, rows, 1, K1, N1, N2));
+  return launch_chain(plan, rows, static_cast<cudaStream_t>(stream));
+}
+
+int irp_conv1x1_chain_ds(const void* d_t2, const void* d_x, const void* d_wcat, const float* d_bias, void* d_y,
+                         const void* d_w1, const float* d_b1, void* d_t1, int64_t rows, int K1, int K2, int N1, int N2,
+                         void* stream) {
+  IRP_REQUIRE(d_t2 && d_x && d_wcat && d_bias && d_y && d_w1 && d_b1 && d_t1 && rows > 0 && K2 > 0,
+              "conv chain ds: bad argument");
+  ChainPlan plan;
+  IRP_TRY(plan_chain(&plan, d_t2, d_wcat, d_bias, nullptr, d_y, d_w1, d_b1, d_t1, rows, 1, K1, N1, N2, d_x, K2));
   return launch_chain(plan, rows, static_cast<cudaStream_t>(stream));
 }
 

@@ -2,6 +2,8 @@
 // bottleneck's conv1 (+ folded BN + ReLU)  (torchvision/models/resnet.py:150-159 then :142-144 of the next block).
 //
 //   Y   = relu(T2 . W3^T + b3 + R)      [M, N1]   written to HBM (it is the block output and the next residual)
+//         or, for a block whose shortcut is a stride-1 1x1 convolution of X (layer1's first block):
+//   Y   = relu([T2 | X] . [W3 | Wds]^T + (b3 + bds))   -- the shortcut is never written to or read from HBM
 //   T1' = relu(Y  . W1^T + b1)          [M, N2]   written to HBM (input of the next block's 3x3)
 //
 // Unfused, conv1 re-reads the whole N1-channel block output from HBM (411 MB per 256 images in layer1) for a GEMM
@@ -38,9 +40,14 @@ struct alignas(64) ChainParams {
   CUtensorMap tmY;     // Y   [M, N1]  same geometry
   CUtensorMap tmB2;    // W1' [N2, N1] dims (N1, N2), box (64, N2/2)
   CUtensorMap tmOut2;  // T1' [M, N2]  dims (N2, M), box (64, 128)
+  CUtensorMap tmA2;    // X   [M, K2]  optional second GEMM1 operand (see k2_blocks)
   const float* bias1;  // [N1]
   const float* bias2;  // [N2]
   int k1_blocks;       // K1 / 64
+  int k2_blocks;       // K2 / 64: GEMM1 continues over X . Wds^T (W3 and Wds concatenated along K in tmB1) -- the
+                       // block's 1x1 downsample convolution computed in the same accumulator instead of being read
+                       // back as a residual (first bottleneck of layer1, where it has stride 1)
+  int has_res;         // 0: no residual tensor (k2_blocks > 0)
   int passes;          // N1 / 128
   int n1;              // N1
   int m_tiles;         // ceil(M / 128)
@@ -130,6 +137,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     tma_prefetch_desc(&p.tmY);
     tma_prefetch_desc(&p.tmB2);
     tma_prefetch_desc(&p.tmOut2);
+    if (p.k2_blocks > 0) tma_prefetch_desc(&p.tmA2);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full1[i], 1);
       mbar_init(&empty1[i], 1);
@@ -172,15 +180,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       uint32_t phase = 0;
       int b2n = 0;  // B2 k-blocks issued so far
       int i = 0;    // local tile counter
+      const int kt = p.k1_blocks + p.k2_blocks;
       for (int mt = pair; mt < pair_tiles; mt += num_pairs, ++i) {
         const int row0 = (mt * 2 + static_cast<int>(rank)) * kTileM;  // may be past M: loads zero-fill, stores clip
         for (int ps = 0; ps < P; ++ps) {
           const int col0 = ps * kChainBN1;
-          for (int kb = 0; kb < p.k1_blocks; ++kb) {
+          for (int kb = 0; kb < kt; ++kb) {
             mbar_wait(&empty1[stage], phase ^ 1);
             const uint32_t full_leader = mapa_u32(&full1[stage], 0);
             if (rank == 0) mbar_arrive_expect_tx(&full1[stage], 2 * S::kStageBytes);
-            tma_load_2d_cg2(smem_a + stage * S::kABytes, &p.tmA, full_leader, kb * 64, row0);
+            if (kb < p.k1_blocks)
+              tma_load_2d_cg2(smem_a + stage * S::kABytes, &p.tmA, full_leader, kb * 64, row0);
+            else
+              tma_load_2d_cg2(smem_a + stage * S::kABytes, &p.tmA2, full_leader, (kb - p.k1_blocks) * 64, row0);
             tma_load_2d_cg2(smem_b1 + stage * S::kB1Bytes, &p.tmB1, full_leader, kb * 64,
                             col0 + static_cast<int>(rank) * (kChainBN1 / 2));
             if (++stage == kStages) {
@@ -190,7 +202,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           }
           // residual chunks of this pass -> the ring buffers epilogue1 overwrites in place
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < 2 && p.has_res; ++c) {
             const int q = q_pass(i, ps, c);
             const int b = q % R;
             if (q >= R) mbar_wait(&stg_empty[b], ((q / R) - 1) & 1);
@@ -220,6 +232,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       int my_tiles = 0;
       for (int mt = pair; mt < pair_tiles; mt += num_pairs) ++my_tiles;
       const int total_passes = my_tiles * P;
+      const int kt = p.k1_blocks + p.k2_blocks;
       // GEMM2 of global pass h (tile h / P, pass h % P)
       auto gemm2 = [&](int h) {
         const int i = h / P, ps = h - i * P;
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         mbar_wait(&acc1_empty[a1], ((g >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + a1 * kChainBN1;
-        for (int kb = 0; kb < p.k1_blocks; ++kb) {
+        for (int kb = 0; kb < kt; ++kb) {
           mbar_wait(&full1[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
@@ -365,10 +378,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           uint8_t* chunk = smem_ring + b * kStgChunkBytes + row_off;
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + a1 * kChainBN1 + c * 64 + lane_base, v);
-          mbar_wait(&res_full[b], (q / R) & 1);
           uint4 rv[4];
+          if (p.has_res) {
+            mbar_wait(&res_full[b], (q / R) & 1);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rv[j] = *reinterpret_cast<const uint4*>(chunk + (((piece0 + j) ^ swz) << 4));
+            for (int j = 0; j < 4; ++j) rv[j] = *reinterpret_cast<const uint4*>(chunk + (((piece0 + j) ^ swz) << 4));
+          } else {
+            // nothing was prefetched into the buffer: wait for its previous use (store read + GEMM2) ourselves
+            if (q >= R) mbar_wait(&stg_empty[b], ((q / R) - 1) & 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rv[j] = make_uint4(0u, 0u, 0u, 0u);
+          }
           const float4* bp = reinterpret_cast<const float4*>(sbias1 + ps * kChainBN1 + c * 64 + half * 32);
           float4 bv[8];
 #pragma unroll

@@ -110,6 +110,16 @@ int irp_conv1x1_chain(const void* d_t2, const void* d_w3, const float* d_b3, con
                       const void* d_w1, const float* d_b1, void* d_t1, int64_t rows, int K1, int N1, int N2,
                       void* stream);
 
+/* The same junction for a block whose shortcut is a stride-1 1x1 convolution of the block input x (layer1's first
+ * bottleneck, torchvision/models/resnet.py:155-156 `identity = self.downsample(x)`): the shortcut is computed in
+ * the conv3 accumulator, so the downsample tensor is never written to or read back from HBM.
+ *   y  [rows,N1] = relu(t2 [rows,K1] . w3^T + x [rows,K2] . wds^T + bias)     wcat = [w3 | wds]  [N1, K1+K2]
+ *   t1 [rows,N2] = relu(y . w1[N2,N1]^T + b1)                                bias = b3 + bds
+ * K1 % 64 == 0, K2 % 64 == 0, K2 > 0, N1 % 128 == 0, N1 <= 1024, N2 in {64,128,256}. */
+int irp_conv1x1_chain_ds(const void* d_t2, const void* d_x, const void* d_wcat, const float* d_bias, void* d_y,
+                         const void* d_w1, const float* d_b1, void* d_t1, int64_t rows, int K1, int K2, int N1, int N2,
+                         void* stream);
+
 /* The fused tail of a layer1 bottleneck + head of the next one (l1_block.cuh), exposed for parity tests:
  *   t2 = relu(conv3x3(t1 [B,H,W,64], w2 [64,3,3,64]) + b2)      (kept on chip)
  *   y  [B,H,W,256] = relu(t2 . w3[256,64]^T + b3 + residual [B,H,W,256])

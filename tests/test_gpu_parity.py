@@ -198,6 +198,37 @@ def test_conv1x1_chain_matches_torch(lib, rows, K1, N1, N2):
     assert ((t1.float() - t1_ref).abs().max() / t1_ref.abs().max()).item() < 6e-3
 
 
+@pytest.mark.parametrize("rows,K1,K2,N1,N2", [
+    (256, 64, 64, 256, 64),        # layer1's first block, one tile pair
+    (3136 * 5 + 77, 64, 64, 256, 64),   # ragged tail, several tiles per pair at a small batch
+    (40000, 64, 64, 256, 64),      # ring / accumulator recycling
+    (1000, 128, 256, 512, 128),    # general K1 != K2
+])
+def test_conv1x1_chain_with_folded_shortcut_matches_torch(lib, rows, K1, K2, N1, N2):
+    """conv3 with the block's stride-1 shortcut conv folded into the same accumulator (no residual tensor), ReLU,
+    chained with the next block's conv1 + ReLU, against fp32 torch."""
+    from irp_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(rows + K1 + K2 + N1 + N2)
+    t2 = torch.randn(rows, K1, device="cuda", generator=g).bfloat16()
+    x = torch.randn(rows, K2, device="cuda", generator=g).bfloat16()
+    w3 = (torch.randn(N1, K1, device="cuda", generator=g) / K1 ** 0.5).bfloat16()
+    wds = (torch.randn(N1, K2, device="cuda", generator=g) / K2 ** 0.5).bfloat16()
+    wcat = torch.cat([w3, wds], 1).contiguous()
+    bias = torch.randn(N1, device="cuda", generator=g)
+    w1 = (torch.randn(N2, N1, device="cuda", generator=g) / N1 ** 0.5).bfloat16()
+    b1 = torch.randn(N2, device="cuda", generator=g)
+    y = torch.full((rows, N1), float("nan"), device="cuda").bfloat16()
+    t1 = torch.full((rows, N2), float("nan"), device="cuda").bfloat16()
+    _lib.check(lib.irp_conv1x1_chain_ds(_ptr(t2), _ptr(x), _ptr(wcat), _ptr(bias), _ptr(y), _ptr(w1), _ptr(b1),
+                                        _ptr(t1), rows, K1, K2, N1, N2, _stream()), "irp_conv1x1_chain_ds")
+    torch.cuda.synchronize()
+    y_ref = (t2.float() @ w3.float().t() + x.float() @ wds.float().t() + bias).relu()
+    assert not torch.isnan(y.float()).any() and not torch.isnan(t1.float()).any()
+    assert ((y.float() - y_ref).abs().max() / y_ref.abs().max()).item() < 6e-3
+    t1_ref = (y.float() @ w1.float().t() + b1).relu()
+    assert ((t1.float() - t1_ref).abs().max() / t1_ref.abs().max()).item() < 6e-3
+
+
 @pytest.mark.parametrize("B,H,N2", [
     (1, 16, 64),      # one 8x16 tile pair
     (1, 24, 64),      # 3x2 tiles: ragged bottom row of tiles
@@ -707,3 +738,39 @@ def test_whole_stage_against_reference_route(trunk):
             cref, cnear = stage_ref.lof_band(zr.astype(np.float32)[m], 30, 0.05, BAND)
             assert int(((cf.cpu().numpy()[m] != cref) & ~cnear).sum()) == 0
     assert res.class_outliers.shape == (160,) and res.z.shape == (160, 20)
+
+
+def test_scale_out_config_shape_batch512_pca128_global_only(lib):
+    """BASELINE.json configs[3] scaled down (1M -> 2 560 images): 224x224 inputs, batch 512, PCA(128), global
+    scorer only.  Embeddings of a sample against the reference route, PCA(128) and the global LOF flags against the
+    oracle on the same features."""
+    from irp_b200.stage import OutlierStage, ResNet50Trunk, pack_images
+    n, k = 2560, 128
+    images, _ = synth.config1_images(n, 10, seed=3)
+    trunk512 = ResNet50Trunk(stage_ref.full_resnet50(seed=1234), torch.device("cuda:0"), max_batch=512)
+    try:
+        stage = OutlierStage(trunk512, batch_size=512, pca_components=k)
+        assert stage.batch_size == 512
+        feats = stage.embed_packed(pack_images(images), from_host=True)
+        sample = list(range(0, n, 40))  # 64 images spread over all five batches
+        ref_feats = stage_ref.embed_arrays([images[i] for i in sample], batch_size=32, seed=1234)
+        cos, linf = _embedding_metrics(feats[sample].cpu().numpy(), ref_feats)
+        assert cos >= COS_MIN and linf <= LINF_REL_MAX
+        pca = stage.fit_pca(feats)
+        z = stage.transform(feats, pca)
+        x = feats.cpu().numpy()
+        ref = pca_ref.pca_fit(x, k)
+        assert pca_ref.subspace_angle(pca.components.cpu().numpy(), ref.components) <= ANGLE_MAX
+        zref = pca_ref.pca_transform(x, ref.mean, ref.components).astype(np.float32)
+        r = pca.components.cpu().numpy() @ ref.components.T
+        np.testing.assert_allclose(z.cpu().numpy().astype(np.float64) @ r, zref, atol=2e-3 * np.abs(zref).max())
+        # global scorer on the ORACLE projection (stage-wise parity)
+        zt = torch.from_numpy(zref).cuda()
+        gs, goff, gf = stage.backend.lof(zt, None, 1, 75, 0.03)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gref, gnear = stage_ref.lof_band(zref, 75, 0.03, BAND)
+        assert int(((gf.bool().cpu().numpy() != gref) & ~gnear).sum()) == 0
+        assert abs(int(gf.sum()) - round(0.03 * n)) <= 2
+    finally:
+        trunk512.close()
