@@ -241,15 +241,20 @@ TRUNK_DRAM_BYTES_PER_CALL = 11.158e9
 def launches_per_step(n_images, batch, dim, max_taps):
     """Kernels of libirp_b200.so launched per step (counted from the launch sites in csrc/*.cu)."""
     batches = (n_images + batch - 1) // batch
-    pre = 2 + (1 if max_taps > 6 else 0)  # resample_plan + fast path (+ generic many-tap path)
-    trunk = 50                   # stem+pool, 16 3x3, 4 downsample, 9 conv1, 9 conv3, 7 chained conv3+conv1, avgpool
+    pre = 3 + (1 if max_taps > 6 else 0)  # resample_plan + horizontal pass + vertical pass (+ many-tap path)
+    trunk = 49                   # stem+pool, 16 3x3, 3 downsample, 9 conv1, 9 conv3, 7 chained conv3+conv1 (the first
+                                 # with the layer1 shortcut conv folded in), avgpool
     per_batch = pre + trunk
     cov = 3                      # split_transpose, add_count, cov_gemm
-    fit = 1 + (dim - 1) + 5      # assemble, tridiag steps, bisect, inverse iteration, mgs, back-transform (+clip)
-    fit += 1
+    k = PCA_K
+    lanczos_steps = max(3 * k + 10, 96)  # first convergence check; the bench data converges there
+    # assemble, start vector, 5 kernels per step, close, bisect, inverse iteration, mgs, residual, Ritz, sign, clip
+    fit = 2 + 5 * lanczos_steps + 1 + 4 + 2 + 1 if dim >= 512 and 8 * k <= dim else 1 + (dim - 1) + 6
     transform = 1
-    lof_grouped = 3 + 9          # count/scan/scatter + sqnorm, gather, knn, lrd, score, unsort, percentile, flag
-    lof_global = 1 + 9
+    # iota/count/scan/scatter (grouped only), sort key + radix sort (4 CUB passes + histogram), sqnorm, gather,
+    # knn, lrd, score, unsort, percentile, flag
+    lof_global = 1 + 1 + 5 + 8
+    lof_grouped = 3 + lof_global
     return batches * per_batch + cov + fit + transform + lof_grouped + lof_global
 
 

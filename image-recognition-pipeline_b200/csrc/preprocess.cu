@@ -49,8 +49,14 @@ __host__ __device__ inline int round_half_even_div2(int d) {
   if ((d & 1) == 0) return q;
   return (q & 1) ? q + 1 : q;
 }
-__host__ __device__ inline Geometry compute_geometry(int h, int w) {
+__host__ __device__ inline Geometry compute_geometry(int h, int w, int transform = IRP_TRANSFORM_WEIGHTS_DEFAULT) {
   Geometry g;
+  if (transform == IRP_TRANSFORM_VAL_256) {
+    // functions/dataload.py:51-56 val_transform: Resize((256, 256)) ignores the aspect ratio, CenterCrop(224)
+    g.out_h = g.out_w = IRP_VAL_RESIZE;
+    g.top = g.left = round_half_even_div2(IRP_VAL_RESIZE - kCrop);
+    return g;
+  }
   if (w <= h) {
     g.out_w = kResize;
     g.out_h = static_cast<int>(static_cast<double>(static_cast<long long>(kResize) * h) / static_cast<double>(w));
@@ -63,7 +69,7 @@ __host__ __device__ inline Geometry compute_geometry(int h, int w) {
   return g;
 }
 
-__global__ void resample_plan_kernel(const int32_t* __restrict__ hw, int n_images, int max_taps,
+__global__ void resample_plan_kernel(const int32_t* __restrict__ hw, int n_images, int max_taps, int transform,
                                      int32_t* __restrict__ plan, int32_t* __restrict__ status,
                                      int32_t* __restrict__ img_taps, __nv_bfloat16* __restrict__ lut) {
   const int img = blockIdx.x;
@@ -82,7 +88,7 @@ __global__ void resample_plan_kernel(const int32_t* __restrict__ hw, int n_image
   const int axis = j / kCrop;  // 0: horizontal (x), 1: vertical (y)
   const int o = j % kCrop;
   const int h = hw[2 * img], w = hw[2 * img + 1];
-  const Geometry g = compute_geometry(h, w);
+  const Geometry g = compute_geometry(h, w, transform);
   const int in_size = axis == 0 ? w : h;
   const int out_size = axis == 0 ? g.out_w : g.out_h;
   const int xx = o + (axis == 0 ? g.left : g.top);
@@ -773,7 +779,16 @@ size_t irp_preprocess_workspace_bytes(int n_images, int max_taps) {
 int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
                    int max_taps, void* d_workspace, size_t workspace_bytes, void* d_out, int out_layout,
                    void* stream) {
+  return irp_preprocess_ex(d_pixels, d_offsets, d_hw, n_images, max_taps, d_workspace, workspace_bytes, d_out,
+                           out_layout, IRP_TRANSFORM_WEIGHTS_DEFAULT, stream);
+}
+
+int irp_preprocess_ex(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
+                      int max_taps, void* d_workspace, size_t workspace_bytes, void* d_out, int out_layout,
+                      int transform, void* stream) {
   IRP_REQUIRE(d_pixels && d_offsets && d_hw && d_workspace && d_out, "preprocess: null argument");
+  IRP_REQUIRE(transform == IRP_TRANSFORM_WEIGHTS_DEFAULT || transform == IRP_TRANSFORM_VAL_256,
+              "preprocess: unknown transform %d", transform);
   IRP_REQUIRE(n_images > 0, "preprocess: n_images %d", n_images);
   IRP_REQUIRE(max_taps >= 3 && max_taps <= 513, "preprocess: max_taps %d out of range", max_taps);
   IRP_REQUIRE(out_layout == IRP_LAYOUT_NCHW || out_layout == IRP_LAYOUT_NHWC4P, "preprocess: bad layout %d",
@@ -792,7 +807,8 @@ int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int3
   __nv_bfloat16* lut = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(d_workspace) + head);
   uint8_t* inter = static_cast<uint8_t*>(d_workspace) + head + 2048;
   IRP_CUDA_OK(cudaMemsetAsync(status, 0, 16 + static_cast<size_t>(n_images) * sizeof(int32_t), st));
-  resample_plan_kernel<<<n_images, 2 * kCrop, 0, st>>>(d_hw, n_images, max_taps, plan, status, img_taps, lut);
+  resample_plan_kernel<<<n_images, 2 * kCrop, 0, st>>>(d_hw, n_images, max_taps, transform, plan, status, img_taps,
+                                                       lut);
   IRP_CUDA_OK(cudaGetLastError());
   if (out_layout == IRP_LAYOUT_NHWC4P)
     return launch_both<IRP_LAYOUT_NHWC4P>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps,
@@ -803,8 +819,14 @@ int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int3
 
 /* Host-side view of the resize/crop geometry (used by the Python mirror to size max_taps and by tests). */
 int irp_preprocess_geometry(int h, int w, int* out_h, int* out_w, int* top, int* left, int* taps) {
+  return irp_preprocess_geometry_ex(h, w, IRP_TRANSFORM_WEIGHTS_DEFAULT, out_h, out_w, top, left, taps);
+}
+
+int irp_preprocess_geometry_ex(int h, int w, int transform, int* out_h, int* out_w, int* top, int* left, int* taps) {
   IRP_REQUIRE(h > 0 && w > 0, "geometry: bad size %dx%d", h, w);
-  const Geometry g = compute_geometry(h, w);
+  IRP_REQUIRE(transform == IRP_TRANSFORM_WEIGHTS_DEFAULT || transform == IRP_TRANSFORM_VAL_256,
+              "geometry: unknown transform %d", transform);
+  const Geometry g = compute_geometry(h, w, transform);
   if (out_h) *out_h = g.out_h;
   if (out_w) *out_w = g.out_w;
   if (top) *top = g.top;

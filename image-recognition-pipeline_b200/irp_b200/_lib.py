@@ -15,6 +15,8 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libirp_b200.so"))
 
 IRP_OK = 0
 LAYOUT_NCHW = 0
+TRANSFORM_WEIGHTS_DEFAULT = 0  # ResNet50_Weights.DEFAULT.transforms() (resize 232, crop 224)
+TRANSFORM_VAL_256 = 1          # functions/dataload.py:51-56 (Resize((256,256)), CenterCrop(224))
 LAYOUT_NHWC4P = 1
 CROP = 224
 PAD_HW = 230
@@ -36,6 +38,11 @@ SIGNATURES = {
     "irp_preprocess_geometry": (_i, [_i, _i] + [C.POINTER(_i)] * 5),
     "irp_preprocess_workspace_bytes": (_sz, [_i, _i]),
     "irp_preprocess": (_i, [_vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _i, _vp]),
+    "irp_preprocess_ex": (_i, [_vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _i, _i, _vp]),
+    "irp_preprocess_geometry_ex": (_i, [_i, _i, _i] + [C.POINTER(_i)] * 5),
+    "irp_classifier_head_workspace_bytes": (_sz, [_i, _i]),
+    "irp_classifier_head": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "irp_cross_entropy_stats": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "irp_resnet50_create": (_i, [C.POINTER(_vp), _i]),
     "irp_resnet50_destroy": (None, [_vp]),
     "irp_resnet50_conv_shape": (_i, [_i] + [C.POINTER(_i)] * 5),
@@ -109,9 +116,11 @@ def init(device_index: int) -> C.CDLL:
     return lib
 
 
-def geometry(h: int, w: int):
-    """(out_h, out_w, top, left, taps) of the resize-232 / crop-224 transform for an h x w image."""
+def geometry(h: int, w: int, transform: int = 0):
+    """(out_h, out_w, top, left, taps) of the resize / crop-224 transform for an h x w image
+    (transform 0: ResNet50_Weights.DEFAULT.transforms(), 1: the classifier's Resize((256,256)) val_transform)."""
     lib = load()
     vals = [C.c_int() for _ in range(5)]
-    check(lib.irp_preprocess_geometry(int(h), int(w), *[C.byref(v) for v in vals]), "irp_preprocess_geometry")
+    check(lib.irp_preprocess_geometry_ex(int(h), int(w), int(transform), *[C.byref(v) for v in vals]),
+          "irp_preprocess_geometry_ex")
     return tuple(v.value for v in vals)

@@ -54,6 +54,30 @@ def _(pixels, offsets, hw, max_taps, layout):
     return pixels.new_empty(shape, dtype=torch.bfloat16)
 
 
+@torch.library.custom_op("irp_b200::preprocess_ex", mutates_args=())
+def preprocess_ex(pixels: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor, max_taps: int, layout: int,
+                  transform: int) -> torch.Tensor:
+    """`preprocess` with the resize geometry selected by `transform` (_lib.TRANSFORM_*): 1 = the classifier's
+    validation transform, Resize((256,256)) + CenterCrop(224) (functions/dataload.py:51-56)."""
+    lib = _lib_for(pixels)
+    assert pixels.dtype == torch.uint8 and offsets.dtype == torch.int64 and hw.dtype == torch.int32
+    n = hw.shape[0]
+    shape = (n, 3, _lib.CROP, _lib.CROP) if layout == _lib.LAYOUT_NCHW else (n, _lib.PAD_HW, _lib.PAD_HW, 4)
+    out = torch.empty(shape, dtype=torch.bfloat16, device=pixels.device)
+    ws_bytes = lib.irp_preprocess_workspace_bytes(n, max_taps)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pixels.device)
+    _lib.check(lib.irp_preprocess_ex(_ptr(pixels), _ptr(offsets), _ptr(hw), n, max_taps, _ptr(ws), ws_bytes,
+                                     _ptr(out), layout, transform, _stream()), "irp_preprocess_ex")
+    return out
+
+
+@preprocess_ex.register_fake
+def _(pixels, offsets, hw, max_taps, layout, transform):
+    n = hw.shape[0]
+    shape = (n, 3, _lib.CROP, _lib.CROP) if layout == _lib.LAYOUT_NCHW else (n, _lib.PAD_HW, _lib.PAD_HW, 4)
+    return pixels.new_empty(shape, dtype=torch.bfloat16)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # A2 ResNet-50 trunk (handle passed as an integer address)
 # ---------------------------------------------------------------------------------------------------------------
@@ -212,3 +236,46 @@ def _(z, group, n_groups, contamination):
     n = z.shape[0]
     return (z.new_empty(n, dtype=torch.float64), z.new_empty(n, dtype=torch.float64),
             z.new_empty(n_groups, dtype=torch.float64), z.new_empty(n, dtype=torch.uint8))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N1 classifier head (functions/model.py:29-40) and the evaluate_full statistics (functions/train.py:208-216)
+# ---------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("irp_b200::classifier_head", mutates_args=())
+def classifier_head(features: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
+                    b2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 [B,in] features -> (logits fp32 [B,C], argmax int32 [B]) through Linear-ReLU-Linear (eval mode)."""
+    lib = _lib_for(features)
+    for t in (features, w1, b1, w2, b2):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    b, in_dim = features.shape
+    hidden, c = w1.shape[0], w2.shape[0]
+    assert w1.shape[1] == in_dim and w2.shape[1] == hidden and b1.numel() == hidden and b2.numel() == c
+    logits = torch.empty((b, c), dtype=torch.float32, device=features.device)
+    pred = torch.empty((b,), dtype=torch.int32, device=features.device)
+    ws_bytes = lib.irp_classifier_head_workspace_bytes(b, hidden)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=features.device)
+    _lib.check(lib.irp_classifier_head(_ptr(features), b, in_dim, _ptr(w1), _ptr(b1), hidden, _ptr(w2), _ptr(b2), c,
+                                       _ptr(logits), _ptr(pred), _ptr(ws), ws_bytes, _stream()),
+               "irp_classifier_head")
+    return logits, pred
+
+
+@classifier_head.register_fake
+def _(features, w1, b1, w2, b2):
+    b, c = features.shape[0], w2.shape[0]
+    return features.new_empty((b, c)), features.new_empty((b,), dtype=torch.int32)
+
+
+def cross_entropy_stats(logits: torch.Tensor, labels: torch.Tensor,
+                        class_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp64 [3] on the device: sum of weighted per-row cross-entropies, sum of weights, number of correct rows."""
+    lib = _lib_for(logits)
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and labels.dtype == torch.int64
+    stats = torch.empty(3, dtype=torch.float64, device=logits.device)
+    w = None
+    if class_weights is not None:
+        w = class_weights.to(device=logits.device, dtype=torch.float32).contiguous()
+    _lib.check(lib.irp_cross_entropy_stats(_ptr(logits), _ptr(labels.contiguous()), logits.shape[0], logits.shape[1],
+                                           _ptr(w), _ptr(stats), _stream()), "irp_cross_entropy_stats")
+    return stats

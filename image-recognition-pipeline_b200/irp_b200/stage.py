@@ -144,8 +144,11 @@ class PackedImages:
         return int((self.hw_np[:, 0].astype(np.int64) * self.hw_np[:, 1] * 3).sum())
 
 
-def taps_for(h: int, w: int) -> int:
-    """2*ceil(max(scale,1))+1 for the resize-232 transform of an h x w image (matches irp_preprocess_geometry)."""
+def taps_for(h: int, w: int, transform: int = 0) -> int:
+    """2*ceil(max(scale,1))+1 for the resize transform of an h x w image (matches irp_preprocess_geometry_ex):
+    transform 0 = short side -> 232, 1 = Resize((256,256)) of the classifier's val_transform."""
+    if transform == _lib.TRANSFORM_VAL_256:
+        return 2 * int(math.ceil(max(h / 256, w / 256, 1.0))) + 1
     if w <= h:
         out_w, out_h = 232, int(232 * h / w)
     else:
@@ -154,8 +157,8 @@ def taps_for(h: int, w: int) -> int:
     return 2 * int(math.ceil(s)) + 1
 
 
-def pack_images(images: Sequence[np.ndarray], pin: bool = True) -> PackedImages:
-    """Pack HWC uint8 RGB arrays into one (pinned) host buffer."""
+def pack_images(images: Sequence[np.ndarray], pin: bool = True, transform: int = 0) -> PackedImages:
+    """Pack HWC uint8 RGB arrays into one (pinned) host buffer; `transform` only sizes the tap bound."""
     sizes = np.array([[im.shape[0], im.shape[1]] for im in images], np.int32).reshape(-1, 2)
     nbytes = sizes[:, 0].astype(np.int64) * sizes[:, 1] * 3
     padded = (nbytes + ALIGN - 1) // ALIGN * ALIGN
@@ -167,7 +170,7 @@ def pack_images(images: Sequence[np.ndarray], pin: bool = True) -> PackedImages:
         if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
             raise ValueError(f"expected HWC uint8 RGB, got {im.dtype} {im.shape}")
         view[o:o + nb] = np.ascontiguousarray(im).reshape(-1)
-    taps = max((taps_for(int(h), int(w)) for h, w in sizes), default=3)
+    taps = max((taps_for(int(h), int(w), transform) for h, w in sizes), default=3)
     return PackedImages(buf[:max(total, 1)], torch.from_numpy(offsets), torch.from_numpy(sizes), taps, offsets, sizes)
 
 

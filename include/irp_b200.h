@@ -70,6 +70,19 @@ int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int3
                    int max_taps, void* d_workspace, size_t workspace_bytes, void* d_out, int out_layout,
                    void* stream);
 
+/* The same kernels with the resize geometry selected by `transform`:
+ *   IRP_TRANSFORM_WEIGHTS_DEFAULT  ResNet50_Weights.DEFAULT.transforms() (above; what irp_preprocess uses)
+ *   IRP_TRANSFORM_VAL_256          the classifier's validation transform, functions/dataload.py:51-56:
+ *                                  Resize((256, 256)) (aspect ratio NOT kept, Pillow antialiased bilinear),
+ *                                  CenterCrop(224), ToTensor, Normalize(ImageNet mean/std)
+ * max_taps for VAL_256: 2*ceil(max(1, h/256, w/256))+1 (irp_preprocess_geometry_ex returns it per image). */
+enum { IRP_TRANSFORM_WEIGHTS_DEFAULT = 0, IRP_TRANSFORM_VAL_256 = 1 };
+enum { IRP_VAL_RESIZE = 256 };
+int irp_preprocess_geometry_ex(int h, int w, int transform, int* out_h, int* out_w, int* top, int* left, int* taps);
+int irp_preprocess_ex(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
+                      int max_taps, void* d_workspace, size_t workspace_bytes, void* d_out, int out_layout,
+                      int transform, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * A0/A2  ResNet-50 trunk  --  replaces initialize_model (functions/data_curation.py:654-659) and the per-image
  * `model(img_tensor)` at :677 (torchvision/models/resnet.py:108-160,266-282 minus fc).  Eval-mode BatchNorm is
@@ -204,6 +217,25 @@ size_t irp_centroid_workspace_bytes(int64_t n_rows, int dim, int n_groups);
 int irp_centroid_zscore(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, int n_groups,
                         double contamination, double* d_dist, double* d_zscore, double* d_thresholds,
                         uint8_t* d_flags, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * N1  classifier inference (first "next" row)  --  the head of AnimalClassifier
+ * (functions/model.py:29-40: Dropout, Linear(in_dim, hidden), ReLU, Dropout, Linear(hidden, num_classes); eval
+ * mode, dropouts are identities) on the trunk's pooled features, and the statistics evaluate_full accumulates per
+ * batch (functions/train.py:208-216).  Inputs come from irp_preprocess_ex(IRP_TRANSFORM_VAL_256) ->
+ * irp_resnet50_embed.  All fp32, row-major, torch.nn.Linear weight layout [out, in].
+ *
+ *   irp_classifier_head     : logits [batch, num_classes]; pred [batch] = argmax (first maximum), may be NULL
+ *   irp_cross_entropy_stats : d_stats[0] = sum_i w[y_i] * CE_i, d_stats[1] = sum_i w[y_i] (w = 1 when
+ *                             d_class_weights is NULL), d_stats[2] = #(argmax_i == y_i); nn.CrossEntropyLoss's
+ *                             batch mean is stats[0] / stats[1].  Labels outside [0, num_classes) are skipped.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t irp_classifier_head_workspace_bytes(int batch, int hidden);
+int irp_classifier_head(const float* d_features, int batch, int in_dim, const float* d_w1, const float* d_b1,
+                        int hidden, const float* d_w2, const float* d_b2, int num_classes, float* d_logits,
+                        int32_t* d_pred, void* d_workspace, size_t workspace_bytes, void* stream);
+int irp_cross_entropy_stats(const float* d_logits, const int64_t* d_labels, int batch, int num_classes,
+                            const float* d_class_weights, double* d_stats, void* stream);
 
 #ifdef __cplusplus
 }

@@ -171,10 +171,56 @@ def golden_lof(dc):
     print("lof.npz: flagged", int(cls_out.sum()), int(glob_out.sum()), "| 2-D:", int(cls2.sum()), int(glob2.sum()))
 
 
+def golden_classifier():
+    """the reference's val_transform, AnimalClassifier and evaluate_full, unmodified except that
+    ``functions.model.resnet50`` is patched to build the random-init network (no download; the seed is set right
+    before the constructor runs so the parameters equal oracle/classifier_ref.build_classifier(seed))."""
+    import importlib.machinery as mach
+    import types as _types
+
+    import torch
+    from PIL import Image
+
+    for name in ("mlflow",):
+        m = _types.ModuleType(name)
+        m.__spec__ = mach.ModuleSpec(name, None)
+        sys.modules.setdefault(name, m)
+    import torchvision.models as tvm
+
+    import functions.dataload as dataload  # reference, unmodified (webdataset stubbed by import_reference)
+    import functions.model as ref_model
+    import functions.train as ref_train
+    from oracle import classifier_ref
+
+    assert ref_model.__file__.startswith(REFERENCE) and ref_train.__file__.startswith(REFERENCE)
+    ref_model.resnet50 = lambda weights=None: tvm.resnet50(weights=None)
+    seed, num_classes, n = 1234, 10, 48
+    torch.manual_seed(seed)
+    model = ref_model.AnimalClassifier(num_classes=num_classes).eval()
+    images, labels = classifier_ref.synthetic_eval_set(n, num_classes, seed=0)
+    _, val_transform = dataload.get_transforms("medium")
+    xs = torch.stack([val_transform(Image.fromarray(im)) for im in images])
+    batches = [(xs[s:s + 16], torch.from_numpy(labels[s:s + 16])) for s in range(0, n, 16)]
+    with torch.no_grad():
+        logits = model(xs).numpy()
+    ref_train.DEVICE = "cpu"
+    loss, acc, preds, labs = ref_train.evaluate_full(model, batches, torch.nn.CrossEntropyLoss(),
+                                                     disable_progress=True)
+    np.savez_compressed(os.path.join(GOLDEN, "classifier.npz"), seed=np.int64(seed), num_classes=np.int64(num_classes),
+                        n=np.int64(n), data_seed=np.int64(0), batch=np.int64(16),
+                        x_head=xs[:4].numpy(), logits=logits, loss=np.float64(loss), acc=np.float64(acc),
+                        preds=np.asarray(preds, np.int64), labels=np.asarray(labs, np.int64))
+    print("classifier.npz: loss %.6f acc %.2f" % (loss, acc), "logit range", logits.min(), logits.max())
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     dc = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "classifier":
+        golden_classifier()
+        sys.exit(0)
     golden_preprocess(dc)
     golden_embeddings(dc)
     golden_pca(dc)
     golden_lof(dc)
+    golden_classifier()

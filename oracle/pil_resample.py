@@ -129,6 +129,34 @@ def transform(img: np.ndarray) -> np.ndarray:
     return normalize(transform_u8(img))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# the classifier's validation transform: /root/reference/functions/dataload.py:51-56
+#   Resize((256, 256)) -> CenterCrop(224) -> ToTensor -> Normalize(ImageNet mean/std)
+# Resize with a (h, w) pair ignores the aspect ratio (torchvision/transforms/functional.py:476-478 -> PIL
+# Image.resize, same antialiased bilinear ImagingResample as above); ToTensor = uint8 -> float32 / 255
+# (functional.py:169-175), Normalize = (x - mean) / std (functional.py `normalize`).
+# ---------------------------------------------------------------------------------------------------------------
+VAL_RESIZE = 256
+
+
+def val_max_taps(h: int, w: int) -> int:
+    s = max(h / VAL_RESIZE, w / VAL_RESIZE, 1.0)
+    return 2 * int(math.ceil(s)) + 1
+
+
+def val_transform_u8(img: np.ndarray) -> np.ndarray:
+    """Resize((256,256)) + CenterCrop(224) -> uint8 [224,224,3]."""
+    h, w = img.shape[:2]
+    r = img if (h, w) == (VAL_RESIZE, VAL_RESIZE) else resize_bilinear_u8(img, VAL_RESIZE, VAL_RESIZE)
+    top, left = crop_offsets(VAL_RESIZE, VAL_RESIZE)
+    return np.ascontiguousarray(r[top:top + CROP, left:left + CROP])
+
+
+def val_transform(img: np.ndarray) -> np.ndarray:
+    """The reference val_transform on an HWC uint8 RGB array -> float32 [3,224,224]."""
+    return normalize(val_transform_u8(img))
+
+
 def to_bf16_bits(x: np.ndarray) -> np.ndarray:
     """float32 -> bfloat16 (round to nearest even), returned as uint16 bit patterns."""
     u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)

@@ -774,3 +774,91 @@ def test_scale_out_config_shape_batch512_pca128_global_only(lib):
         assert abs(int(gf.sum()) - round(0.03 * n)) <= 2
     finally:
         trunk512.close()
+
+
+# =============================================================================================== N1 classifier
+def _val_preprocess(ops_mod, images, layout):
+    from irp_b200 import _lib
+    from irp_b200.stage import pack_images
+    p = pack_images(images, transform=_lib.TRANSFORM_VAL_256).to("cuda:0")
+    return ops_mod.preprocess_ex(p.pixels, p.offsets, p.hw, p.max_taps, layout, _lib.TRANSFORM_VAL_256)
+
+
+def test_val_transform_golden_and_ragged_sizes_bit_exact(ops_mod):
+    """functions/dataload.py:51-56 (Resize((256,256)), CenterCrop(224), ToTensor, Normalize) on the device: equal to
+    the reference's float32 output rounded to bf16, for the golden images and for assorted aspect ratios
+    (upscales, 4x downscales, already-256 inputs)."""
+    from oracle import classifier_ref
+    g = load_golden("classifier.npz")
+    images, _ = classifier_ref.synthetic_eval_set(int(g["n"]), int(g["num_classes"]), seed=int(g["data_seed"]))
+    out = _val_preprocess(ops_mod, images[:4], 0).cpu()
+    assert torch.equal(out, torch.from_numpy(g["x_head"]).bfloat16())
+    sizes = [(256, 256), (300, 400), (97, 640), (1024, 300), (224, 224), (31, 29), (600, 800)]
+    imgs = [np.random.default_rng(50 + i).integers(0, 256, (h, w, 3), dtype=np.uint8) for i, (h, w) in enumerate(sizes)]
+    want = torch.from_numpy(np.stack([pil_resample.val_transform(im) for im in imgs])).bfloat16()
+    assert torch.equal(_val_preprocess(ops_mod, imgs, 0).cpu(), want)
+    padded = _val_preprocess(ops_mod, imgs, 1).cpu()
+    assert torch.equal(padded[:, 3:227, 3:227, :3], want.permute(0, 2, 3, 1))
+    assert padded[:, :3].abs().sum() == 0 and padded[:, :, :3].abs().sum() == 0 and padded[..., 3].abs().sum() == 0
+
+
+@pytest.mark.parametrize("B,C", [(1, 10), (37, 10), (256, 10), (300, 3), (64, 37)])
+def test_classifier_head_matches_torch(ops_mod, B, C):
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + C)
+    feats = torch.randn(B, 2048, device="cuda", generator=g).abs() * 3
+    w1 = torch.randn(512, 2048, device="cuda", generator=g) / 45
+    b1 = torch.randn(512, device="cuda", generator=g)
+    w2 = torch.randn(C, 512, device="cuda", generator=g) / 22
+    b2 = torch.randn(C, device="cuda", generator=g)
+    logits, pred = ops_mod.classifier_head(feats, w1, b1, w2, b2)
+    ref = torch.relu(feats.double() @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double()
+    assert (logits.double() - ref).abs().max().item() < 1e-4 * ref.abs().max().item()
+    assert torch.equal(pred.long(), logits.argmax(1))
+    labels = torch.randint(0, C, (B,), device="cuda", generator=g)
+    labels[0] = C - 1
+    weights = torch.rand(C, device="cuda", generator=g) + 0.5
+    for w in (None, weights):
+        stats = ops_mod.cross_entropy_stats(logits, labels, w).cpu().numpy()
+        ce = F.cross_entropy(logits.double(), labels, weight=None if w is None else w.double(), reduction="mean")
+        assert abs(stats[0] / stats[1] - ce.item()) < 1e-9 * max(1.0, abs(ce.item()))
+        assert stats[2] == float((logits.argmax(1) == labels).sum().item())
+
+
+def test_classifier_matches_reference_golden_and_evaluate_full_drop_in(lib, capsys):
+    """AnimalClassifier inference + evaluate_full (functions/model.py:9-41, functions/train.py:192-238) through the
+    drop-in against the outputs of the reference's own code (tests/golden/classifier.npz)."""
+    from functions import train as b200_train
+    from irp_b200 import _lib
+    from irp_b200.classifier import B200Classifier
+    from irp_b200.stage import pack_images
+    from oracle import classifier_ref
+    g = load_golden("classifier.npz")
+    n, c, b = int(g["n"]), int(g["num_classes"]), int(g["batch"])
+    ref_model = classifier_ref.build_classifier(c, seed=int(g["seed"]))
+    images, labels = classifier_ref.synthetic_eval_set(n, c, seed=int(g["data_seed"]))
+    model = B200Classifier(ref_model, "cuda:0", max_batch=32)
+    try:
+        # 1. the reference's calling convention: normalised float tensors from the DataLoader
+        batches = classifier_ref.val_batches(images, labels, b)
+        logits = torch.cat([model(x) for x, _ in batches]).cpu().numpy()
+        ref = g["logits"]
+        scale = np.abs(ref).max()
+        assert np.abs(logits - ref).max() <= 2e-2 * scale
+        cos = (logits * ref).sum(1) / np.linalg.norm(logits, axis=1) / np.linalg.norm(ref, axis=1)
+        assert cos.min() >= 0.999
+        top2 = np.sort(ref, 1)[:, -2:]
+        decided = (top2[:, 1] - top2[:, 0]) > 4e-2 * scale  # rows whose argmax cannot flip inside the tolerance
+        assert np.array_equal(logits.argmax(1)[decided], g["preds"][decided])
+        loss, acc, preds, labs = b200_train.evaluate_full(model, batches, torch.nn.CrossEntropyLoss(),
+                                                          disable_progress=True)
+        assert "Evaluated on 48 samples" in capsys.readouterr().out
+        assert isinstance(preds, list) and len(preds) == n and np.array_equal(np.asarray(labs), g["labels"])
+        assert abs(loss - float(g["loss"])) <= 2e-2 * max(1.0, float(g["loss"]))
+        assert np.array_equal(np.asarray(preds)[decided], g["preds"][decided])
+        assert abs(acc - float(g["acc"])) <= 100.0 * (~decided).sum() / n + 1e-9
+        # 2. the fused route: decoded uint8 images, val_transform on the device
+        lg2, pr2 = model.predict_packed(pack_images(images, transform=_lib.TRANSFORM_VAL_256))
+        assert np.abs(lg2.cpu().numpy() - logits).max() <= 1e-5 * scale  # same pixels, same kernels
+        assert torch.equal(pr2.long().cpu(), torch.from_numpy(logits.argmax(1)))
+    finally:
+        model.close()

@@ -136,3 +136,37 @@ def test_centroid_scorer_definition():
         np.testing.assert_allclose(dist[m], np.linalg.norm(z[m] - mu, axis=1), rtol=1e-12)
         assert abs(zs[m].mean()) < 1e-9 and abs(zs[m].std() - 1) < 1e-9
         assert 0.03 <= flags[m].mean() <= 0.07
+
+
+# ------------------------------------------------------------------------------------------------ N1 classifier
+def test_val_transform_matches_reference_golden_and_torchvision_in_process():
+    """dataload.py:51-56 restated in numpy: bit-for-bit against the fixture the reference transform produced and
+    against torchvision run in-process on other sizes."""
+    from oracle import classifier_ref
+    g = load_golden("classifier.npz")
+    images, _ = classifier_ref.synthetic_eval_set(int(g["n"]), int(g["num_classes"]), seed=int(g["data_seed"]))
+    for i in range(4):
+        assert np.array_equal(pil_resample.val_transform(images[i]), g["x_head"][i])
+    from PIL import Image
+    from torchvision import transforms
+    tfm = transforms.Compose([transforms.Resize((256, 256)), transforms.CenterCrop(224), transforms.ToTensor(),
+                              transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    for (h, w), seed in zip([(256, 256), (300, 400), (97, 640), (1024, 300), (224, 224)], range(5)):
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(pil_resample.val_transform(img), tfm(Image.fromarray(img)).numpy()), (h, w)
+
+
+def test_classifier_ref_matches_reference_golden():
+    """AnimalClassifier + evaluate_full restated (oracle/classifier_ref.py) against the reference's own outputs."""
+    from oracle import classifier_ref
+    g = load_golden("classifier.npz")
+    n, c, b = int(g["n"]), int(g["num_classes"]), int(g["batch"])
+    model = classifier_ref.build_classifier(c, seed=int(g["seed"]))
+    images, labels = classifier_ref.synthetic_eval_set(n, c, seed=int(g["data_seed"]))
+    batches = classifier_ref.val_batches(images, labels, b)
+    import torch
+    out = classifier_ref.logits(model, torch.cat([x for x, _ in batches]))
+    np.testing.assert_allclose(out, g["logits"], rtol=1e-4, atol=1e-4)
+    loss, acc, preds, labs = classifier_ref.evaluate_full(model, batches)
+    assert abs(loss - float(g["loss"])) < 1e-4 and acc == float(g["acc"])
+    assert np.array_equal(np.asarray(preds), g["preds"]) and np.array_equal(np.asarray(labs), g["labels"])
