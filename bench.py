@@ -382,7 +382,7 @@ def run_ours(args, rank, local_rank, world):
                      "peak_source": f"{peaks['source']} bf16_tflops_sustained"},
         "roofline_preprocess": {"bound": "hbm", "achieved": pre_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                 "frac": pre_gbs / peaks["hbm_gbs"], "traffic": None,
-                                "kernel": "resample_kernel (+ resample_plan_kernel)",
+                                "kernel": "hpass_kernel + vpass_kernel (+ resample_plan_kernel)",
                                 "per_launch": "3*ceil(224/232*short)^2 source bytes + 301056 output bytes per image"},
         "stage_ms": {"preprocess": pre_ms / args.steps, "trunk": emb_ms / args.steps,
                      "pca_lof_other": ms_step - (pre_ms + emb_ms) / args.steps},

@@ -862,12 +862,12 @@ static size_t weight_elems(const ConvSpec& s, int stem_mode) {
   return static_cast<size_t>(s.cout) * s.ksize * s.ksize * s.cin;
 }
 
-static int resnet50_plan(irp_resnet50* net, const void* d_x, int l1_mode) {
-  const auto& sp = specs();
+// Everything in the plan that depends on the INPUT pointer (the stem's tensor maps): re-encoded alone when a call
+// brings a different input buffer, which is every call once preprocessing of the next batch overlaps the trunk of
+// the current one (two input buffers alternate).
+static int plan_stem_input(irp_resnet50* net, const void* d_x) {
   const int B = net->micro;
-  enum { A = 0, Bb = 1, T1 = 2, T2 = 3, DS = 4, STEM = 5, T1B = 6 };
-  int t1_in = T1;  // buffer holding the current block's conv1 output
-  // stem
+  enum { A = 0, STEM = 5 };
   if (net->stem_mode == 3) {
     StemPoolParams& sp3 = net->stem3;
     memset(&sp3, 0, sizeof(sp3));
@@ -900,6 +900,16 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x, int l1_mode) {
     IRP_TRY(plan_conv(&net->plans[0], net->im2col, net->weights[0], net->biases[0], nullptr, net->buf[STEM], B, 112,
                       112, 192, 64, 1, 1, 1));
   }
+  net->planned_input = d_x;
+  return IRP_OK;
+}
+
+static int resnet50_plan(irp_resnet50* net, const void* d_x, int l1_mode) {
+  const auto& sp = specs();
+  const int B = net->micro;
+  enum { A = 0, Bb = 1, T1 = 2, T2 = 3, DS = 4, STEM = 5, T1B = 6 };
+  int t1_in = T1;  // buffer holding the current block's conv1 output
+  IRP_TRY(plan_stem_input(net, d_x));
   net->out_buf[0] = STEM;
   int cur = A, other = Bb;
   size_t i = 1;
@@ -1114,8 +1124,10 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
   if (d_capture != nullptr && capture_index >= 0 && capture_index < static_cast<int>(specs().size()) &&
       specs()[capture_index].role == 2 && specs()[capture_index].cin == 64)
     l1_mode = 0;
-  if (!net->planned || net->planned_input != d_x || net->planned_l1 != l1_mode)
+  if (!net->planned || net->planned_l1 != l1_mode)
     IRP_TRY(resnet50_plan(net, d_x, l1_mode));
+  else if (net->planned_input != d_x)
+    IRP_TRY(plan_stem_input(net, d_x));
   const auto& sp = specs();
   enum { A = 0, STEM = 5 };
   for (int s0 = 0; s0 < batch; s0 += net->micro) {
