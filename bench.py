@@ -233,9 +233,9 @@ class TimedBackend:
         return out
 
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the 50 kernels of ONE irp_resnet50_embed call at batch 256,
-# from the ncu pass committed as profiles/r01_ncu_trunk_traffic_v4.csv (6 645 MB read + 4 513 MB written).
-TRUNK_DRAM_BYTES_PER_CALL = 11.158e9
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the 49 kernels of ONE irp_resnet50_embed call at batch 256,
+# from the ncu pass committed as profiles/r01_ncu_trunk_traffic_v6.csv (5 823 MB read + 3 645 MB written).
+TRUNK_DRAM_BYTES_PER_CALL = 9.468e9
 
 
 def launches_per_step(n_images, batch, dim, max_taps):
