@@ -373,8 +373,8 @@ def run_ours(args, rank, local_rank, world):
                    "parallelism": f"dp{world}: images sharded, one all-reduce of the PCA partial sums"},
         "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": conv_tflops / peaks["tflops_sustained"], "traffic": TRUNK_DRAM_BYTES_PER_CALL,
-                     "traffic_source": "ncu dram__bytes_read+write over the 50 kernels of one trunk call, "
-                                       "profiles/r01_ncu_trunk_traffic_v4.csv",
+                     "traffic_source": "ncu dram__bytes_read+write over the 49 kernels of one trunk call, "
+                                       "profiles/r01_ncu_trunk_traffic_v6.csv",
                      "kernel": "conv_gemm2_kernel / conv_chain_kernel / conv3x3_c64_kernel / stem_pool_kernel (the 53 "
                                "convolutions of one irp_resnet50_embed call, batch 256)",
                      "per_launch": f"{FLOPS_PER_IMAGE:.4e} FLOP/image x {BATCH} images per trunk call; "
