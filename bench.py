@@ -317,6 +317,14 @@ def run_ours(args, rank, local_rank, world):
 
     pre_ms = sum(e[0].elapsed_time(e[1]) for e, _ in backend.events)
     emb_ms = sum(e[1].elapsed_time(e[2]) for e, _ in backend.events)
+    # per-rank embed time (preprocess + trunk): the step ends when the SLOWEST rank reaches the PCA all-reduce, so
+    # the spread between GPUs of one box shows up as waiting time in every other rank's "pca_lof_other"
+    rank_embed_ms = None
+    if world > 1:
+        mine = torch.tensor([(pre_ms + emb_ms) / args.steps], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_embed_ms = [round(float(t.item()), 3) for t in allr]
     n_emb = sum(n for _, n in backend.events)
     calls = len(backend.events)
     conv_tflops = FLOPS_PER_IMAGE * n_emb / (emb_ms * 1e-3) / 1e12
@@ -385,7 +393,8 @@ def run_ours(args, rank, local_rank, world):
                                 "kernel": "hpass_kernel + vpass_kernel (+ resample_plan_kernel)",
                                 "per_launch": "3*ceil(224/232*short)^2 source bytes + 301056 output bytes per image"},
         "stage_ms": {"preprocess": pre_ms / args.steps, "trunk": emb_ms / args.steps,
-                     "pca_lof_other": ms_step - (pre_ms + emb_ms) / args.steps},
+                     "pca_lof_other": ms_step - (pre_ms + emb_ms) / args.steps,
+                     "embed_per_rank": rank_embed_ms},
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "gpu_launches": launches_per_step(N_IMAGES, BATCH, 2048, packed.max_taps) * args.steps,
     }

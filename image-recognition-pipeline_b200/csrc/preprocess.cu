@@ -57,6 +57,21 @@ __host__ __device__ inline Geometry compute_geometry(int h, int w, int transform
     g.top = g.left = round_half_even_div2(IRP_VAL_RESIZE - kCrop);
     return g;
   }
+  if (transform == IRP_TRANSFORM_WDS_LANCZOS) {
+    // functions/data_curation.py:896-913 resize_and_crop_image: smaller side -> 224, the other one
+    // int(side * (224 / smaller)) (Python float arithmetic), crop offsets by floor division
+    const double t = static_cast<double>(kCrop);
+    if (w < h) {
+      g.out_w = kCrop;
+      g.out_h = static_cast<int>(static_cast<double>(h) * (t / static_cast<double>(w)));
+    } else {
+      g.out_h = kCrop;
+      g.out_w = static_cast<int>(static_cast<double>(w) * (t / static_cast<double>(h)));
+    }
+    g.top = (g.out_h - kCrop) / 2;
+    g.left = (g.out_w - kCrop) / 2;
+    return g;
+  }
   if (w <= h) {
     g.out_w = kResize;
     g.out_h = static_cast<int>(static_cast<double>(static_cast<long long>(kResize) * h) / static_cast<double>(w));
@@ -67,6 +82,21 @@ __host__ __device__ inline Geometry compute_geometry(int h, int w, int transform
   g.top = round_half_even_div2(g.out_h - kCrop);
   g.left = round_half_even_div2(g.out_w - kCrop);
   return g;
+}
+
+// Pillow's filter kernels (src/libImaging/Resample.c: bilinear_filter, sinc_filter, lanczos_filter)
+__device__ __forceinline__ double triangle_weight(double x) {
+  if (x < 0.0) x = -x;
+  return x < 1.0 ? __dsub_rn(1.0, x) : 0.0;
+}
+__device__ __forceinline__ double sinc_weight(double x) {
+  if (x == 0.0) return 1.0;
+  x = __dmul_rn(x, 3.14159265358979323846);
+  return __ddiv_rn(sin(x), x);
+}
+__device__ __forceinline__ double lanczos3_weight(double x) {
+  if (-3.0 <= x && x < 3.0) return __dmul_rn(sinc_weight(x), sinc_weight(__ddiv_rn(x, 3.0)));
+  return 0.0;
 }
 
 __global__ void resample_plan_kernel(const int32_t* __restrict__ hw, int n_images, int max_taps, int transform,
@@ -105,10 +135,12 @@ __global__ void resample_plan_kernel(const int32_t* __restrict__ hw, int n_image
     atomicMax(&img_taps[img], 1);
     return;
   }
-  // Pillow precompute_coeffs (bilinear: support 1.0), evaluated in fp64 without FMA contraction.
+  // Pillow precompute_coeffs (bilinear: support 1.0, Lanczos: support 3.0), evaluated in fp64 without FMA
+  // contraction.
+  const bool lanczos = transform == IRP_TRANSFORM_WDS_LANCZOS;
   const double scale = __ddiv_rn(static_cast<double>(in_size), static_cast<double>(out_size));
   const double filterscale = scale < 1.0 ? 1.0 : scale;
-  const double support = filterscale;  // 1.0 * filterscale
+  const double support = lanczos ? __dmul_rn(3.0, filterscale) : filterscale;
   const double center = __dmul_rn(__dadd_rn(static_cast<double>(xx), 0.5), scale);
   const double ss = __ddiv_rn(1.0, filterscale);
   int xmin = static_cast<int>(__dadd_rn(__dsub_rn(center, support), 0.5));
@@ -122,15 +154,12 @@ __global__ void resample_plan_kernel(const int32_t* __restrict__ hw, int n_image
   }
   double ww = 0.0;
   for (int x = 0; x < n; ++x) {
-    double a = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
-    if (a < 0.0) a = -a;
-    const double wgt = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
-    ww = __dadd_rn(ww, wgt);
+    const double a = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
+    ww = __dadd_rn(ww, lanczos ? lanczos3_weight(a) : triangle_weight(a));
   }
   for (int x = 0; x < n; ++x) {
-    double a = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
-    if (a < 0.0) a = -a;
-    double wgt = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+    const double a = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
+    double wgt = lanczos ? lanczos3_weight(a) : triangle_weight(a);
     if (ww != 0.0) wgt = __ddiv_rn(wgt, ww);
     // normalize_coeffs_8bpc: round half away from zero into 22-bit fixed point
     const double scaled = __dmul_rn(wgt, static_cast<double>(1 << kPrecisionBits));
@@ -519,7 +548,16 @@ __global__ void __launch_bounds__(kThreads, (TH <= 8 ? 3 : (TH <= 16 ? 2 : 1))) 
 //                  three 2-byte stores (NCHW); the threads of the 3-pixel border write zeros.
 // The arithmetic is the band kernels' (and Pillow's): acc = 2^21 + sum src * coef, clip8(acc >> 22), twice.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kTwoPassMaxRows = 576;  // >= 224 * 2.5 + 2 * 3 + 2: source rows the crop window of a fast image can need
+constexpr int kTwoPassMaxRows = 640;  // source rows of the crop window an image may need to take this path
+constexpr int kTwoPassTaps = 16;      // and its largest tap count (<= kFastTaps: unrolled register-resident weights)
+
+// Images whose crop window needs at most kTwoPassMaxRows source rows and kTwoPassTaps taps take the two-pass
+// path; anything beyond that (downscales by more than ~2.7x with the Lanczos filter, ~2.8x bilinear) the generic
+// band kernel.
+__device__ __forceinline__ bool two_pass_image(const int32_t* __restrict__ plan_v, int taps) {
+  const int span = plan_v[kCrop - 1] + plan_v[2 * kCrop - 1] - plan_v[0];
+  return taps <= kTwoPassTaps && span <= kTwoPassMaxRows;
+}
 constexpr int kHRowsPerCta = 16;
 constexpr int kVRowsPerCta = 8;  // (padded) output rows per CTA of the vertical pass
 

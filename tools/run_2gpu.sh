@@ -1,0 +1,7 @@
+#!/bin/bash
+cd /root/repo
+mkdir -p gpurun_out
+N=${1:-2}
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_${N}gpu.log 2> gpurun_out/bench_${N}gpu.err; echo "rc=$?"
+tail -c 2500 gpurun_out/bench_${N}gpu.log; tail -n 5 gpurun_out/bench_${N}gpu.err
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1gpu_samebox.log 2>/dev/null; tail -c 600 gpurun_out/bench_1gpu_samebox.log | cut -c1-400
