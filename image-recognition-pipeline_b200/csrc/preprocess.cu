@@ -175,6 +175,17 @@ __device__ __forceinline__ int clip8_fixed(int acc) {
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
+constexpr int kTwoPassMaxRows = 640;  // source rows of the crop window an image may need to take this path
+constexpr int kTwoPassTaps = 16;      // and its largest tap count (<= kFastTaps: unrolled register-resident weights)
+
+// Images whose crop window needs at most kTwoPassMaxRows source rows and kTwoPassTaps taps take the two-pass
+// path; anything beyond that (downscales by more than ~2.7x with the Lanczos filter, ~2.8x bilinear) the generic
+// band kernel.
+__device__ __forceinline__ bool two_pass_image(const int32_t* __restrict__ plan_v, int taps) {
+  const int span = plan_v[kCrop - 1] + plan_v[2 * kCrop - 1] - plan_v[0];
+  return taps <= kTwoPassTaps && span <= kTwoPassMaxRows;
+}
+
 // dynamic smem: int32 hfirst[224], hcount[224], hcoef[224*T], vfirst[8], vcount[8], vcoef[8*T];
 //               bf16 lut[768]; uint8 hbuf[kChunkRows*672]; bf16 obuf[...]
 template <int LAYOUT>
@@ -183,10 +194,14 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(const uint8_t* __res
                                                             const int32_t* __restrict__ hw, int max_taps,
                                                             const int32_t* __restrict__ plan,
                                                             const int32_t* __restrict__ img_taps,
-                                                            __nv_bfloat16* __restrict__ out) {
+                                                            __nv_bfloat16* __restrict__ out, int two_pass) {
   extern __shared__ __align__(16) uint8_t smem[];
-  if (img_taps[blockIdx.y] <= kFastTaps) return;  // handled by resample_fast_kernel
   const int T = max_taps;
+  {  // images the fast kernels of the selected mode handle are skipped here
+    const int taps = img_taps[blockIdx.y];
+    const int32_t* pv = plan + (static_cast<size_t>(blockIdx.y) * 2 + 1) * plan_ints_per_axis(T);
+    if (two_pass ? two_pass_image(pv, taps) : taps <= kFastTaps) return;
+  }
   int32_t* hfirst = reinterpret_cast<int32_t*>(smem);
   int32_t* hcount = hfirst + kCrop;
   int32_t* hcoef = hcount + kCrop;
@@ -277,7 +292,16 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(const uint8_t* __res
   }
 
   // ---- normalise + stage ----
-  if (LAYOUT == IRP_LAYOUT_NHWC4P) {
+  if (LAYOUT == IRP_LAYOUT_U8_HWC) {
+    uint8_t* o8 = reinterpret_cast<uint8_t*>(out) + (static_cast<size_t>(img) * kCrop + y0) * kRowElems;
+#pragma unroll
+    for (int y = 0; y < kBandRows; ++y)
+#pragma unroll
+      for (int k = 0; k < kElemsPerThread; ++k) {
+        const int e = tid + k * kThreads;
+        if (e < kRowElems) o8[static_cast<size_t>(y) * kRowElems + e] = static_cast<uint8_t>(clip8_fixed(acc[y][k]));
+      }
+  } else if (LAYOUT == IRP_LAYOUT_NHWC4P) {
     // obuf[8][230][4]; zero everything first (borders + pad channel)
     uint32_t* z = reinterpret_cast<uint32_t*>(obuf);
     for (int i = tid; i < kBandRows * kPad * 2; i += kThreads) z[i] = 0u;
@@ -548,16 +572,6 @@ __global__ void __launch_bounds__(kThreads, (TH <= 8 ? 3 : (TH <= 16 ? 2 : 1))) 
 //                  three 2-byte stores (NCHW); the threads of the 3-pixel border write zeros.
 // The arithmetic is the band kernels' (and Pillow's): acc = 2^21 + sum src * coef, clip8(acc >> 22), twice.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kTwoPassMaxRows = 640;  // source rows of the crop window an image may need to take this path
-constexpr int kTwoPassTaps = 16;      // and its largest tap count (<= kFastTaps: unrolled register-resident weights)
-
-// Images whose crop window needs at most kTwoPassMaxRows source rows and kTwoPassTaps taps take the two-pass
-// path; anything beyond that (downscales by more than ~2.7x with the Lanczos filter, ~2.8x bilinear) the generic
-// band kernel.
-__device__ __forceinline__ bool two_pass_image(const int32_t* __restrict__ plan_v, int taps) {
-  const int span = plan_v[kCrop - 1] + plan_v[2 * kCrop - 1] - plan_v[0];
-  return taps <= kTwoPassTaps && span <= kTwoPassMaxRows;
-}
 constexpr int kHRowsPerCta = 16;
 constexpr int kVRowsPerCta = 8;  // (padded) output rows per CTA of the vertical pass
 
@@ -569,23 +583,45 @@ __global__ void __launch_bounds__(kCrop) hpass_kernel(const uint8_t* __restrict_
                                                      uint8_t* __restrict__ inter) {
   const int img = blockIdx.y;
   const int nt = img_taps[img];
-  if (nt > kFastTaps) return;  // the generic kernel handles this image
   const int T = max_taps;
   const int32_t* plan_h = plan + (static_cast<size_t>(img) * 2 + 0) * plan_ints_per_axis(T);
   const int32_t* plan_v = plan + (static_cast<size_t>(img) * 2 + 1) * plan_ints_per_axis(T);
+  if (!two_pass_image(plan_v, nt)) return;  // the generic kernel handles this image
   const int row_lo = plan_v[0];
   const int row_hi = plan_v[kCrop - 1] + plan_v[2 * kCrop - 1];  // first + count of the last output row
   const int r0 = row_lo + blockIdx.x * kHRowsPerCta;
   if (r0 >= row_hi) return;
   const int x = threadIdx.x;
   const int first = plan_h[x], n = plan_h[kCrop + x];
-  int cf[kFastTaps];
-#pragma unroll
-  for (int t = 0; t < kFastTaps; ++t) cf[t] = t < n ? plan_h[2 * kCrop + static_cast<size_t>(x) * T + t] : 0;
   const int w = hw[2 * img + 1];
   const size_t row_bytes = static_cast<size_t>(w) * 3;
   const uint8_t* src = pixels + offsets[img] + static_cast<size_t>(first) * 3;
   uint8_t* dst = inter + (static_cast<size_t>(img) * kTwoPassMaxRows) * kRowElems + x * 3;
+  if (nt > kFastTaps) {
+    // 7..kTwoPassTaps taps (Lanczos, or bilinear downscales by 2.5-2.8x): weights stay in the (L1-cached) plan
+    const int32_t* cfp = plan_h + 2 * kCrop + static_cast<size_t>(x) * T;
+    for (int rr = 0; rr < kHRowsPerCta; ++rr) {
+      const int r = r0 + rr;
+      if (r >= row_hi) break;
+      const uint8_t* sp = src + static_cast<size_t>(r) * row_bytes;
+      int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+#pragma unroll 4
+      for (int t = 0; t < n; ++t) {
+        const int c = __ldg(cfp + t);
+        a0 += static_cast<int>(__ldg(sp + 3 * t + 0)) * c;
+        a1 += static_cast<int>(__ldg(sp + 3 * t + 1)) * c;
+        a2 += static_cast<int>(__ldg(sp + 3 * t + 2)) * c;
+      }
+      uint8_t* d = dst + static_cast<size_t>(r - row_lo) * kRowElems;
+      d[0] = static_cast<uint8_t>(clip8_fixed(a0));
+      d[1] = static_cast<uint8_t>(clip8_fixed(a1));
+      d[2] = static_cast<uint8_t>(clip8_fixed(a2));
+    }
+    return;
+  }
+  int cf[kFastTaps];
+#pragma unroll
+  for (int t = 0; t < kFastTaps; ++t) cf[t] = t < n ? plan_h[2 * kCrop + static_cast<size_t>(x) * T + t] : 0;
 #pragma unroll 4
   for (int rr = 0; rr < kHRowsPerCta; ++rr) {
     const int r = r0 + rr;
@@ -614,9 +650,9 @@ __global__ void __launch_bounds__(256) vpass_kernel(const int32_t* __restrict__ 
                                                     const __nv_bfloat16* __restrict__ lut,
                                                     __nv_bfloat16* __restrict__ out) {
   const int img = blockIdx.y;
-  if (img_taps[img] > kFastTaps) return;
   const int T = max_taps;
   const int32_t* plan_v = plan + (static_cast<size_t>(img) * 2 + 1) * plan_ints_per_axis(T);
+  if (!two_pass_image(plan_v, img_taps[img])) return;
   constexpr int kSide = LAYOUT == IRP_LAYOUT_NHWC4P ? kPad : kCrop;  // rows / columns this launch covers
   constexpr int kBorder = LAYOUT == IRP_LAYOUT_NHWC4P ? 3 : 0;
   const int px = threadIdx.x;          // (padded) output column
@@ -628,7 +664,7 @@ __global__ void __launch_bounds__(256) vpass_kernel(const int32_t* __restrict__ 
   for (int py = blockIdx.x * kVRowsPerCta; py < min(kSide, (static_cast<int>(blockIdx.x) + 1) * kVRowsPerCta); ++py) {
   const int y = py - kBorder;          // (padded) output row py
   const bool inside = y >= 0 && y < kCrop && x >= 0 && x < kCrop;
-  uint32_t rgb[3] = {0u, 0u, 0u};  // bf16 bit patterns
+  uint32_t rgb[3] = {0u, 0u, 0u};  // bf16 bit patterns (uint8 values for IRP_LAYOUT_U8_HWC)
   if (inside) {
     const int vf = plan_v[y], vn = plan_v[kCrop + y];
     const int32_t* vc = plan_v + 2 * kCrop + static_cast<size_t>(y) * T;
@@ -641,11 +677,22 @@ __global__ void __launch_bounds__(256) vpass_kernel(const int32_t* __restrict__ 
       a1 += static_cast<int>(rp[1]) * c;
       a2 += static_cast<int>(rp[2]) * c;
     }
-    rgb[0] = __ldg(l16 + clip8_fixed(a0));
-    rgb[1] = __ldg(l16 + 256 + clip8_fixed(a1));
-    rgb[2] = __ldg(l16 + 512 + clip8_fixed(a2));
+    if (LAYOUT == IRP_LAYOUT_U8_HWC) {
+      rgb[0] = clip8_fixed(a0);
+      rgb[1] = clip8_fixed(a1);
+      rgb[2] = clip8_fixed(a2);
+    } else {
+      rgb[0] = __ldg(l16 + clip8_fixed(a0));
+      rgb[1] = __ldg(l16 + 256 + clip8_fixed(a1));
+      rgb[2] = __ldg(l16 + 512 + clip8_fixed(a2));
+    }
   }
-  if (LAYOUT == IRP_LAYOUT_NHWC4P) {
+  if (LAYOUT == IRP_LAYOUT_U8_HWC) {
+    uint8_t* o8 = reinterpret_cast<uint8_t*>(out) + ((static_cast<size_t>(img) * kCrop + py) * kCrop + px) * 3;
+    o8[0] = static_cast<uint8_t>(rgb[0]);
+    o8[1] = static_cast<uint8_t>(rgb[1]);
+    o8[2] = static_cast<uint8_t>(rgb[2]);
+  } else if (LAYOUT == IRP_LAYOUT_NHWC4P) {
     uint2 o;
     o.x = rgb[0] | (rgb[1] << 16);
     o.y = rgb[2];
@@ -724,7 +771,7 @@ template <int LAYOUT>
 static int launch_resample(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
                            int max_taps, const int32_t* plan, const int32_t* img_taps, __nv_bfloat16* out,
                            cudaStream_t st, uint8_t* inter, const __nv_bfloat16* lut) {
-  if (two_pass_enabled()) {
+  if (two_pass_enabled() || LAYOUT == IRP_LAYOUT_U8_HWC) {
     dim3 hgrid((kTwoPassMaxRows + kHRowsPerCta - 1) / kHRowsPerCta, n_images);
     hpass_kernel<<<hgrid, kCrop, 0, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, img_taps, inter);
     constexpr int kSide = LAYOUT == IRP_LAYOUT_NHWC4P ? kPad : kCrop;
@@ -733,10 +780,11 @@ static int launch_resample(const uint8_t* d_pixels, const int64_t* d_offsets, co
     IRP_CUDA_OK(cudaGetLastError());
     return IRP_OK;
   }
+  constexpr int BL = LAYOUT == IRP_LAYOUT_U8_HWC ? IRP_LAYOUT_NCHW : LAYOUT;  // band kernels: bf16 layouts only
   switch (fast_band_rows()) {
-    default: IRP_TRY((launch_fast<LAYOUT, 8>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st))); break;
-    case 32: IRP_TRY((launch_fast<LAYOUT, 32>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st))); break;
-    case 16: IRP_TRY((launch_fast<LAYOUT, 16>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st))); break;
+    default: IRP_TRY((launch_fast<BL, 8>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st))); break;
+    case 32: IRP_TRY((launch_fast<BL, 32>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st))); break;
+    case 16: IRP_TRY((launch_fast<BL, 16>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps, out, st))); break;
   }
   return IRP_OK;
 }
@@ -780,7 +828,8 @@ static int launch_generic(const uint8_t* d_pixels, const int64_t* d_offsets, con
     cfg = smem;
   }
   dim3 grid(kCrop / kBandRows, n_images);
-  k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, img_taps, out);
+  k<<<grid, kThreads, smem, st>>>(d_pixels, d_offsets, d_hw, max_taps, plan, img_taps, out,
+                                  (two_pass_enabled() || LAYOUT == IRP_LAYOUT_U8_HWC) ? 1 : 0);
   IRP_CUDA_OK(cudaGetLastError());
   return IRP_OK;
 }
@@ -825,12 +874,13 @@ int irp_preprocess_ex(const uint8_t* d_pixels, const int64_t* d_offsets, const i
                       int max_taps, void* d_workspace, size_t workspace_bytes, void* d_out, int out_layout,
                       int transform, void* stream) {
   IRP_REQUIRE(d_pixels && d_offsets && d_hw && d_workspace && d_out, "preprocess: null argument");
-  IRP_REQUIRE(transform == IRP_TRANSFORM_WEIGHTS_DEFAULT || transform == IRP_TRANSFORM_VAL_256,
+  IRP_REQUIRE(transform == IRP_TRANSFORM_WEIGHTS_DEFAULT || transform == IRP_TRANSFORM_VAL_256 ||
+                  transform == IRP_TRANSFORM_WDS_LANCZOS,
               "preprocess: unknown transform %d", transform);
   IRP_REQUIRE(n_images > 0, "preprocess: n_images %d", n_images);
   IRP_REQUIRE(max_taps >= 3 && max_taps <= 513, "preprocess: max_taps %d out of range", max_taps);
-  IRP_REQUIRE(out_layout == IRP_LAYOUT_NCHW || out_layout == IRP_LAYOUT_NHWC4P, "preprocess: bad layout %d",
-              out_layout);
+  IRP_REQUIRE(out_layout == IRP_LAYOUT_NCHW || out_layout == IRP_LAYOUT_NHWC4P || out_layout == IRP_LAYOUT_U8_HWC,
+              "preprocess: bad layout %d", out_layout);
   IRP_REQUIRE(workspace_bytes >= irp_preprocess_workspace_bytes(n_images, max_taps),
               "preprocess: workspace %zu < %zu bytes", workspace_bytes,
               irp_preprocess_workspace_bytes(n_images, max_taps));
@@ -848,6 +898,9 @@ int irp_preprocess_ex(const uint8_t* d_pixels, const int64_t* d_offsets, const i
   resample_plan_kernel<<<n_images, 2 * kCrop, 0, st>>>(d_hw, n_images, max_taps, transform, plan, status, img_taps,
                                                        lut);
   IRP_CUDA_OK(cudaGetLastError());
+  if (out_layout == IRP_LAYOUT_U8_HWC)
+    return launch_both<IRP_LAYOUT_U8_HWC>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps,
+                                          static_cast<__nv_bfloat16*>(d_out), st, inter, lut);
   if (out_layout == IRP_LAYOUT_NHWC4P)
     return launch_both<IRP_LAYOUT_NHWC4P>(d_pixels, d_offsets, d_hw, n_images, max_taps, plan, img_taps,
                                           static_cast<__nv_bfloat16*>(d_out), st, inter, lut);
@@ -862,7 +915,8 @@ int irp_preprocess_geometry(int h, int w, int* out_h, int* out_w, int* top, int*
 
 int irp_preprocess_geometry_ex(int h, int w, int transform, int* out_h, int* out_w, int* top, int* left, int* taps) {
   IRP_REQUIRE(h > 0 && w > 0, "geometry: bad size %dx%d", h, w);
-  IRP_REQUIRE(transform == IRP_TRANSFORM_WEIGHTS_DEFAULT || transform == IRP_TRANSFORM_VAL_256,
+  IRP_REQUIRE(transform == IRP_TRANSFORM_WEIGHTS_DEFAULT || transform == IRP_TRANSFORM_VAL_256 ||
+                  transform == IRP_TRANSFORM_WDS_LANCZOS,
               "geometry: unknown transform %d", transform);
   const Geometry g = compute_geometry(h, w, transform);
   if (out_h) *out_h = g.out_h;
@@ -873,6 +927,7 @@ int irp_preprocess_geometry_ex(int h, int w, int transform, int* out_h, int* out
     const double sx = static_cast<double>(w) / g.out_w, sy = static_cast<double>(h) / g.out_h;
     double s = sx > sy ? sx : sy;
     if (s < 1.0) s = 1.0;
+    if (transform == IRP_TRANSFORM_WDS_LANCZOS) s *= 3.0;  // Lanczos support
     int c = static_cast<int>(s);
     if (static_cast<double>(c) < s) ++c;
     *taps = 2 * c + 1;

@@ -258,3 +258,43 @@ def create_results_dataframe(embedding, labels, paths, class_outliers, global_ou
         'is_class_outlier': class_outliers,
         'is_global_outlier': global_outliers
     })
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# WebDataset curation: the resize step (reference functions/data_curation.py:883-913)
+# -----------------------------------------------------------------------------------------------------------------
+def _to_rgb(img):
+    """The reference's mode handling (data_curation.py:886-892): RGBA composited on white through its own alpha,
+    any other non-RGB mode converted."""
+    from PIL import Image
+
+    if img.mode == 'RGBA':
+        background = Image.new('RGB', img.size, (255, 255, 255))
+        background.paste(img, mask=img.split()[3])
+        return background
+    if img.mode != 'RGB':
+        return img.convert('RGB')
+    return img
+
+
+def resize_and_crop_images(images, device="cuda:0", batch_size=256):
+    """Batch form of `resize_and_crop_image`: a list of PIL images -> uint8 array [n,224,224,3] (the pixels of the
+    images the reference function returns), Lanczos resize + center crop on the device."""
+    dev = torch.device(device)
+    arrays = [np.asarray(_to_rgb(im)) for im in images]
+    out = np.empty((len(arrays), _lib.CROP, _lib.CROP, 3), np.uint8)
+    for lo in range(0, len(arrays), batch_size):
+        part = pack_images(arrays[lo:lo + batch_size], transform=_lib.TRANSFORM_WDS_LANCZOS).to(dev)
+        res = ops.preprocess_ex(part.pixels, part.offsets, part.hw, part.max_taps, _lib.LAYOUT_U8_HWC,
+                                _lib.TRANSFORM_WDS_LANCZOS)
+        out[lo:lo + len(res)] = res.cpu().numpy()
+    return out
+
+
+def resize_and_crop_image(img, target_size=224, device="cuda:0"):
+    """Resize and center crop image to target_size x target_size (drop-in: returns a PIL image)."""
+    from PIL import Image
+
+    if target_size != _lib.CROP:
+        raise ValueError("the B200 path is built for target_size=224 (the reference's only call site)")
+    return Image.fromarray(resize_and_crop_images([img], device=device)[0])

@@ -17,6 +17,8 @@ IRP_OK = 0
 LAYOUT_NCHW = 0
 TRANSFORM_WEIGHTS_DEFAULT = 0  # ResNet50_Weights.DEFAULT.transforms() (resize 232, crop 224)
 TRANSFORM_VAL_256 = 1          # functions/dataload.py:51-56 (Resize((256,256)), CenterCrop(224))
+TRANSFORM_WDS_LANCZOS = 2      # functions/data_curation.py:883-913 (smaller side -> 224, LANCZOS, center crop)
+LAYOUT_U8_HWC = 2              # uint8 [n,224,224,3]: the resized pixels themselves (no normalisation)
 LAYOUT_NHWC4P = 1
 CROP = 224
 PAD_HW = 230

@@ -54,16 +54,25 @@ def _(pixels, offsets, hw, max_taps, layout):
     return pixels.new_empty(shape, dtype=torch.bfloat16)
 
 
+def _preprocess_out(n: int, layout: int):
+    if layout == _lib.LAYOUT_U8_HWC:
+        return (n, _lib.CROP, _lib.CROP, 3), torch.uint8
+    if layout == _lib.LAYOUT_NCHW:
+        return (n, 3, _lib.CROP, _lib.CROP), torch.bfloat16
+    return (n, _lib.PAD_HW, _lib.PAD_HW, 4), torch.bfloat16
+
+
 @torch.library.custom_op("irp_b200::preprocess_ex", mutates_args=())
 def preprocess_ex(pixels: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor, max_taps: int, layout: int,
                   transform: int) -> torch.Tensor:
-    """`preprocess` with the resize geometry selected by `transform` (_lib.TRANSFORM_*): 1 = the classifier's
-    validation transform, Resize((256,256)) + CenterCrop(224) (functions/dataload.py:51-56)."""
+    """`preprocess` with the resize geometry / filter selected by `transform` (_lib.TRANSFORM_*): 1 = the
+    classifier's validation transform (functions/dataload.py:51-56), 2 = the WebDataset stage's Lanczos
+    resize_and_crop_image (functions/data_curation.py:883-913); layout 2 returns the uint8 pixels [n,224,224,3]."""
     lib = _lib_for(pixels)
     assert pixels.dtype == torch.uint8 and offsets.dtype == torch.int64 and hw.dtype == torch.int32
     n = hw.shape[0]
-    shape = (n, 3, _lib.CROP, _lib.CROP) if layout == _lib.LAYOUT_NCHW else (n, _lib.PAD_HW, _lib.PAD_HW, 4)
-    out = torch.empty(shape, dtype=torch.bfloat16, device=pixels.device)
+    shape, dtype = _preprocess_out(n, layout)
+    out = torch.empty(shape, dtype=dtype, device=pixels.device)
     ws_bytes = lib.irp_preprocess_workspace_bytes(n, max_taps)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pixels.device)
     _lib.check(lib.irp_preprocess_ex(_ptr(pixels), _ptr(offsets), _ptr(hw), n, max_taps, _ptr(ws), ws_bytes,
@@ -73,9 +82,8 @@ def preprocess_ex(pixels: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor,
 
 @preprocess_ex.register_fake
 def _(pixels, offsets, hw, max_taps, layout, transform):
-    n = hw.shape[0]
-    shape = (n, 3, _lib.CROP, _lib.CROP) if layout == _lib.LAYOUT_NCHW else (n, _lib.PAD_HW, _lib.PAD_HW, 4)
-    return pixels.new_empty(shape, dtype=torch.bfloat16)
+    shape, dtype = _preprocess_out(hw.shape[0], layout)
+    return pixels.new_empty(shape, dtype=dtype)
 
 
 # ---------------------------------------------------------------------------------------------------------------

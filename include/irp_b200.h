@@ -60,7 +60,7 @@ int irp_init(int device);
  *                                                     channel are (re)written by this call)
  * max_taps bounds the per-output filter taps: 2*ceil(max(1, max_i short_side_i/232))+1 for the batch.
  * ---------------------------------------------------------------------------------------------------------- */
-enum { IRP_LAYOUT_NCHW = 0, IRP_LAYOUT_NHWC4P = 1 };
+enum { IRP_LAYOUT_NCHW = 0, IRP_LAYOUT_NHWC4P = 1, IRP_LAYOUT_U8_HWC = 2 };
 enum { IRP_CROP = 224, IRP_RESIZE = 232, IRP_PAD_HW = 230 };
 
 /* Host-only helper: resized size, crop offsets and the tap bound (2*ceil(max(scale,1))+1) for one h x w image. */
@@ -75,8 +75,14 @@ int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int3
  *   IRP_TRANSFORM_VAL_256          the classifier's validation transform, functions/dataload.py:51-56:
  *                                  Resize((256, 256)) (aspect ratio NOT kept, Pillow antialiased bilinear),
  *                                  CenterCrop(224), ToTensor, Normalize(ImageNet mean/std)
- * max_taps for VAL_256: 2*ceil(max(1, h/256, w/256))+1 (irp_preprocess_geometry_ex returns it per image). */
-enum { IRP_TRANSFORM_WEIGHTS_DEFAULT = 0, IRP_TRANSFORM_VAL_256 = 1 };
+ *   IRP_TRANSFORM_WDS_LANCZOS      the WebDataset stage's resize_and_crop_image, functions/data_curation.py:
+ *                                  883-913: smaller side -> 224 with Pillow's LANCZOS filter
+ *                                  (support 3), the other side int(side * (224 / smaller)), crop offsets by floor
+ *                                  division.  Meant for IRP_LAYOUT_U8_HWC: uint8 [n,224,224,3], the bytes of the
+ *                                  PIL image the reference returns (any layout / transform pair is accepted).
+ * max_taps for VAL_256: 2*ceil(max(1, h/256, w/256))+1; for WDS_LANCZOS: 2*ceil(3*max(1, smaller/224))+1
+ * (irp_preprocess_geometry_ex returns it per image). */
+enum { IRP_TRANSFORM_WEIGHTS_DEFAULT = 0, IRP_TRANSFORM_VAL_256 = 1, IRP_TRANSFORM_WDS_LANCZOS = 2 };
 enum { IRP_VAL_RESIZE = 256 };
 int irp_preprocess_geometry_ex(int h, int w, int transform, int* out_h, int* out_w, int* top, int* left, int* taps);
 int irp_preprocess_ex(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,

@@ -171,6 +171,37 @@ def golden_lof(dc):
     print("lof.npz: flagged", int(cls_out.sum()), int(glob_out.sum()), "| 2-D:", int(cls2.sum()), int(glob2.sum()))
 
 
+def wds_input(seed, h, w, smooth):
+    """Test image for the Lanczos fixtures: uniform noise, or blocky smooth content (8x8 cells) plus mild noise --
+    numpy only, so the tests can rebuild the inputs without depending on any resampling code."""
+    rng = np.random.default_rng(seed)
+    if not smooth:
+        return rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    cells = rng.integers(0, 256, ((h + 7) // 8, (w + 7) // 8, 3)).astype(np.int32)
+    img = np.repeat(np.repeat(cells, 8, axis=0), 8, axis=1)[:h, :w] + rng.integers(-12, 13, (h, w, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def golden_wds_resize(dc):
+    """the reference's resize_and_crop_image (data_curation.py:883-913), unmodified, on RGB inputs
+    of assorted sizes (up- and downscales, both orientations, already-224 sides)."""
+    from PIL import Image
+
+    sizes = [(224, 224), (300, 400), (400, 300), (150, 200), (57, 60), (700, 500), (225, 224), (231, 500),
+             (224, 600), (1000, 1300)]
+    seeds, outs = [], []
+    for i, (h, w) in enumerate(sizes):
+        seed = 3000 + i
+        img = wds_input(seed, h, w, smooth=(i % 2 == 0))
+        out = np.asarray(dc.resize_and_crop_image(Image.fromarray(img)))
+        assert out.shape == (224, 224, 3) and out.dtype == np.uint8
+        seeds.append(seed)
+        outs.append(out)
+    np.savez_compressed(os.path.join(GOLDEN, "wds_resize.npz"), sizes=np.array(sizes, np.int32),
+                        seeds=np.array(seeds, np.int64), crops=np.stack(outs))
+    print("wds_resize.npz:", len(sizes), "images")
+
+
 def golden_classifier():
     """the reference's val_transform, AnimalClassifier and evaluate_full, unmodified except that
     ``functions.model.resnet50`` is patched to build the random-init network (no download; the seed is set right
@@ -219,8 +250,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "classifier":
         golden_classifier()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "wds":
+        golden_wds_resize(dc)
+        sys.exit(0)
     golden_preprocess(dc)
     golden_embeddings(dc)
     golden_pca(dc)
     golden_lof(dc)
     golden_classifier()
+    golden_wds_resize(dc)

@@ -47,13 +47,36 @@ def max_taps(h: int, w: int) -> int:
     return 2 * int(math.ceil(s)) + 1
 
 
-def precompute_coeffs(in_size: int, out_size: int):
-    """Pillow precompute_coeffs + normalize_coeffs_8bpc for the bilinear (triangle) filter.
+def _triangle(x: float) -> float:
+    x = abs(x)
+    return 1.0 - x if x < 1.0 else 0.0
+
+
+def _sinc(x: float) -> float:
+    if x == 0.0:
+        return 1.0
+    x = x * math.pi
+    return math.sin(x) / x
+
+
+def _lanczos3(x: float) -> float:
+    """Pillow lanczos_filter: truncated sinc, support 3."""
+    if -3.0 <= x < 3.0:
+        return _sinc(x) * _sinc(x / 3.0)
+    return 0.0
+
+
+FILTERS = {"bilinear": (_triangle, 1.0), "lanczos": (_lanczos3, 3.0)}
+
+
+def precompute_coeffs(in_size: int, out_size: int, filt: str = "bilinear"):
+    """Pillow precompute_coeffs + normalize_coeffs_8bpc for the bilinear (triangle) or the Lanczos filter.
 
     Returns (first[out_size] int, count[out_size] int, coef[out_size, ksize] int64 fixed point)."""
+    weight, base_support = FILTERS[filt]
     scale = in_size / out_size
     filterscale = max(scale, 1.0)
-    support = 1.0 * filterscale
+    support = base_support * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
     first = np.zeros(out_size, np.int64)
     count = np.zeros(out_size, np.int64)
@@ -67,8 +90,7 @@ def precompute_coeffs(in_size: int, out_size: int):
         ws = []
         ww = 0.0
         for x in range(n):
-            a = abs((x + xmin - center + 0.5) * ss)
-            wgt = 1.0 - a if a < 1.0 else 0.0
+            wgt = weight((x + xmin - center + 0.5) * ss)
             ws.append(wgt)
             ww += wgt
         for x in range(n):
@@ -83,10 +105,10 @@ def _clip8(acc: np.ndarray) -> np.ndarray:
     return np.clip(acc >> PRECISION_BITS, 0, 255).astype(np.uint8)
 
 
-def _pass(img: np.ndarray, axis: int, out_size: int) -> np.ndarray:
+def _pass(img: np.ndarray, axis: int, out_size: int, filt: str = "bilinear") -> np.ndarray:
     """One separable pass along `axis` (0 = rows/vertical, 1 = cols/horizontal) rounded to uint8 like Pillow."""
     in_size = img.shape[axis]
-    first, count, coef = precompute_coeffs(in_size, out_size)
+    first, count, coef = precompute_coeffs(in_size, out_size, filt)
     src = np.moveaxis(img, axis, 0).astype(np.int64)
     out = np.empty((out_size,) + src.shape[1:], np.uint8)
     for o in range(out_size):
@@ -97,14 +119,14 @@ def _pass(img: np.ndarray, axis: int, out_size: int) -> np.ndarray:
     return np.moveaxis(out, 0, axis)
 
 
-def resize_bilinear_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
-    """Pillow Image.resize((out_w, out_h), BILINEAR) on an HWC uint8 array (horizontal pass first)."""
+def resize_bilinear_u8(img: np.ndarray, out_h: int, out_w: int, filt: str = "bilinear") -> np.ndarray:
+    """Pillow Image.resize((out_w, out_h), BILINEAR | LANCZOS) on an HWC uint8 array (horizontal pass first)."""
     h, w = img.shape[:2]
     out = img
     if w != out_w:
-        out = _pass(out, 1, out_w)
+        out = _pass(out, 1, out_w, filt)
     if h != out_h:
-        out = _pass(out, 0, out_h)
+        out = _pass(out, 0, out_h, filt)
     return out
 
 
@@ -155,6 +177,33 @@ def val_transform_u8(img: np.ndarray) -> np.ndarray:
 def val_transform(img: np.ndarray) -> np.ndarray:
     """The reference val_transform on an HWC uint8 RGB array -> float32 [3,224,224]."""
     return normalize(val_transform_u8(img))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the WebDataset stage's resize (SURVEY.md section 8f, row N2): /root/reference/functions/data_curation.py:883-913
+# resize_and_crop_image: RGBA is composited on white / other modes converted to RGB (host side, not restated here),
+# smaller side -> 224 and the other one int(side * (224 / smaller)), Image.resize(..., LANCZOS), crop by floor
+# division, returns the uint8 image.
+# ---------------------------------------------------------------------------------------------------------------
+def wds_resized_size(h: int, w: int, target: int = CROP) -> tuple[int, int]:
+    if w < h:
+        return int(h * (target / w)), target
+    return target, int(w * (target / h))
+
+
+def wds_max_taps(h: int, w: int) -> int:
+    out_h, out_w = wds_resized_size(h, w)
+    s = 3.0 * max(h / out_h, w / out_w, 1.0)
+    return 2 * int(math.ceil(s)) + 1
+
+
+def wds_transform_u8(img: np.ndarray) -> np.ndarray:
+    """resize_and_crop_image on an HWC uint8 RGB array -> uint8 [224,224,3]."""
+    h, w = img.shape[:2]
+    out_h, out_w = wds_resized_size(h, w)
+    r = resize_bilinear_u8(img, out_h, out_w, "lanczos")
+    top, left = (out_h - CROP) // 2, (out_w - CROP) // 2
+    return np.ascontiguousarray(r[top:top + CROP, left:left + CROP])
 
 
 def to_bf16_bits(x: np.ndarray) -> np.ndarray:

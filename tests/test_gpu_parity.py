@@ -862,3 +862,49 @@ def test_classifier_matches_reference_golden_and_evaluate_full_drop_in(lib, caps
         assert torch.equal(pr2.long().cpu(), torch.from_numpy(logits.argmax(1)))
     finally:
         model.close()
+
+
+# =============================================================================================== N2 Lanczos resize
+def test_wds_lanczos_resize_bit_exact(ops_mod, lib):
+    """resize_and_crop_image (functions/data_curation.py:883-913; Pillow LANCZOS, support 3): the device output is
+    the reference's image byte for byte -- golden fixtures, the oracle on further sizes (up to a 2.7x downscale on
+    the two-pass path, 4.5x through the band kernel), and the PIL-in / PIL-out drop-in with an RGBA input."""
+    from irp_b200 import _lib
+    from irp_b200.stage import pack_images
+    from oracle.make_golden import wds_input
+    g = load_golden("wds_resize.npz")
+    imgs = [wds_input(int(s), int(h), int(w), smooth=(i % 2 == 0))
+            for i, ((h, w), s) in enumerate(zip(g["sizes"], g["seeds"]))]
+
+    def run(images):
+        p = pack_images(images, transform=_lib.TRANSFORM_WDS_LANCZOS).to("cuda:0")
+        return ops_mod.preprocess_ex(p.pixels, p.offsets, p.hw, p.max_taps, _lib.LAYOUT_U8_HWC,
+                                     _lib.TRANSFORM_WDS_LANCZOS).cpu().numpy()
+
+    out = run(imgs)
+    for i in range(len(imgs)):
+        assert np.array_equal(out[i], g["crops"][i]), tuple(g["sizes"][i])
+    sizes = [(260, 333), (90, 120), (224, 230), (512, 380), (600, 601), (1010, 1400), (31, 500)]
+    more = [np.random.default_rng(70 + i).integers(0, 256, (h, w, 3), dtype=np.uint8) for i, (h, w) in enumerate(sizes)]
+    out = run(more)
+    for i, im in enumerate(more):
+        assert np.array_equal(out[i], pil_resample.wds_transform_u8(im)), sizes[i]
+    # drop-in: PIL image in, PIL image out, RGBA composited on white like the reference
+    from PIL import Image
+    from functions import data_curation as dc
+    rgba = np.random.default_rng(5).integers(0, 256, (180, 240, 4), dtype=np.uint8)
+    pil = Image.fromarray(rgba, "RGBA")
+    got = dc.resize_and_crop_image(pil)
+    bg = Image.new("RGB", pil.size, (255, 255, 255))
+    bg.paste(pil, mask=pil.split()[3])
+    assert got.size == (224, 224) and got.mode == "RGB"
+    assert np.array_equal(np.asarray(got), pil_resample.wds_transform_u8(np.asarray(bg)))
+
+
+def test_bilinear_images_with_7_to_16_taps_take_the_two_pass_path_bit_exact(ops_mod):
+    """Downscales by 2.5x-7x (7 to 16 taps) used to go through the band kernel; up to 16 taps / 640 source rows they
+    now run on the two-pass path, beyond that still the band kernel -- all bit-exact with the reference transform."""
+    sizes = [(600, 640), (650, 900), (700, 700), (1200, 1210), (1700, 1650), (233, 3000)]
+    imgs = [np.random.default_rng(90 + i).integers(0, 256, (h, w, 3), dtype=np.uint8) for i, (h, w) in enumerate(sizes)]
+    assert torch.equal(_preprocess(ops_mod, imgs, 0).cpu(), _expected_bf16(imgs))
+    assert torch.equal(_preprocess(ops_mod, imgs, 1).cpu()[:, 3:227, 3:227, :3], _expected_bf16(imgs).permute(0, 2, 3, 1))

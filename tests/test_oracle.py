@@ -170,3 +170,23 @@ def test_classifier_ref_matches_reference_golden():
     loss, acc, preds, labs = classifier_ref.evaluate_full(model, batches)
     assert abs(loss - float(g["loss"])) < 1e-4 and acc == float(g["acc"])
     assert np.array_equal(np.asarray(preds), g["preds"]) and np.array_equal(np.asarray(labs), g["labels"])
+
+
+# ------------------------------------------------------------------------------------------------ N2 Lanczos resize
+def _wds_inputs(g):
+    from oracle.make_golden import wds_input
+    return [wds_input(int(s), int(h), int(w), smooth=(i % 2 == 0)) for i, ((h, w), s) in enumerate(zip(g["sizes"], g["seeds"]))]
+
+
+def test_wds_lanczos_resize_matches_reference_golden_and_pillow_in_process():
+    """data_curation.py:883-913 (resize_and_crop_image, LANCZOS) restated in numpy: bit-for-bit against the fixture
+    the reference function produced, and against Pillow run in-process on other sizes."""
+    g = load_golden("wds_resize.npz")
+    for img, want in zip(_wds_inputs(g), g["crops"]):
+        assert np.array_equal(pil_resample.wds_transform_u8(img), want), img.shape
+    from PIL import Image
+    for (h, w), seed in zip([(260, 333), (90, 120), (224, 230), (512, 380)], range(4)):
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        oh, ow = pil_resample.wds_resized_size(h, w)
+        ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.Resampling.LANCZOS))
+        assert np.array_equal(pil_resample.resize_bilinear_u8(img, oh, ow, "lanczos"), ref), (h, w)
