@@ -214,10 +214,12 @@ class TimedBackend:
         self.trunk = inner.trunk
         self.events = []
         self.enabled = False
-        self.cov_accumulate = inner.cov_accumulate
-        self.pca_fit = inner.pca_fit
-        self.pca_transform = inner.pca_transform
-        self.lof = inner.lof
+
+    def __getattr__(self, name):
+        # everything that is not timed here (cov_accumulate, pca_fit, pca_transform, lof, lof_sharded, ...) is the
+        # product backend's own method -- in particular lof_sharded, without which a multi-rank run would fall back
+        # to every rank searching all rows
+        return getattr(self.inner, name)
 
     def embed(self, part, max_taps):
         from irp_b200 import _lib, ops
