@@ -59,54 +59,104 @@ def load_peaks():
 # clocks sampling (nvidia-smi during the timed region)
 # --------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled every 200 ms DURING the timed region.
+
+    Reads NVML in-process (pynvml: the library behind nvidia-smi).  An `nvidia-smi -lms` child process, which this
+    used to be, re-initialises NVML over every GPU of the box and stalled one timed step of a 4-GPU run by
+    100-300 ms about two seconds after its start (reproduced three times; gone with the sampler off); it remains
+    only as the fallback when pynvml is missing.  Only samples taken after `begin()` are reported."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []          # (time, sm_mhz, max_mhz, set of reasons)
         self.proc = None
         self.thread = None
+        self.stop_flag = threading.Event()
+        self.t_begin = 0.0
+        self.source = None
+
+    def begin(self):
+        self.t_begin = time.time()
+
+    # ---- NVML in-process ----
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            p = torch.cuda.get_device_properties(self.index)
+            bus = "%08X:%02X:%02X.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[self.index]) if self.index < len(ids) else self.index
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+
+    def _poll_nvml(self, pynvml, handle):
+        bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        mx = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+                self.rows.append((time.time(), sm, mx, {n for n, b in bits.items() if mask & b}))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    # ---- nvidia-smi fallback ----
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            r = [p.strip() for p in line.split(",")]
+            if len(r) >= 7:
+                try:
+                    reasons = {n for n, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")}
+                    self.rows.append((time.time(), float(r[0]), float(r[1]), reasons))
+                except ValueError:
+                    continue
 
     def start(self):
         try:
+            pynvml, handle = self._nvml_handle()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, args=(pynvml, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.source = "nvidia-smi"
+        self.thread = threading.Thread(target=self._read_smi, daemon=True)
         self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) >= 7:
-                self.rows.append(parts)
-
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"]}
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        rows = [r for r in self.rows if r[0] >= self.t_begin]
+        sm = [r[1] for r in rows]
+        mx = [r[2] for r in rows]
+        reasons = set().union(*[r[3] for r in rows]) if rows else set()
         busy = [s for s in sm if s > 0]
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -293,21 +343,34 @@ def run_ours(args, rank, local_rank, world):
         return res, None
 
     # ---- value: inputs resident in HBM ----
+    import gc
+    if os.environ.get("IRP_BENCH_GC", "1") == "0":
+        gc.collect()
+        gc.disable()
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and os.environ.get("IRP_BENCH_NO_SAMPLER", "0") == "0":
+        sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    backend.enabled = True
+    backend.enabled = os.environ.get("IRP_BENCH_NO_EVENTS", "0") == "0"
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record()
+    step_marks = [e0]
     for _ in range(args.steps):
         res, _ = step()
+        m = torch.cuda.Event(enable_timing=True)
+        m.record()
+        step_marks.append(m)
     e1.record()
     barrier()
     backend.enabled = False
+    per_step_ms = [round(a.elapsed_time(b), 2) for a, b in zip(step_marks[:-1], step_marks[1:])]
+    if getattr(stage, "traces", None):
+        for i, tr in enumerate(stage.traces):
+            print(f"[trace rank {rank}] step {i}: {tr}", file=sys.stderr, flush=True)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -329,8 +392,8 @@ def run_ours(args, rank, local_rank, world):
         rank_embed_ms = [round(float(t.item()), 3) for t in allr]
     n_emb = sum(n for _, n in backend.events)
     calls = len(backend.events)
-    conv_tflops = FLOPS_PER_IMAGE * n_emb / (emb_ms * 1e-3) / 1e12
-    pre_gbs = algorithmic_preprocess_bytes(hw) * args.steps / (pre_ms * 1e-3) / 1e9
+    conv_tflops = FLOPS_PER_IMAGE * n_emb / (max(emb_ms, 1e-9) * 1e-3) / 1e12
+    pre_gbs = algorithmic_preprocess_bytes(hw) * args.steps / (max(pre_ms, 1e-9) * 1e-3) / 1e9
 
     # ---- e2e: pinned host buffers, copies inside the timed region ----
     host = None
@@ -396,7 +459,7 @@ def run_ours(args, rank, local_rank, world):
                                 "per_launch": "3*ceil(224/232*short)^2 source bytes + 301056 output bytes per image"},
         "stage_ms": {"preprocess": pre_ms / args.steps, "trunk": emb_ms / args.steps,
                      "pca_lof_other": ms_step - (pre_ms + emb_ms) / args.steps,
-                     "embed_per_rank": rank_embed_ms},
+                     "embed_per_rank": rank_embed_ms, "per_step": per_step_ms},
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "gpu_launches": launches_per_step(N_IMAGES, BATCH, 2048, packed.max_taps) * args.steps,
     }

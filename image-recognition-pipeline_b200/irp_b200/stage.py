@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -376,14 +377,38 @@ class OutlierStage:
     def run(self, packed: PackedImages, class_ids: torch.Tensor, n_classes: int,
             from_host: bool = False) -> StageResult:
         """`packed` / `class_ids` are THIS rank's shard; returned flags cover all ranks' rows in rank order."""
+        trace = self._trace_begin()
         feats = self.embed_packed(packed, from_host=from_host)
+        self._trace(trace, "embed")
         pca = self.fit_pca(feats)
+        self._trace(trace, "fit_pca")
         z_local = self.transform(feats, pca)
         ids_local = class_ids.to(self.device, non_blocking=True).to(torch.int32)
         z_all = self.gather_rows(z_local)
         ids_all = self.gather_rows(ids_local)
+        self._trace(trace, "transform+gather")
         cf, gf, cs, gs = self.detect(z_all.contiguous(), ids_all.contiguous(), n_classes)
+        self._trace(trace, "detect")
         return StageResult(feats, z_all, pca, cf, gf, cs, gs)
+
+    # ---- optional per-phase wall-clock trace (IRP_STAGE_TRACE=1; synchronises after every phase) ----
+    def _trace_begin(self):
+        if os.environ.get("IRP_STAGE_TRACE", "0") == "0":
+            return None
+        import time
+        torch.cuda.synchronize(self.device)
+        return [("start", time.perf_counter())]
+
+    def _trace(self, trace, label):
+        if trace is None:
+            return
+        import time
+        torch.cuda.synchronize(self.device)
+        trace.append((label, time.perf_counter()))
+        if label == "detect":
+            if not hasattr(self, "traces"):
+                self.traces = []
+            self.traces.append([(b[0], round(1e3 * (b[1] - a[1]), 2)) for a, b in zip(trace[:-1], trace[1:])])
 
 
 def shard_range(n: int, rank: int, world_size: int):
