@@ -340,13 +340,13 @@ def run_ours(args, rank, local_rank, world):
             out = (stage.to_host(res.features, "features"), stage.to_host(res.z[: len(packed)], "z"),
                    stage.to_host(res.class_outliers, "class_flags"), stage.to_host(res.global_outliers, "global_flags"))
             return res, out
+        # Every step ends with the host waiting for its result (the drop-in returns the flags to the caller).  Without
+        # it the host runs a whole step ahead of the GPU; with 4 ranks one of the first timed steps then stalled for
+        # 100-300 ms (ranks enqueue their collectives out of phase) -- with the step closed like this it does not.
+        torch.cuda.current_stream().synchronize()
         return res, None
 
     # ---- value: inputs resident in HBM ----
-    import gc
-    if os.environ.get("IRP_BENCH_GC", "1") == "0":
-        gc.collect()
-        gc.disable()
     sampler = ClockSampler(local_rank)
     if rank == 0 and os.environ.get("IRP_BENCH_NO_SAMPLER", "0") == "0":
         sampler.start()
