@@ -120,3 +120,19 @@ def test_two_rank_gloo_matches_single_rank(tmp_path):
         np.testing.assert_allclose(r["z"], ref.z.numpy(), atol=1e-4)
         assert np.array_equal(r["cls"], ref.class_outliers.numpy())
         assert np.array_equal(r["glob"], ref.global_outliers.numpy())
+
+
+def test_classifier_drop_ins_refuse_to_run_without_the_cuda_path():
+    """No CPU fallback on the widened path either: evaluate_full wants a B200Classifier, and building one needs a
+    CUDA device."""
+    import torch
+    from functions import train as b200_train
+    from irp_b200.classifier import B200Classifier
+    from oracle import classifier_ref
+    model = classifier_ref.build_classifier(3, seed=0)
+    with pytest.raises(TypeError):
+        b200_train.evaluate_full(model, [], torch.nn.CrossEntropyLoss(), disable_progress=True)
+    with pytest.raises(RuntimeError):
+        B200Classifier(model, "cpu")
+    with pytest.raises(ValueError):
+        B200Classifier(torch.nn.Linear(4, 4), "cpu")

@@ -190,3 +190,19 @@ def test_wds_lanczos_resize_matches_reference_golden_and_pillow_in_process():
         oh, ow = pil_resample.wds_resized_size(h, w)
         ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.Resampling.LANCZOS))
         assert np.array_equal(pil_resample.resize_bilinear_u8(img, oh, ow, "lanczos"), ref), (h, w)
+
+
+def test_geometry_of_the_widening_transforms_matches_c_abi_host_helper():
+    """irp_preprocess_geometry_ex for the classifier's val_transform and the Lanczos WebDataset resize against the
+    oracle's restatement of the reference formulas (sizes, crop offsets, tap bounds), and the Python tap helper."""
+    from irp_b200 import _lib
+    from irp_b200.stage import taps_for
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        h, w = int(rng.integers(20, 3000)), int(rng.integers(20, 3000))
+        assert _lib.geometry(h, w, _lib.TRANSFORM_VAL_256) == (256, 256, 16, 16, pil_resample.val_max_taps(h, w))
+        oh, ow = pil_resample.wds_resized_size(h, w)
+        want = (oh, ow, (oh - 224) // 2, (ow - 224) // 2, pil_resample.wds_max_taps(h, w))
+        assert _lib.geometry(h, w, _lib.TRANSFORM_WDS_LANCZOS) == want, (h, w)
+        for t in (_lib.TRANSFORM_WEIGHTS_DEFAULT, _lib.TRANSFORM_VAL_256, _lib.TRANSFORM_WDS_LANCZOS):
+            assert taps_for(h, w, t) == _lib.geometry(h, w, t)[4]
