@@ -285,16 +285,17 @@ class TimedBackend:
         return out
 
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the 49 kernels of ONE irp_resnet50_embed call at batch 256,
-# from the ncu pass committed as profiles/r01_ncu_trunk_traffic_v6.csv (5 823 MB read + 3 645 MB written).
-TRUNK_DRAM_BYTES_PER_CALL = 9.468e9
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the 46 kernels of ONE irp_resnet50_embed call at batch 256,
+# from the ncu pass committed as profiles/r01_ncu_trunk_traffic_v6.csv (5 411 MB read + 3 282 MB written; the pass
+# captured 49 launches across two calls, profiles/r01_trunk_layer_table_v6.md lists the 46 of one call).
+TRUNK_DRAM_BYTES_PER_CALL = 8.694e9
 
 
 def launches_per_step(n_images, batch, dim, max_taps):
     """Kernels of libirp_b200.so launched per step (counted from the launch sites in csrc/*.cu)."""
     batches = (n_images + batch - 1) // batch
     pre = 3 + (1 if max_taps > 6 else 0)  # resample_plan + horizontal pass + vertical pass (+ many-tap path)
-    trunk = 49                   # stem+pool, 16 3x3, 3 downsample, 9 conv1, 9 conv3, 7 chained conv3+conv1 (the first
+    trunk = 46                   # stem+pool, 16 3x3, 3 downsample, 9 conv1, 9 conv3, 7 chained conv3+conv1 (the first
                                  # with the layer1 shortcut conv folded in), avgpool
     per_batch = pre + trunk
     cov = 3                      # split_transpose, add_count, cov_gemm
@@ -446,7 +447,7 @@ def run_ours(args, rank, local_rank, world):
                    "parallelism": f"dp{world}: images sharded, one all-reduce of the PCA partial sums"},
         "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": conv_tflops / peaks["tflops_sustained"], "traffic": TRUNK_DRAM_BYTES_PER_CALL,
-                     "traffic_source": "ncu dram__bytes_read+write over the 49 kernels of one trunk call, "
+                     "traffic_source": "ncu dram__bytes_read+write over the 46 kernels of one trunk call, "
                                        "profiles/r01_ncu_trunk_traffic_v6.csv",
                      "kernel": "conv_gemm2_kernel / conv_chain_kernel / conv3x3_c64_kernel / stem_pool_kernel (the 53 "
                                "convolutions of one irp_resnet50_embed call, batch 256)",

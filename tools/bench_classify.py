@@ -93,7 +93,7 @@ line = {
                  "note": "whole step (preprocess + trunk + head) against the conv FLOPs; same trunk kernels as bench.py"},
     "cpu_baseline": {"value": sample / cpu_s, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                      "sample": f"{sample} images: PIL val_transform + torchvision ResNet-50 fp32 + head, batch 32"},
-    "gpu_launches": n_batches * (3 + 49 + 2 + 1),
+    "gpu_launches": n_batches * (3 + 46 + 2 + 1),
     "clocks": clocks if sampler else None,
 }
 print(json.dumps(line))
