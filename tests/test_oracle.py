@@ -206,3 +206,25 @@ def test_geometry_of_the_widening_transforms_matches_c_abi_host_helper():
         assert _lib.geometry(h, w, _lib.TRANSFORM_WDS_LANCZOS) == want, (h, w)
         for t in (_lib.TRANSFORM_WEIGHTS_DEFAULT, _lib.TRANSFORM_VAL_256, _lib.TRANSFORM_WDS_LANCZOS):
             assert taps_for(h, w, t) == _lib.geometry(h, w, t)[4]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_resample_restatements_against_pillow_on_random_sizes(seed):
+    """Random sizes (incl. extreme aspect ratios, tiny sides, > 3x downscales): the three transforms' numpy
+    restatements are bit-for-bit what Pillow / torchvision produce in-process."""
+    from PIL import Image
+    from torchvision import transforms
+    from torchvision.models import ResNet50_Weights
+    rng = np.random.default_rng(1000 + seed)
+    h, w = int(rng.integers(8, 900)), int(rng.integers(8, 900))
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    pil = Image.fromarray(img)
+    assert np.array_equal(pil_resample.transform(img), ResNet50_Weights.DEFAULT.transforms()(pil).numpy()), (h, w)
+    val = transforms.Compose([transforms.Resize((256, 256)), transforms.CenterCrop(224), transforms.ToTensor(),
+                              transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    assert np.array_equal(pil_resample.val_transform(img), val(pil).numpy()), (h, w)
+    oh, ow = pil_resample.wds_resized_size(h, w)
+    r = pil.resize((ow, oh), Image.Resampling.LANCZOS)
+    left, top = (ow - 224) // 2, (oh - 224) // 2
+    ref = np.asarray(r.crop((left, top, left + 224, top + 224)))
+    assert np.array_equal(pil_resample.wds_transform_u8(img), ref), (h, w)
