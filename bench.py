@@ -31,6 +31,29 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+def _is_reference_arm(argv) -> bool:
+    for i, a in enumerate(argv):
+        if a == "--impl" and i + 1 < len(argv) and argv[i + 1] == "reference":
+            return True
+        if a == "--impl=reference":
+            return True
+    return False
+
+
+if _is_reference_arm(sys.argv):
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU arm must use all the host cores whatever
+    # launched it, so the thread pools are sized BEFORE torch / numpy / sklearn are imported.
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_v] = str(host_cores())
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 

@@ -1,6 +1,8 @@
 // Library-wide plumbing: last-error string, device check, tensor-map encoder lookup.
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "common.h"
 
@@ -63,14 +65,34 @@ int encode_bf16_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims
   return IRP_OK;
 }
 
+constexpr int kMaxDevices = 64;
+
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static int n[kMaxDevices] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
+}
+
+int ensure_smem(const void* func, size_t bytes) {
+  // kernel attributes are per device: remember the limit already granted per (device, kernel)
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> granted;
+  if (bytes <= 48 * 1024) return IRP_OK;
+  int dev = 0;
+  IRP_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& g = granted[std::make_pair(dev, func)];
+  if (bytes > g) {
+    IRP_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    g = bytes;
+  }
+  return IRP_OK;
 }
 
 }  // namespace irp
@@ -82,7 +104,7 @@ int irp_abi_version(void) { return IRP_B200_ABI_VERSION; }
 const char* irp_last_error(void) { return irp::g_last_error; }
 
 int irp_init(int device) {
-  IRP_CUDA_OK(cudaSetDevice(device));
+  // validates `device` without changing the caller's current device
   int major = 0, minor = 0;
   IRP_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
   IRP_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));

@@ -48,7 +48,16 @@ EncodeTiledFn get_encode_tiled();
 int encode_bf16_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, int swizzle_bytes);
 
+// SM count of the CURRENT device (cached per device).
 int num_sms();
+
+// Opt the kernel `func` in to `bytes` of dynamic shared memory on the CURRENT device (no-op up to 48 KB; cached per
+// (device, kernel), so a second GPU in the same process gets its own opt-in).
+int ensure_smem(const void* func, size_t bytes);
+template <typename K>
+inline int ensure_smem(K* kernel, size_t bytes) {
+  return ensure_smem(reinterpret_cast<const void*>(kernel), bytes);
+}
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

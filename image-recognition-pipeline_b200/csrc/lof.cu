@@ -1217,35 +1217,21 @@ int irp_lof_knn_part(const float* d_z, int64_t n_rows, int dim, const int32_t* d
     if (exhaustive) {
       const size_t smem = (2 * static_cast<size_t>(dpad) * kKnnTile + kKnnTile * (kKnnTile + 1) +
                            static_cast<size_t>(kKnnTile) * k) * 8 + static_cast<size_t>(kKnnTile) * k * 4;
-      static size_t cfg = 0;
-      if (smem > cfg) {
-        IRP_CUDA_OK(cudaFuncSetAttribute(knn_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-        cfg = smem;
-      }
+      IRP_TRY(ensure_smem(knn_resident_kernel, smem));
       knn_resident_kernel<<<knn_grid, kKnnThreads, smem, st>>>(w.zs, w.sr.gstart, n_groups, dpad, k, w.sq, part,
                                                                n_parts, w.knn_d, w.knn_i, d_kdist);
     } else {
       const size_t lists = static_cast<size_t>(kKnnTile) * k * 12 + 8;
       const size_t smem = lists + (static_cast<size_t>(dpad) * (kKnnTile + kFltCand) + kFltCand + kKnnTile) * 4 +
                           8 * kFltCap * 2 + 64 + kKnnTile * 16 + 64;
-      static size_t cfg = 0;
-      if (smem > cfg) {
-        IRP_CUDA_OK(cudaFuncSetAttribute(knn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-        cfg = smem;
-      }
+      IRP_TRY(ensure_smem(knn_filter_kernel, smem));
       knn_filter_kernel<<<knn_grid, kKnnThreads, smem, st>>>(w.zs, zs32, w.sr.gstart, n_groups, dpad, k, w.sq, max_sq,
                                                              part, n_parts, w.knn_d, w.knn_i, d_kdist);
     }
   } else {
     const size_t smem = (2 * kKnnDChunk * kKnnTile + kKnnTile * (kKnnTile + 1) + static_cast<size_t>(kKnnTile) * k) * 8 +
                         static_cast<size_t>(kKnnTile) * k * 4;
-    static size_t cfg = 0;
-    if (smem > cfg) {
-      IRP_CUDA_OK(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      cfg = smem;
-    }
+    IRP_TRY(ensure_smem(knn_kernel, smem));
     knn_kernel<<<knn_grid, kKnnThreads, smem, st>>>(d_z, w.sr.order, w.sr.gstart, n_groups, dim, k, w.sq, part, n_parts,
                                                     w.knn_d, w.knn_i, d_kdist);
   }

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
                                                               __nv_bfloat16* __restrict__ at,
                                                               __nv_bfloat16* __restrict__ bt,
                                                               __nv_bfloat16* __restrict__ ct,
-                                                              double* __restrict__ col_sum) {
+                                                              double* __restrict__ col_part) {
   __shared__ float tile[kSplitTile][kSplitTile + 1];
   const long long r0 = static_cast<long long>(blockIdx.x) * kSplitTile;
   const int c0 = blockIdx.y * kSplitTile;
@@ -42,12 +42,12 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
     tile[i][tx] = v;
   }
   __syncthreads();
-  // column sums of this tile in fp64 (independent of how the rows are split into tiles / shards)
+  // column sums of this row tile in fp64, rows in order; col_sum_reduce_kernel adds the tiles in order
   if (ty == 0) {
     double s = 0.0;
 #pragma unroll 8
     for (int i = 0; i < kSplitTile; ++i) s += static_cast<double>(tile[i][tx]);
-    atomicAdd(&col_sum[c0 + tx], s);
+    col_part[static_cast<size_t>(blockIdx.x) * dim + c0 + tx] = s;
   }
   // transposed write: thread tx walks samples (contiguous in the output), ty strides features
   for (int j = ty; j < kSplitTile; j += 4) {
@@ -64,9 +64,34 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
   }
 }
 
+// col_sum[c] += sum over row tiles of col_part[tile][c].  Block = 32 columns x 8 tile lanes: lane g adds tiles
+// g, g+8, ... in ascending order, the 8 lane sums are then added in lane order by one thread per column -- the
+// order of every addition is fixed by construction, so the result does not depend on the block schedule.
+__global__ void __launch_bounds__(256) col_sum_reduce_kernel(const double* __restrict__ col_part, int n_tiles, int dim,
+                                                             double* __restrict__ col_sum) {
+  __shared__ double part[8][33];
+  const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double s = 0.0;
+  if (c < dim) {
+#pragma unroll 4
+    for (int t = g; t < n_tiles; t += 8) s += col_part[static_cast<size_t>(t) * dim + c];
+  }
+  part[g][cx] = s;
+  __syncthreads();
+  if (g == 0 && c < dim) {
+    double tot = col_sum[c];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += part[i][cx];
+    col_sum[c] = tot;
+  }
+}
+
 // ============================================================================================================
 // 2. scatter GEMM on tcgen05:  S[i,j] += sum_k (a_i a_j + a_i b_j + b_i a_j + b_i b_j + a_i c_j + c_i a_j)[k]
-//    over one K chunk per work unit; upper-triangular 128x128 tiles only; fp64 atomics into S.
+//    upper-triangular 128x128 tiles only.  A CTA owns whole tiles and walks their K chunks in ascending order
+//    (fp32 TMEM accumulation per chunk, fp64 read-modify-write of S per chunk by the same thread), so every
+//    element of S sees its additions in one fixed order: no atomics, results independent of the block schedule.
 // ============================================================================================================
 constexpr int kCovBN = 128, kCovBK = 64, kCovStages = 6, kCovThreads = 192;
 constexpr int kCovABytes = 128 * kCovBK * 2, kCovBBytes = kCovBN * kCovBK * 2;
@@ -80,7 +105,6 @@ struct alignas(64) CovParams {
   int k_blocks_total; // n_pad / 64
   int k_blocks_per_chunk;
   int n_chunks;
-  int num_units;      // n_tri * n_chunks
   int dim;
   double* scatter;    // [dim][dim] fp64, upper-triangular tiles accumulate here
 };
@@ -143,10 +167,10 @@ __global__ void __launch_bounds__(kCovThreads, 1) cov_gemm_kernel(const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-        const int chunk = u % p.n_chunks;
+      for (int t = blockIdx.x; t < p.n_tri; t += gridDim.x)
+      for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
         int ti, tj;
-        tri_decode(u / p.n_chunks, p.tiles_1d, &ti, &tj);
+        tri_decode(t, p.tiles_1d, &ti, &tj);
         const int kb0 = chunk * p.k_blocks_per_chunk;
         const int kb1 = min(p.k_blocks_total, kb0 + p.k_blocks_per_chunk);
         for (int pass = 0; pass < kCovPasses; ++pass) {
@@ -170,8 +194,8 @@ __global__ void __launch_bounds__(kCovThreads, 1) cov_gemm_kernel(const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-        const int chunk = u % p.n_chunks;
+      for (int t = blockIdx.x; t < p.n_tri; t += gridDim.x)
+      for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
         const int kb0 = chunk * p.k_blocks_per_chunk;
         const int kb1 = min(p.k_blocks_total, kb0 + p.k_blocks_per_chunk);
         const int per_pass = kb1 - kb0;
@@ -208,9 +232,10 @@ __global__ void __launch_bounds__(kCovThreads, 1) cov_gemm_kernel(const __grid_c
     const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+    for (int t = blockIdx.x; t < p.n_tri; t += gridDim.x)
+    for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
       int ti, tj;
-      tri_decode(u / p.n_chunks, p.tiles_1d, &ti, &tj);
+      tri_decode(t, p.tiles_1d, &ti, &tj);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 2 * kCovBN + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -224,8 +249,7 @@ __global__ void __launch_bounds__(kCovThreads, 1) cov_gemm_kernel(const __grid_c
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          atomicAdd(dst + c + i,
-                    static_cast<double>(__uint_as_float(v[i])) + static_cast<double>(__uint_as_float(s[i])));
+          dst[c + i] += static_cast<double>(__uint_as_float(v[i])) + static_cast<double>(__uint_as_float(s[i]));
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
@@ -247,7 +271,7 @@ __global__ void __launch_bounds__(kCovThreads, 1) cov_gemm_kernel(const __grid_c
 // ============================================================================================================
 __global__ void assemble_cov_kernel(const double* __restrict__ count, const double* __restrict__ sum,
                                     const double* __restrict__ scatter, const float* __restrict__ shift, int dim,
-                                    double* __restrict__ mean, double* __restrict__ cov, double* __restrict__ trace) {
+                                    double* __restrict__ mean, double* __restrict__ cov) {
   const double n = count[0];
   const long long total = static_cast<long long>(dim) * dim;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -259,11 +283,24 @@ __global__ void assemble_cov_kernel(const double* __restrict__ count, const doub
     const double di = sum[i] / n, dj = sum[j] / n;
     const double c = (s - n * di * dj) / (n - 1.0);
     cov[idx] = c;
-    if (i == j) {
-      mean[i] = static_cast<double>(shift[i]) + di;
-      atomicAdd(trace, c);
-    }
+    if (i == j) mean[i] = static_cast<double>(shift[i]) + di;
   }
+}
+
+// trace of the covariance: one block, each thread sums its strided share of the diagonal in ascending order and
+// the block combines the 1024 partials in a fixed tree, so the total variance is bitwise repeatable.
+__global__ void __launch_bounds__(1024) trace_kernel(const double* __restrict__ cov, int dim,
+                                                     double* __restrict__ trace) {
+  __shared__ double part[1024];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < dim; i += 1024) s += cov[static_cast<size_t>(i) * dim + i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) trace[0] = part[0];
 }
 
 // ============================================================================================================
@@ -1044,7 +1081,8 @@ extern "C" {
 size_t irp_cov_workspace_bytes(int64_t n_rows, int dim) {
   if (n_rows <= 0 || dim <= 0) return 0;
   const size_t n_pad = align_up(static_cast<size_t>(n_rows), 64);
-  return 3 * align_up(static_cast<size_t>(dim) * n_pad * sizeof(__nv_bfloat16), 1024) + 1024;
+  return 3 * align_up(static_cast<size_t>(dim) * n_pad * sizeof(__nv_bfloat16), 1024) +
+         align_up(n_pad / kSplitTile * static_cast<size_t>(dim) * sizeof(double), 1024) + 1024;
 }
 
 int irp_cov_accumulate(const float* d_x, int64_t n_rows, int dim, const float* d_shift, double* d_count,
@@ -1060,9 +1098,12 @@ int irp_cov_accumulate(const float* d_x, int64_t n_rows, int dim, const float* d
   __nv_bfloat16* at = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(ws + arr);
   __nv_bfloat16* ct = reinterpret_cast<__nv_bfloat16*>(ws + 2 * arr);
+  double* col_part = reinterpret_cast<double*>(ws + 3 * arr);
   dim3 grid(static_cast<unsigned>(n_pad / kSplitTile), dim / kSplitTile);
   split_transpose_kernel<<<grid, 256, 0, st>>>(d_x, n_rows, dim, d_shift, static_cast<long long>(n_pad), at, bt, ct,
-                                               d_sum);
+                                               col_part);
+  IRP_CUDA_OK(cudaGetLastError());
+  col_sum_reduce_kernel<<<ceil_div(dim, 32), 256, 0, st>>>(col_part, static_cast<int>(n_pad / kSplitTile), dim, d_sum);
   IRP_CUDA_OK(cudaGetLastError());
   add_count_kernel<<<1, 1, 0, st>>>(d_count, static_cast<double>(n_rows));
   IRP_CUDA_OK(cudaGetLastError());
@@ -1082,15 +1123,10 @@ int irp_cov_accumulate(const float* d_x, int64_t n_rows, int dim, const float* d
   p.k_blocks_per_chunk = 8;
   if (const char* e = getenv("IRP_COV_CHUNK")) p.k_blocks_per_chunk = atoi(e) > 0 ? atoi(e) : 8;
   p.n_chunks = ceil_div(p.k_blocks_total, p.k_blocks_per_chunk);
-  p.num_units = p.n_tri * p.n_chunks;
   p.dim = dim;
   p.scatter = d_scatter;
-  static bool configured = false;
-  if (!configured) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(cov_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCovSmem));
-    configured = true;
-  }
-  const int grid_g = p.num_units < num_sms() ? p.num_units : num_sms();
+  IRP_TRY(ensure_smem(cov_gemm_kernel, kCovSmem));
+  const int grid_g = p.n_tri < num_sms() ? p.n_tri : num_sms();
   cov_gemm_kernel<<<grid_g, kCovThreads, kCovSmem, st>>>(p);
   IRP_CUDA_OK(cudaGetLastError());
   return IRP_OK;
@@ -1144,14 +1180,8 @@ static int lanczos_topk(const double* A, int n, int k, double* Q, double* diag, 
   int m = 0;
   IRP_CUDA_OK(launch_pdl(lz_start_kernel, dim3(1), dim3(1024), 0, st, w2, n));
   const size_t vec_smem = static_cast<size_t>(n) * sizeof(double);
-  static size_t bis_cfg = 0, ii_cfg = 0, ritz_cfg = 0, vec_cfg = 0;
-  if (vec_smem > 32 * 1024 && vec_smem > vec_cfg) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(lz_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(vec_smem)));
-    IRP_CUDA_OK(cudaFuncSetAttribute(lz_close_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(vec_smem)));
-    vec_cfg = vec_smem;
-  }
+  IRP_TRY(ensure_smem(lz_matvec_kernel, vec_smem));
+  IRP_TRY(ensure_smem(lz_close_kernel, vec_smem));
   const dim3 axpy_grid(ceil_div(n, 32));
   int checks = 0;
   for (;;) {
@@ -1167,18 +1197,10 @@ static int lanczos_topk(const double* A, int n, int k, double* Q, double* diag, 
     IRP_CUDA_OK(cudaGetLastError());
     m = m_target;
     const size_t bis_smem = 2 * static_cast<size_t>(m) * sizeof(double);
-    if (bis_smem > 32 * 1024 && bis_smem > bis_cfg) {
-      IRP_CUDA_OK(cudaFuncSetAttribute(bisect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(bis_smem)));
-      bis_cfg = bis_smem;
-    }
+    IRP_TRY(ensure_smem(bisect_topk_kernel, bis_smem));
     bisect_topk_kernel<<<k, kBisThreads, bis_smem, st>>>(diag, off, m, k, d_eigenvalues, tnorm);
     const size_t ii_smem = 6 * static_cast<size_t>(m) * sizeof(double) + static_cast<size_t>(m) + 16;
-    if (ii_smem > 32 * 1024 && ii_smem > ii_cfg) {
-      IRP_CUDA_OK(cudaFuncSetAttribute(inverse_iteration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(ii_smem)));
-      ii_cfg = ii_smem;
-    }
+    IRP_TRY(ensure_smem(inverse_iteration_kernel, ii_smem));
     inverse_iteration_kernel<<<k, 32, ii_smem, st>>>(diag, off, m, k, d_eigenvalues, tnorm, Z);
     cluster_mgs_kernel<<<1, 256, 0, st>>>(Z, m, k, d_eigenvalues, tnorm);
     lz_residual_kernel<<<1, 256, 0, st>>>(Z, off, m, k, tnorm, out);
@@ -1194,11 +1216,7 @@ static int lanczos_topk(const double* A, int n, int k, double* Q, double* diag, 
     if (!(host[1] > 1e-10 * tn) || !(host[0] == host[0])) return IRP_OK;  // breakdown (invariant subspace) or NaN
     if (host[0] <= 1e-12 * tn) {
       const size_t ritz_smem = static_cast<size_t>(m) * sizeof(double);
-      if (ritz_smem > 32 * 1024 && ritz_smem > ritz_cfg) {
-        IRP_CUDA_OK(cudaFuncSetAttribute(lz_ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(ritz_smem)));
-        ritz_cfg = ritz_smem;
-      }
+      IRP_TRY(ensure_smem(lz_ritz_kernel, ritz_smem));
       lz_ritz_kernel<<<dim3(k, ceil_div(n, 256)), 256, ritz_smem, st>>>(Q, Z, n, m, d_components);
       lz_sign_kernel<<<k, 256, 0, st>>>(d_components, n);
       IRP_CUDA_OK(cudaGetLastError());
@@ -1246,7 +1264,9 @@ int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scat
   double* Z = work + static_cast<size_t>(k) * 5 * n;
 
   IRP_CUDA_OK(cudaMemsetAsync(tau, 0, 8 * static_cast<size_t>(n) * sizeof(double), st));
-  assemble_cov_kernel<<<num_sms() * 4, 256, 0, st>>>(d_count, d_sum, d_scatter, d_shift, n, d_mean, A, scal);
+  assemble_cov_kernel<<<num_sms() * 4, 256, 0, st>>>(d_count, d_sum, d_scatter, d_shift, n, d_mean, A);
+  IRP_CUDA_OK(cudaGetLastError());
+  trace_kernel<<<1, 1024, 0, st>>>(A, n, scal);
   IRP_CUDA_OK(cudaGetLastError());
 
   bool done = false;
@@ -1255,12 +1275,7 @@ int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scat
   if (!done) {
   // ---- tridiagonalisation: launches j = -1 .. n-3 ----
   const size_t tri_smem = 3 * static_cast<size_t>(n) * sizeof(double);
-  static size_t tri_cfg = 0;
-  if (tri_smem > 32 * 1024 && tri_smem > tri_cfg) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(tridiag_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(tri_smem)));
-    tri_cfg = tri_smem;
-  }
+  IRP_TRY(ensure_smem(tridiag_step_kernel, tri_smem));
   const int rows_per_cta = kTriThreads / 32;
   for (int j = -1; j <= n - 3; ++j) {
     const int rows = n - (j + 2);
@@ -1277,22 +1292,12 @@ int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scat
 
   // ---- eigenvalues (top-k) ----
   const size_t bis_smem = 2 * static_cast<size_t>(n) * sizeof(double);
-  static size_t bis_cfg = 0;
-  if (bis_smem > 32 * 1024 && bis_smem > bis_cfg) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(bisect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(bis_smem)));
-    bis_cfg = bis_smem;
-  }
+  IRP_TRY(ensure_smem(bisect_topk_kernel, bis_smem));
   bisect_topk_kernel<<<k, kBisThreads, bis_smem, st>>>(diag, off, n, k, d_eigenvalues, scal + 1);
   IRP_CUDA_OK(cudaGetLastError());
   // ---- eigenvectors of T ----
   const size_t ii_smem = 6 * static_cast<size_t>(n) * sizeof(double) + static_cast<size_t>(n) + 16;
-  static size_t ii_cfg = 0;
-  if (ii_smem > 32 * 1024 && ii_smem > ii_cfg) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(inverse_iteration_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(ii_smem)));
-    ii_cfg = ii_smem;
-  }
+  IRP_TRY(ensure_smem(inverse_iteration_kernel, ii_smem));
   (void)work;
   inverse_iteration_kernel<<<k, 32, ii_smem, st>>>(diag, off, n, k, d_eigenvalues, scal + 1, Z);
   IRP_CUDA_OK(cudaGetLastError());
@@ -1316,11 +1321,7 @@ int irp_pca_transform(const float* d_x, int64_t n_rows, int dim, const double* d
               "pca_transform: n_rows %lld dim %d k %d unsupported (k <= 128, dim %% 64 == 0)",
               static_cast<long long>(n_rows), dim, k);
   const size_t smem = (static_cast<size_t>(kProjRows) + k) * (kProjChunk + 1) * sizeof(double);
-  static size_t cfg = 0;
-  if (smem > 32 * 1024 && smem > cfg) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    cfg = smem;
-  }
+  IRP_TRY(ensure_smem(project_kernel, smem));
   const unsigned grid = static_cast<unsigned>(ceil_div64(n_rows, kProjRows));
   project_kernel<<<grid, kProjThreads, smem, static_cast<cudaStream_t>(stream)>>>(d_x, n_rows, dim, d_mean,
                                                                                   d_components, k, d_z);

@@ -18,8 +18,9 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(t: torch.Tensor) -> C.c_void_p:
+    """The current torch stream OF THE TENSOR'S DEVICE (not of the process-wide current device)."""
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
 def _lib_for(t: torch.Tensor):
@@ -28,10 +29,28 @@ def _lib_for(t: torch.Tensor):
     return _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
 
 
+def _on_device_of(arg: int = 0):
+    """Run the op with the device of its `arg`-th tensor argument current: the library launches on, and sets kernel
+    attributes for, the CUDA runtime's current device, which need not be the tensors' device in a multi-GPU process."""
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapped(*a, **kw):
+            t = a[arg]
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                with torch.cuda.device(t.device):
+                    return fn(*a, **kw)
+            return fn(*a, **kw)
+        return wrapped
+    return deco
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # A1 preprocess
 # ---------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("irp_b200::preprocess", mutates_args=())
+@_on_device_of(0)
 def preprocess(pixels: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor, max_taps: int,
                layout: int) -> torch.Tensor:
     """Ragged uint8 HWC batch -> bf16 [n,3,224,224] (layout 0) or padded NHWC4 [n,230,230,4] (layout 1)."""
@@ -43,7 +62,7 @@ def preprocess(pixels: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor, ma
     ws_bytes = lib.irp_preprocess_workspace_bytes(n, max_taps)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pixels.device)
     _lib.check(lib.irp_preprocess(_ptr(pixels), _ptr(offsets), _ptr(hw), n, max_taps, _ptr(ws), ws_bytes, _ptr(out),
-                                  layout, _stream()), "irp_preprocess")
+                                  layout, _stream(pixels)), "irp_preprocess")
     return out
 
 
@@ -63,6 +82,7 @@ def _preprocess_out(n: int, layout: int):
 
 
 @torch.library.custom_op("irp_b200::preprocess_ex", mutates_args=())
+@_on_device_of(0)
 def preprocess_ex(pixels: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor, max_taps: int, layout: int,
                   transform: int) -> torch.Tensor:
     """`preprocess` with the resize geometry / filter selected by `transform` (_lib.TRANSFORM_*): 1 = the
@@ -76,7 +96,7 @@ def preprocess_ex(pixels: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor,
     ws_bytes = lib.irp_preprocess_workspace_bytes(n, max_taps)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pixels.device)
     _lib.check(lib.irp_preprocess_ex(_ptr(pixels), _ptr(offsets), _ptr(hw), n, max_taps, _ptr(ws), ws_bytes,
-                                     _ptr(out), layout, transform, _stream()), "irp_preprocess_ex")
+                                     _ptr(out), layout, transform, _stream(pixels)), "irp_preprocess_ex")
     return out
 
 
@@ -90,13 +110,14 @@ def _(pixels, offsets, hw, max_taps, layout, transform):
 # A2 ResNet-50 trunk (handle passed as an integer address)
 # ---------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("irp_b200::resnet50_embed", mutates_args=())
+@_on_device_of(1)
 def resnet50_embed(handle: int, x_nhwc4p: torch.Tensor) -> torch.Tensor:
     """bf16 [B,230,230,4] -> fp32 [B,2048] pooled embeddings."""
     lib = _lib_for(x_nhwc4p)
     assert x_nhwc4p.dtype == torch.bfloat16 and x_nhwc4p.is_contiguous()
     b = x_nhwc4p.shape[0]
     out = torch.empty((b, _lib.EMBED_DIM), dtype=torch.float32, device=x_nhwc4p.device)
-    _lib.check(lib.irp_resnet50_embed(C.c_void_p(handle), _ptr(x_nhwc4p), b, _ptr(out), _stream()),
+    _lib.check(lib.irp_resnet50_embed(C.c_void_p(handle), _ptr(x_nhwc4p), b, _ptr(out), _stream(x_nhwc4p)),
                "irp_resnet50_embed")
     return out
 
@@ -110,6 +131,7 @@ def _(handle, x_nhwc4p):
 # A3 PCA
 # ---------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("irp_b200::cov_accumulate", mutates_args=("count", "total", "scatter"))
+@_on_device_of(0)
 def cov_accumulate(x: torch.Tensor, shift: torch.Tensor, count: torch.Tensor, total: torch.Tensor,
                    scatter: torch.Tensor) -> None:
     """count += n; total += sum(x - shift); scatter += (x - shift)^T (x - shift)  (fp64 accumulators)."""
@@ -120,10 +142,11 @@ def cov_accumulate(x: torch.Tensor, shift: torch.Tensor, count: torch.Tensor, to
     ws_bytes = lib.irp_cov_workspace_bytes(n, d)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     _lib.check(lib.irp_cov_accumulate(_ptr(x), n, d, _ptr(shift), _ptr(count), _ptr(total), _ptr(scatter), _ptr(ws),
-                                      ws_bytes, _stream()), "irp_cov_accumulate")
+                                      ws_bytes, _stream(x)), "irp_cov_accumulate")
 
 
 @torch.library.custom_op("irp_b200::pca_fit", mutates_args=())
+@_on_device_of(0)
 def pca_fit(count: torch.Tensor, total: torch.Tensor, scatter: torch.Tensor, shift: torch.Tensor,
             k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """-> (mean fp64[d], components fp64[k,d], eigenvalues fp64[k+1] = top-k then total variance)."""
@@ -135,7 +158,7 @@ def pca_fit(count: torch.Tensor, total: torch.Tensor, scatter: torch.Tensor, shi
     ws_bytes = lib.irp_pca_fit_workspace_bytes(d, k)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=scatter.device)
     _lib.check(lib.irp_pca_fit(_ptr(count), _ptr(total), _ptr(scatter), _ptr(shift), d, k, _ptr(mean), _ptr(comps),
-                               _ptr(evals), _ptr(ws), ws_bytes, _stream()), "irp_pca_fit")
+                               _ptr(evals), _ptr(ws), ws_bytes, _stream(count)), "irp_pca_fit")
     return mean, comps, evals
 
 
@@ -146,6 +169,7 @@ def _(count, total, scatter, shift, k):
 
 
 @torch.library.custom_op("irp_b200::pca_transform", mutates_args=())
+@_on_device_of(0)
 def pca_transform(x: torch.Tensor, mean: torch.Tensor, components: torch.Tensor) -> torch.Tensor:
     """(x - mean) @ components^T with fp64 accumulation -> fp32 [n,k]."""
     lib = _lib_for(x)
@@ -153,7 +177,7 @@ def pca_transform(x: torch.Tensor, mean: torch.Tensor, components: torch.Tensor)
     n, d = x.shape
     k = components.shape[0]
     z = torch.empty((n, k), dtype=torch.float32, device=x.device)
-    _lib.check(lib.irp_pca_transform(_ptr(x), n, d, _ptr(mean), _ptr(components), k, _ptr(z), _stream()),
+    _lib.check(lib.irp_pca_transform(_ptr(x), n, d, _ptr(mean), _ptr(components), k, _ptr(z), _stream(x)),
                "irp_pca_transform")
     return z
 
@@ -167,6 +191,7 @@ def _(x, mean, components):
 # A4 scoring
 # ---------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("irp_b200::lof", mutates_args=())
+@_on_device_of(0)
 def lof(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: int, n_neighbors: int,
         contamination: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """-> (negative_outlier_factor fp64[n], offset fp64[n_groups], flags uint8[n])."""
@@ -179,7 +204,7 @@ def lof(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: int, n_neighbo
     ws_bytes = lib.irp_lof_workspace_bytes(n, d, n_neighbors)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
     _lib.check(lib.irp_lof(_ptr(z), n, d, _ptr(group), n_groups, n_neighbors, C.c_double(contamination), _ptr(scores),
-                           _ptr(offsets), _ptr(flags), _ptr(ws), ws_bytes, _stream()), "irp_lof")
+                           _ptr(offsets), _ptr(flags), _ptr(ws), ws_bytes, _stream(z)), "irp_lof")
     return scores, offsets, flags
 
 
@@ -190,6 +215,7 @@ def _(z, group, n_groups, n_neighbors, contamination):
             z.new_empty(n, dtype=torch.uint8))
 
 
+@_on_device_of(0)
 def lof_sharded(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: int, n_neighbors: int,
                 contamination: float, part: int, n_parts: int, all_reduce) -> Tuple[torch.Tensor, torch.Tensor,
                                                                                    torch.Tensor]:
@@ -205,22 +231,23 @@ def lof_sharded(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: int, n
     vec = lambda: torch.empty(n, dtype=torch.float64, device=z.device)
     kdist, lrd, score = vec(), vec(), vec()
     _lib.check(lib.irp_lof_knn_part(_ptr(z), n, d, _ptr(group), n_groups, k, part, n_parts, _ptr(kdist), _ptr(ws),
-                                    ws_bytes, _stream()), "irp_lof_knn_part")
+                                    ws_bytes, _stream(z)), "irp_lof_knn_part")
     all_reduce(kdist)
     _lib.check(lib.irp_lof_lrd_part(n, n_groups, k, part, n_parts, _ptr(kdist), _ptr(lrd), _ptr(ws), ws_bytes,
-                                    _stream()), "irp_lof_lrd_part")
+                                    _stream(z)), "irp_lof_lrd_part")
     all_reduce(lrd)
     _lib.check(lib.irp_lof_score_part(n, n_groups, k, part, n_parts, _ptr(lrd), _ptr(score), _ptr(ws), ws_bytes,
-                                      _stream()), "irp_lof_score_part")
+                                      _stream(z)), "irp_lof_score_part")
     all_reduce(score)
     scores, offsets, flags = vec(), torch.empty(n_groups, dtype=torch.float64, device=z.device), \
         torch.empty(n, dtype=torch.uint8, device=z.device)
     _lib.check(lib.irp_lof_finish(n, n_groups, k, C.c_double(contamination), _ptr(score), _ptr(scores), _ptr(offsets),
-                                  _ptr(flags), _ptr(ws), ws_bytes, _stream()), "irp_lof_finish")
+                                  _ptr(flags), _ptr(ws), ws_bytes, _stream(z)), "irp_lof_finish")
     return scores, offsets, flags
 
 
 @torch.library.custom_op("irp_b200::centroid_zscore", mutates_args=())
+@_on_device_of(0)
 def centroid_zscore(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: int,
                     contamination: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """-> (distance fp64[n], zscore fp64[n], threshold fp64[n_groups], flags uint8[n])."""
@@ -234,7 +261,7 @@ def centroid_zscore(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: in
     ws_bytes = lib.irp_centroid_workspace_bytes(n, d, n_groups)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
     _lib.check(lib.irp_centroid_zscore(_ptr(z), n, d, _ptr(group), n_groups, C.c_double(contamination), _ptr(dist),
-                                       _ptr(zs), _ptr(thr), _ptr(flags), _ptr(ws), ws_bytes, _stream()),
+                                       _ptr(zs), _ptr(thr), _ptr(flags), _ptr(ws), ws_bytes, _stream(z)),
                "irp_centroid_zscore")
     return dist, zs, thr, flags
 
@@ -250,6 +277,7 @@ def _(z, group, n_groups, contamination):
 # N1 classifier head (functions/model.py:29-40) and the evaluate_full statistics (functions/train.py:208-216)
 # ---------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("irp_b200::classifier_head", mutates_args=())
+@_on_device_of(0)
 def classifier_head(features: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
                     b2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """fp32 [B,in] features -> (logits fp32 [B,C], argmax int32 [B]) through Linear-ReLU-Linear (eval mode)."""
@@ -264,7 +292,7 @@ def classifier_head(features: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, 
     ws_bytes = lib.irp_classifier_head_workspace_bytes(b, hidden)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=features.device)
     _lib.check(lib.irp_classifier_head(_ptr(features), b, in_dim, _ptr(w1), _ptr(b1), hidden, _ptr(w2), _ptr(b2), c,
-                                       _ptr(logits), _ptr(pred), _ptr(ws), ws_bytes, _stream()),
+                                       _ptr(logits), _ptr(pred), _ptr(ws), ws_bytes, _stream(features)),
                "irp_classifier_head")
     return logits, pred
 
@@ -275,6 +303,7 @@ def _(features, w1, b1, w2, b2):
     return features.new_empty((b, c)), features.new_empty((b,), dtype=torch.int32)
 
 
+@_on_device_of(0)
 def cross_entropy_stats(logits: torch.Tensor, labels: torch.Tensor,
                         class_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp64 [3] on the device: sum of weighted per-row cross-entropies, sum of weights, number of correct rows."""
@@ -285,5 +314,5 @@ def cross_entropy_stats(logits: torch.Tensor, labels: torch.Tensor,
     if class_weights is not None:
         w = class_weights.to(device=logits.device, dtype=torch.float32).contiguous()
     _lib.check(lib.irp_cross_entropy_stats(_ptr(logits), _ptr(labels.contiguous()), logits.shape[0], logits.shape[1],
-                                           _ptr(w), _ptr(stats), _stream()), "irp_cross_entropy_stats")
+                                           _ptr(w), _ptr(stats), _stream(logits)), "irp_cross_entropy_stats")
     return stats
