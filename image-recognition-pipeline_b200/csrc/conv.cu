@@ -8,11 +8,10 @@
 #include <vector>
 
 #include "common.h"
-#include "conv_gemm.cuh"
+#include "conv_params.cuh"
 #include "conv_gemm2.cuh"
 #include "conv3x3_c64.cuh"
 #include "conv_chain.cuh"
-#include "l1_block.cuh"
 #include "stem_conv.cuh"
 
 namespace irp {
@@ -53,47 +52,6 @@ __global__ void add_bias_kernel(const float* __restrict__ a, const float* __rest
 }
 
 // 3x3 / stride 2 / pad 1 max pooling, NHWC bf16, 8 channels (16 bytes) per thread.
-__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
-                                    int W, int C, int Ho, int Wo) {
-  const int cg = C / 8;
-  const long long total = static_cast<long long>(B) * Ho * Wo * cg;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % cg);
-    long long pix = i / cg;
-    const int wo = static_cast<int>(pix % Wo);
-    pix /= Wo;
-    const int ho = static_cast<int>(pix % Ho);
-    const int n = static_cast<int>(pix / Ho);
-    __nv_bfloat162 m[4];
-    bool first = true;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int h = ho * 2 + r - 1;
-      if (h < 0 || h >= H) continue;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int w = wo * 2 + s - 1;
-        if (w < 0 || w >= W) continue;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + h) * W + w) * C) + g);
-        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
-        if (first) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) m[j] = pv[j];
-          first = false;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], pv[j]);
-        }
-      }
-    }
-    uint4 o;
-    memcpy(&o, m, sizeof(o));
-    reinterpret_cast<uint4*>(y + ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C)[g] = o;
-  }
-}
-
-// Global average pool: NHWC bf16 [B, HW, C] -> fp32 [B, C]; one thread per (image, channel pair).
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
   const int c2 = C / 2;
   const long long total = static_cast<long long>(B) * c2;
@@ -114,45 +72,14 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __res
   }
 }
 
-// Fallback stem feed: explicit im2col of the padded NHWC4 input into [B*112*112, 192] bf16
-// (K index = (r*7+s)*3+c for the first 147 entries, zero after).
-__global__ void stem_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ a, int B) {
-  constexpr int kK = 192, kP = IRP_PAD_HW;
-  const long long total = static_cast<long long>(B) * 112 * 112 * (kK / 8);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % (kK / 8));
-    long long pix = i / (kK / 8);
-    const int wo = static_cast<int>(pix % 112);
-    pix /= 112;
-    const int ho = static_cast<int>(pix % 112);
-    const int n = static_cast<int>(pix / 112);
-    __nv_bfloat16 v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      __nv_bfloat16 e = __float2bfloat16_rn(0.f);
-      if (k < 147) {
-        const int c = k % 3, s = (k / 3) % 7, r = k / 21;
-        e = x[((static_cast<size_t>(n) * kP + (2 * ho + r)) * kP + (2 * wo + s)) * 4 + c];
-      }
-      v[j] = e;
-    }
-    uint4 o;
-    memcpy(&o, v, sizeof(o));
-    reinterpret_cast<uint4*>(a)[i] = o;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // conv planning
 // ------------------------------------------------------------------------------------------------------------
-enum ConvKind { kConvFlat = 0, kConvSpatial = 1, kConvStem = 2, kConvPatch64 = 3 };
+enum ConvKind { kConvFlat = 0, kConvSpatial = 1, kConvPatch64 = 3 };
 
 struct ConvPlan {
   ConvParams p;
   int bn_tile = 128;  // BN of the kernel instance
-  int version = 2;    // 2: CTA-pair kernel (conv_gemm2.cuh), 1: single-CTA kernel (conv_gemm.cuh)
   ConvKind kind = kConvFlat;
   bool has_res = false;
   int H = 0, W = 0, Ho = 0, Wo = 0, cin = 0, cout = 0, ksize = 1, stride = 1;
@@ -204,54 +131,24 @@ static int encode_out_maps(ConvPlan* plan, void* out, const void* residual, int 
   IRP_TRY(encode_bf16_map(&p.tmOut, out, 4, dims, strides, box, 128));
   plan->has_res = residual != nullptr;
   if (residual) IRP_TRY(encode_bf16_map(&p.tmRes, const_cast<void*>(residual), 4, dims, strides, box, 128));
+  if (plan->kind == kConvFlat) {
+    uint32_t wbox[4] = {64, 32, 1, 1};  // one epilogue warp's rows (warp-store epilogue)
+    IRP_TRY(encode_bf16_map(&p.tmOutW, out, 4, dims, strides, wbox, 128));
+  }
+  p.cout = plan->cout;
   p.out_box_bytes = p.bw * p.bh * p.bn * 128;
   return IRP_OK;
-}
-
-// Programmatic dependent launch between consecutive trunk kernels (IRP_NO_PDL=1 turns it off).
-static bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("IRP_NO_PDL");
-    v = (e && atoi(e) != 0) ? 0 : 1;
-  }
-  return v == 1;
-}
-
-static bool patch64_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("IRP_NO_PATCH64");
-    v = (e && atoi(e) != 0) ? 0 : 1;
-  }
-  return v == 1;
-}
-
-// Kernel generation: 2 (CTA pairs) unless IRP_CONV_V1=1 asks for the single-CTA kernel (A/B comparisons).
-static int conv_version() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("IRP_CONV_V1");
-    v = (e && atoi(e) != 0) ? 1 : 2;
-  }
-  return v;
 }
 
 // Tile width of the CTA-pair kernel for a conv with `pair_m_tiles` 256-row tiles: the operand stream per tile is
 // proportional to (256 + BN) bytes per unit of K and the tiles run in ceil(tiles / pairs) waves, so pick the BN
 // that minimises waves * (256 + BN); ties go to the wider tile (fewer operand bytes per FLOP).
 static int choose_bn2(int cout, long long pair_m_tiles) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("IRP_CONV_BN");
-    forced = e ? atoi(e) : 0;
-  }
   const int pairs = num_sms() / 2;
   int best = 64;
   long long best_cost = -1;
   for (int bn = 64; bn <= 256; bn *= 2) {
     if (cout % bn != 0) continue;
-    if (forced > 0 && bn != forced && cout % forced == 0) continue;
     const long long tiles = pair_m_tiles * (cout / bn);
     const long long cost = ceil_div64(tiles, pairs) * (256 + bn);
     if (best_cost < 0 || cost <= best_cost) {
@@ -282,7 +179,6 @@ static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* 
   plan->ksize = ksize;
   plan->stride = stride;
   plan->max_batch = max_batch;
-  plan->version = conv_version();
   plan->bn_tile = (Cout % 128 == 0) ? 128 : 64;
   constexpr int BK = 64;
   p.cin = Cin;
@@ -293,10 +189,9 @@ static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* 
   p.n_tiles_n = Cout / plan->bn_tile;
 
   char* xb = static_cast<char*>(const_cast<void*>(x));
-  if (ksize == 3 && stride == 1 && Cin == 64 && Cout == 64 && residual == nullptr && patch64_enabled()) {
+  if (ksize == 3 && stride == 1 && Cin == 64 && Cout == 64 && residual == nullptr) {
     // patch-resident kernel (conv3x3_c64.cuh): 8 x 16 output tiles, 10 x 18 input patches, resident weights
     plan->kind = kConvPatch64;
-    plan->version = 3;
     plan->bn_tile = 64;
     p.n_tiles_n = 1;
     p.bw = kC64TileW;
@@ -366,7 +261,7 @@ static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* 
     }
   }
   p.a_box_bytes = p.bw * p.bh * p.bn * BK * 2;
-  if (plan->version == 2) {
+  {
     const long long rows = static_cast<long long>(max_batch) * Ho * Wo;
     const long long m_tiles = plan->kind == kConvFlat
                                   ? ceil_div64(rows, kTileM)
@@ -382,125 +277,66 @@ static int plan_conv(ConvPlan* plan, const void* x, const void* w, const float* 
     uint64_t dims[2] = {K, static_cast<uint64_t>(Cout)};
     uint64_t strides[1] = {K * 2};
     // the CTA-pair kernel loads half of the tile's weight rows per CTA
-    uint32_t box[2] = {BK, static_cast<uint32_t>(plan->version == 2 ? plan->bn_tile / 2 : plan->bn_tile)};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(plan->bn_tile / 2)};
     IRP_TRY(encode_bf16_map(&p.tmB, const_cast<void*>(w), 2, dims, strides, box, 128));
   }
   return IRP_OK;
 }
 
-template <int BN, int BK, bool STEM, bool RES, int NB, int CM = 1, int CN = 1>
-static int launch_instance(const ConvParams& p, cudaStream_t stream) {
-  using S = ConvSmem<BN, BK, NB>;
-  constexpr int kCluster = CM * CN;
-  static bool configured = false;
-  static int max_ctas = 0;
-  auto kernel = conv_gemm_kernel<BN, BK, STEM, RES, NB, CM, CN>;
+// Launch attributes shared by the trunk's CTA-pair kernels: 2-CTA clusters + programmatic dependent launch (a
+// kernel's prologue overlaps its predecessor's tail; every kernel orders its reads with griddepcontrol.wait).
+struct PairLaunch {
   cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(kConvThreads);
-  cfg.dynamicSmemBytes = S::kTotalBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = kCluster > 1 ? 1 : 0;
-  if (!configured) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
-    max_ctas = num_sms();
-    if (kCluster > 1) {
-      // how many clusters can be co-resident (GPC granularity strands a few SMs for cluster size 4)
-      cfg.gridDim = dim3(num_sms() / kCluster * kCluster);
-      int clusters = 0;
-      IRP_CUDA_OK(cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg));
-      if (clusters < 1) clusters = 1;
-      max_ctas = clusters * kCluster;
+  cudaLaunchAttribute attr[2];
+  PairLaunch(int grid, int threads, size_t smem, cudaStream_t stream, bool cluster2) {
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    int n = 0;
+    if (cluster2) {
+      attr[n].id = cudaLaunchAttributeClusterDimension;
+      attr[n].val.clusterDim.x = 2;
+      attr[n].val.clusterDim.y = 1;
+      attr[n].val.clusterDim.z = 1;
+      ++n;
     }
-    configured = true;
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
   }
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int num_groups = ceil_div(m_tiles, CM) * (p.n_tiles_n / CN);
-  int grid = num_groups * kCluster;
-  if (grid > max_ctas) grid = max_ctas;
-  if (grid <= 0) return IRP_OK;
-  cfg.gridDim = dim3(grid);
-  IRP_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
-  return IRP_OK;
-}
+};
 
-// cluster shape policy: 0 = none, 21 = 2x1 (share weights), 12 = 1x2 (share activations), 22 = 2x2
-static int cluster_policy(const ConvPlan& plan, int k_blocks) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("IRP_CLUSTER");
-    forced = e ? atoi(e) : 0;
-    if (!e) forced = 1000;  // no override
-  }
-  const int n_tiles = plan.cout / plan.bn_tile;
-  int want = forced == 1000 ? 0 : forced;
-  if ((want == 22 || want == 12) && (n_tiles % 2) != 0) want = want == 22 ? 21 : 0;
-  (void)k_blocks;
-  return want;
-}
-
-template <int BN, bool RES, int NB>
-static int launch_clustered(const ConvParams& p, int shape, cudaStream_t stream) {
-  switch (shape) {
-    case 21: return launch_instance<BN, 64, false, RES, NB, 2, 1>(p, stream);
-    case 12: return launch_instance<BN, 64, false, RES, NB, 1, 2>(p, stream);
-    case 22: return launch_instance<BN, 64, false, RES, NB, 2, 2>(p, stream);
-    default: return launch_instance<BN, 64, false, RES, NB, 1, 1>(p, stream);
-  }
-}
-
-template <int BN, bool RES>
+template <int BN, bool RES, bool WS>
 static int launch_instance2(const ConvParams& p, cudaStream_t stream) {
-  using S = Conv2Smem<BN, RES>;
-  static bool configured = false;
-  auto kernel = conv_gemm2_kernel<BN, RES>;
-  if (!configured) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
-    configured = true;
-  }
+  using S = Conv2Smem<BN, RES, WS>;
+  auto kernel = conv_gemm2_kernel<BN, RES, WS>;
+  IRP_TRY(ensure_smem(kernel, S::kTotalBytes));
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int num_groups = ((m_tiles + 1) / 2) * p.n_tiles_n;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (num_groups < pairs ? num_groups : pairs);
   if (grid <= 0) return IRP_OK;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kConv2Threads);
-  cfg.dynamicSmemBytes = S::kTotalBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  IRP_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
+  PairLaunch l(grid, kConv2Threads, S::kTotalBytes, stream, true);
+  IRP_CUDA_OK(cudaLaunchKernelEx(&l.cfg, kernel, p));
   return IRP_OK;
 }
 
-template <bool RES>
+template <bool RES, bool WS>
 static int launch_conv2(const ConvParams& p, int bn, cudaStream_t stream) {
   switch (bn) {
-    case 256: return launch_instance2<256, RES>(p, stream);
-    case 128: return launch_instance2<128, RES>(p, stream);
-    default: return launch_instance2<64, RES>(p, stream);
+    case 256: return launch_instance2<256, RES, WS>(p, stream);
+    case 128: return launch_instance2<128, RES, WS>(p, stream);
+    default: return launch_instance2<64, RES, WS>(p, stream);
   }
 }
 
 // Launch a planned conv on `batch` images (batch <= plan->max_batch).
-static int launch_conv(const ConvPlan& plan, int batch, cudaStream_t stream, int n_base = 0) {
+static int launch_conv(const ConvPlan& plan, int batch, cudaStream_t stream) {
   ConvParams p = plan.p;
-  p.n_base = n_base;
   if (plan.kind == kConvFlat) {
     const long long M = static_cast<long long>(batch) * plan.Ho * plan.Wo;
     p.tiles_w = static_cast<int>(ceil_div64(M, kTileM));
@@ -512,78 +348,23 @@ static int launch_conv(const ConvPlan& plan, int batch, cudaStream_t stream, int
     p.tiles_n = ceil_div(batch, p.bn);
   }
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
-  const int k_blocks = p.ntaps * p.kc_blocks;
-  if (plan.kind == kConvStem) return launch_instance<64, 32, true, false, 2>(p, stream);
   if (plan.kind == kConvPatch64) {
-    static bool configured = false;
-    if (!configured) {
-      IRP_CUDA_OK(cudaFuncSetAttribute(conv3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kC64SmemBytes));
-      configured = true;
-    }
+    IRP_TRY(ensure_smem(conv3x3_c64_kernel, kC64SmemBytes));
     const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     if (grid <= 0) return IRP_OK;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kC64Threads);
-    cfg.dynamicSmemBytes = kC64SmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    IRP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3x3_c64_kernel, p));
+    PairLaunch l(grid, kC64Threads, kC64SmemBytes, stream, false);
+    IRP_CUDA_OK(cudaLaunchKernelEx(&l.cfg, conv3x3_c64_kernel, p));
     return IRP_OK;
   }
-  if (plan.version == 2)
-    return plan.has_res ? launch_conv2<true>(p, plan.bn_tile, stream) : launch_conv2<false>(p, plan.bn_tile, stream);
-  if (plan.bn_tile == 128) {
-    const int shape = cluster_policy(plan, k_blocks);
-    if (plan.has_res) return launch_clustered<128, true, 3>(p, shape, stream);
-    if (k_blocks >= 9) return launch_clustered<128, false, 1>(p, shape, stream);
-    return launch_clustered<128, false, 2>(p, shape, stream);
-  }
-  if (plan.has_res) return launch_instance<64, 64, false, true, 3>(p, stream);
-  if (k_blocks >= 9) return launch_instance<64, 64, false, false, 1>(p, stream);
-  return launch_instance<64, 64, false, false, 2>(p, stream);
-}
-
-// Stem through the overlapping 5-D TMA view of the padded NHWC4 input (see conv_gemm.cuh, STEM path).
-static int plan_stem_tma(ConvPlan* plan, const void* x_nhwc4p, const void* w, const float* bias, void* out,
-                         int max_batch, int input_batch) {
-  ConvParams& p = plan->p;
-  memset(&p, 0, sizeof(p));
-  plan->kind = kConvStem;
-  plan->bn_tile = 64;
-  plan->max_batch = max_batch;
-  plan->Ho = 112;
-  plan->Wo = 112;
-  plan->cout = 64;
-  constexpr int P = IRP_PAD_HW;
-  p.cin = 32;  // K per filter row: 8 pixels x 4 channels
-  p.kc_blocks = 1;
-  p.ntaps = 7;
-  p.bias = bias;
-  p.relu = 1;
-  p.n_tiles_n = 1;
-  p.bw = 16;
-  p.bh = 8;
-  p.bn = 1;
-  p.a_box_bytes = kTileM * 32 * 2;
-  uint64_t dims[5] = {32, 112, 2, P / 2, static_cast<uint64_t>(input_batch)};
-  uint64_t strides[4] = {16, static_cast<uint64_t>(P) * 8, static_cast<uint64_t>(P) * 16,
-                         static_cast<uint64_t>(P) * P * 8};
-  uint32_t box[5] = {32, 16, 1, 8, 1};
-  IRP_TRY(encode_bf16_map(&p.tmA[0], const_cast<void*>(x_nhwc4p), 5, dims, strides, box, 64));
-  uint64_t wd[2] = {7 * 32, 64};
-  uint64_t ws[1] = {7 * 32 * 2};
-  uint32_t wb[2] = {32, 64};
-  IRP_TRY(encode_bf16_map(&p.tmB, const_cast<void*>(w), 2, wd, ws, wb, 64));
-  IRP_TRY(encode_out_maps(plan, out, nullptr, max_batch));
-  return IRP_OK;
+  // 1x1 stride 1 with narrow tiles: barrier-free warp-store epilogue (measured: 40 -> 36 us on layer1's first conv1).
+  // At BN = 256 it loses (46 -> 51 us on layer3's conv3 + residual): the whole-bias staging costs a pipeline stage
+  // and those launches are bound by L2 <-> SM traffic, not by the epilogue's barrier.
+  if (plan.kind == kConvFlat && plan.bn_tile < 256)
+    return plan.has_res ? launch_conv2<true, true>(p, plan.bn_tile, stream)
+                        : launch_conv2<false, true>(p, plan.bn_tile, stream);
+  return plan.has_res ? launch_conv2<true, false>(p, plan.bn_tile, stream)
+                      : launch_conv2<false, false>(p, plan.bn_tile, stream);
 }
 
 // conv3 of one bottleneck chained with conv1 of the next (conv_chain.cuh)
@@ -622,9 +403,9 @@ static int plan_chain(ChainPlan* plan, const void* t2, const void* w3, const flo
   IRP_TRY(map2d(&p.tmA2, x2 ? x2 : t2, x2 ? K2 : K1, M, kTileM));
   p.k2_blocks = K2 / 64;
   p.has_res = residual != nullptr ? 1 : 0;
-  IRP_TRY(map2d(&p.tmY, y, N1, M, kTileM));
+  IRP_TRY(map2d(&p.tmYW, y, N1, M, 32));
   IRP_TRY(map2d(&p.tmB2, w1, N1, N2, N2 / 2));
-  IRP_TRY(map2d(&p.tmOut2, t1, N2, M, kTileM));
+  IRP_TRY(map2d(&p.tmOut2W, t1, N2, M, 32));
   p.bias1 = b3;
   p.bias2 = b1;
   p.k1_blocks = K1 / 64;
@@ -639,32 +420,14 @@ static int plan_chain(ChainPlan* plan, const void* t2, const void* w3, const flo
 template <int N2>
 static int launch_chain_instance(const ChainParams& p, cudaStream_t stream) {
   using S = ChainSmem<N2>;
-  static bool configured = false;
   auto kernel = conv_chain_kernel<N2>;
-  if (!configured) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
-    configured = true;
-  }
+  IRP_TRY(ensure_smem(kernel, S::kTotalBytes));
   const int pair_tiles = (p.m_tiles + 1) / 2;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (pair_tiles < pairs ? pair_tiles : pairs);
   if (grid <= 0) return IRP_OK;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kChainThreads);
-  cfg.dynamicSmemBytes = S::kTotalBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  IRP_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
+  PairLaunch l(grid, kChainThreads, S::kTotalBytes, stream, true);
+  IRP_CUDA_OK(cudaLaunchKernelEx(&l.cfg, kernel, p));
   return IRP_OK;
 }
 
@@ -676,100 +439,6 @@ static int launch_chain(const ChainPlan& plan, long long rows, cudaStream_t stre
     case 128: return launch_chain_instance<128>(p, stream);
     default: return launch_chain_instance<256>(p, stream);
   }
-}
-
-// conv2 + conv3 + next conv1 of a layer1 bottleneck in one launch (l1_block.cuh)
-struct L1Plan {
-  L1BlockParams p;
-  int n2 = 0;
-  bool valid = false;
-};
-
-static int plan_l1_block(L1Plan* plan, const void* t1_in, const void* w2, const float* b2, const void* w3,
-                         const float* b3, const void* residual, void* y, const void* w1, const float* b1, void* t1_out,
-                         int max_batch, int H, int W, int N2) {
-  IRP_REQUIRE(N2 == 64 || N2 == 128, "l1 block: N2 %d", N2);
-  L1BlockParams& p = plan->p;
-  memset(&p, 0, sizeof(p));
-  auto act_map = [&](CUtensorMap* m, const void* base, uint64_t C, uint32_t bw, uint32_t bh) -> int {
-    uint64_t dims[4] = {C, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(max_batch)};
-    uint64_t strides[3] = {C * 2, static_cast<uint64_t>(W) * C * 2, static_cast<uint64_t>(H) * W * C * 2};
-    uint32_t box[4] = {64, bw, bh, 1};
-    return encode_bf16_map(m, const_cast<void*>(base), 4, dims, strides, box, 128);
-  };
-  auto w_map = [&](CUtensorMap* m, const void* base, uint64_t K, uint64_t N, uint32_t box_n) -> int {
-    uint64_t dims[2] = {K, N};
-    uint64_t strides[1] = {K * 2};
-    uint32_t box[2] = {64, box_n};
-    return encode_bf16_map(m, const_cast<void*>(base), 2, dims, strides, box, 128);
-  };
-  IRP_TRY(act_map(&p.tmIn, t1_in, 64, kC64PatchW, kC64PatchH));
-  IRP_TRY(w_map(&p.tmW2, w2, 576, 64, 32));
-  IRP_TRY(w_map(&p.tmW3, w3, 64, kL1N1, 64));
-  IRP_TRY(w_map(&p.tmW1, w1, kL1N1, N2, N2 / 2));
-  IRP_TRY(act_map(&p.tmRes, residual, kL1N1, kC64TileW, kC64TileH));
-  IRP_TRY(act_map(&p.tmY, y, kL1N1, kC64TileW, kC64TileH));
-  IRP_TRY(act_map(&p.tmOut2, t1_out, N2, kC64TileW, kC64TileH));
-  p.bias2 = b2;
-  p.bias3 = b3;
-  p.bias1 = b1;
-  p.tiles_w = ceil_div(W, kC64TileW);
-  p.tiles_h = ceil_div(H, kC64TileH);
-  plan->n2 = N2;
-  plan->valid = true;
-  return IRP_OK;
-}
-
-// mapped host memory the device writes a record into when an mbarrier wait times out (ptx.cuh mbar_wait_dbg)
-static uint32_t* g_trap_host = nullptr;
-static int ensure_trap_record() {
-  if (g_trap_host != nullptr) return IRP_OK;
-  IRP_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&g_trap_host), 64, cudaHostAllocMapped));
-  memset(g_trap_host, 0, 64);
-  uint32_t* dptr = nullptr;
-  IRP_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_trap_host, 0));
-  IRP_CUDA_OK(cudaMemcpyToSymbol(g_irp_trap_rec, &dptr, sizeof(dptr)));
-  return IRP_OK;
-}
-
-template <int N2>
-static int launch_l1_instance(const L1BlockParams& p, cudaStream_t stream) {
-  using S = L1Smem<N2>;
-  static bool configured = false;
-  auto kernel = l1_block_kernel<N2>;
-  IRP_TRY(ensure_trap_record());
-  if (!configured) {
-    IRP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
-    configured = true;
-  }
-  const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int pair_tiles = (tiles + 1) / 2;
-  const int pairs = num_sms() / 2;
-  const int grid = 2 * (pair_tiles < pairs ? pair_tiles : pairs);
-  if (grid <= 0) return IRP_OK;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kL1Threads);
-  cfg.dynamicSmemBytes = S::kTotalBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  IRP_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
-  return IRP_OK;
-}
-
-static int launch_l1_block(const L1Plan& plan, int batch, cudaStream_t stream) {
-  L1BlockParams p = plan.p;
-  p.tiles_n = batch;
-  return plan.n2 == 64 ? launch_l1_instance<64>(p, stream) : launch_l1_instance<128>(p, stream);
 }
 
 static int grid_for(long long total, int threads) {
@@ -825,92 +494,53 @@ static const std::vector<ConvSpec>& specs() {
 }  // namespace
 
 struct irp_resnet50 {
-  StemPoolParams stem3;                // stem_mode 3: stem + max pool fused (stem_pool_kernel)
-  StemParams stem2;                    // stem_mode 2: patch-resident no-swizzle stem kernel
-  __nv_bfloat16* stem2_w = nullptr;    // its weights (core-matrix order)
+  StemPoolParams stem;                 // stem + max pool fused (stem_pool_kernel)
+  __nv_bfloat16* stem_w = nullptr;     // its weights (core-matrix order, stem_fold_kernel)
   int max_batch = 0;
-  int micro = 0;  // images per pass through the trunk (activation arena size); inter-layer tensors of one
-                  // micro-batch are meant to stay resident in the 126 MB L2
-  int stem_mode = 3;  // 3: stem + max pool fused, 2: patch-resident stem kernel (stem_conv.cuh), 0: overlapping
-                      // TMA view, 1: im2col + flat GEMM
   std::vector<ConvPlan> plans;
-  std::vector<ChainPlan> chains;  // indexed by the conv3 of the first block of a fused junction
+  std::vector<ChainPlan> chains;     // indexed by the conv3 of the first block of a fused junction
   std::vector<ChainPlan> chains_ds;  // same junction with the block's stride-1 shortcut conv folded into GEMM1
   int cat_c3 = -1, cat_ds = -1;      // conv3 / shortcut conv whose folded weights are also kept concatenated along K
   __nv_bfloat16* wcat = nullptr;     // [cout][cin_c3 + cin_ds]
   float* bcat = nullptr;             // bias_c3 + bias_ds
-  bool ds_fuse = true;               // IRP_NO_DS_FUSE=1: keep the shortcut conv of layer1's first block separate
-  std::vector<L1Plan> l1blocks;   // indexed by the conv2 of a layer1 block whose conv2+conv3+next conv1 are fused
-  int l1_level = 0;               // IRP_L1_FUSE=1: layer1 blocks through l1_block.cuh.  Off by default: measured 346 us
-                                  // against 81 + 218 us for conv3x3_c64 + conv_chain -- with everything on one SM the
-                                  // kernel is shared-memory-bandwidth bound (~700 KB of smem traffic per 128-pixel tile)
-  int planned_l1 = -1;            // l1 mode the current plans were built for
-  int chain_level = 1;            // 0: off, 1: layer1 + layer2 junctions, 2: also layer3
   std::vector<__nv_bfloat16*> weights;
   std::vector<float*> biases;
   std::vector<int> out_buf;  // arena buffer id holding each conv's output
   // arena
-  __nv_bfloat16* buf[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // A, B, T1, T2, DS, STEM, T1B
-  __nv_bfloat16* im2col = nullptr;
+  __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // A, B, T1, T2, DS
   const void* planned_input = nullptr;
-  ConvPlan stem_plan_tma;
   bool planned = false;
 };
 
-static size_t weight_elems(const ConvSpec& s, int stem_mode) {
-  if (s.role == 0) return stem_mode == 0 ? 64 * 7 * 8 * 4 : 64 * 192;
-  return static_cast<size_t>(s.cout) * s.ksize * s.ksize * s.cin;
-}
+// Junctions conv3 (+ residual) -> next conv1 are chained in one kernel up to this many conv3 output channels:
+// layer1 and layer2.  Layer3 (N1 = 1024) was measured slower chained (eight 128-column passes per tile: the second
+// GEMM's weight stream and ring traffic cost more than the 104 MB re-read they save).
+constexpr int kChainMaxCout = 512;
 
-// Everything in the plan that depends on the INPUT pointer (the stem's tensor maps): re-encoded alone when a call
-// brings a different input buffer, which is every call once preprocessing of the next batch overlaps the trunk of
-// the current one (two input buffers alternate).
+// Everything in the plan that depends on the INPUT pointer (the stem's tensor map): re-encoded alone when a call
+// brings a different input buffer.
 static int plan_stem_input(irp_resnet50* net, const void* d_x) {
-  const int B = net->micro;
-  enum { A = 0, STEM = 5 };
-  if (net->stem_mode == 3) {
-    StemPoolParams& sp3 = net->stem3;
-    memset(&sp3, 0, sizeof(sp3));
-    constexpr uint64_t P = IRP_PAD_HW;
-    uint64_t idims[3] = {P * 4, P, static_cast<uint64_t>(net->max_batch)};
-    uint64_t istr[2] = {P * 8, P * P * 8};
-    uint32_t ibox[3] = {kSpPatchW * 4, kSpPatchH, 1};
-    IRP_TRY(encode_bf16_map(&sp3.tmIn, const_cast<void*>(d_x), 3, idims, istr, ibox, 0));
-    sp3.weights = net->stem2_w;
-    sp3.bias = net->biases[0];
-    sp3.out = net->buf[A];
-  }
-  if (net->stem_mode >= 2) {
-    StemParams& sp2 = net->stem2;
-    memset(&sp2, 0, sizeof(sp2));
-    constexpr uint64_t P = IRP_PAD_HW;
-    uint64_t idims[3] = {P * 4, P, static_cast<uint64_t>(net->max_batch)};
-    uint64_t istr[2] = {P * 8, P * P * 8};
-    uint32_t ibox[3] = {kStemPatchW * 4, kStemPatchH, 1};
-    IRP_TRY(encode_bf16_map(&sp2.tmIn, const_cast<void*>(d_x), 3, idims, istr, ibox, 0));
-    uint64_t odims[4] = {64, 112, 112, static_cast<uint64_t>(B)};
-    uint64_t ostr[3] = {128, 112 * 128, 112 * 112 * 128};
-    uint32_t obox[4] = {64, kStemTileW, kStemTileH, 1};
-    IRP_TRY(encode_bf16_map(&sp2.tmOut, net->buf[STEM], 4, odims, ostr, obox, 128));
-    sp2.weights = net->stem2_w;
-    sp2.bias = net->biases[0];
-  } else if (net->stem_mode == 0) {
-    IRP_TRY(plan_stem_tma(&net->plans[0], d_x, net->weights[0], net->biases[0], net->buf[STEM], B, net->max_batch));
-  } else {
-    IRP_TRY(plan_conv(&net->plans[0], net->im2col, net->weights[0], net->biases[0], nullptr, net->buf[STEM], B, 112,
-                      112, 192, 64, 1, 1, 1));
-  }
+  enum { A = 0 };
+  StemPoolParams& sp = net->stem;
+  memset(&sp, 0, sizeof(sp));
+  constexpr uint64_t P = IRP_PAD_HW;
+  uint64_t idims[3] = {P * 4, P, static_cast<uint64_t>(net->max_batch)};
+  uint64_t istr[2] = {P * 8, P * P * 8};
+  uint32_t ibox[3] = {kSpPatchW * 4, kSpPatchH, 1};
+  IRP_TRY(encode_bf16_map(&sp.tmIn, const_cast<void*>(d_x), 3, idims, istr, ibox, 0));
+  sp.weights = net->stem_w;
+  sp.bias = net->biases[0];
+  sp.out = net->buf[A];
   net->planned_input = d_x;
   return IRP_OK;
 }
 
-static int resnet50_plan(irp_resnet50* net, const void* d_x, int l1_mode) {
+static int resnet50_plan(irp_resnet50* net, const void* d_x) {
   const auto& sp = specs();
-  const int B = net->micro;
-  enum { A = 0, Bb = 1, T1 = 2, T2 = 3, DS = 4, STEM = 5, T1B = 6 };
-  int t1_in = T1;  // buffer holding the current block's conv1 output
+  const int B = net->max_batch;
+  enum { A = 0, Bb = 1, T1 = 2, T2 = 3, DS = 4 };
   IRP_TRY(plan_stem_input(net, d_x));
-  net->out_buf[0] = STEM;
+  net->out_buf[0] = A;  // conv 0 + max pool: the pooled stem output
   int cur = A, other = Bb;
   size_t i = 1;
   while (i < sp.size()) {
@@ -918,12 +548,10 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x, int l1_mode) {
     const ConvSpec &c1 = sp[i], &c2 = sp[i + 1], &c3 = sp[i + 2];
     IRP_TRY(plan_conv(&net->plans[i], net->buf[cur], net->weights[i], net->biases[i], nullptr, net->buf[T1], B, c1.H,
                       c1.W, c1.cin, c1.cout, 1, 1, 1));
-    net->out_buf[i] = t1_in;  // T1 unless the previous block's fused kernel wrote this conv1 output elsewhere
-    IRP_TRY(plan_conv(&net->plans[i + 1], net->buf[t1_in], net->weights[i + 1], net->biases[i + 1], nullptr,
+    net->out_buf[i] = T1;
+    IRP_TRY(plan_conv(&net->plans[i + 1], net->buf[T1], net->weights[i + 1], net->biases[i + 1], nullptr,
                       net->buf[T2], B, c2.H, c2.W, c2.cin, c2.cout, 3, c2.stride, 1));
     net->out_buf[i + 1] = T2;
-    const int t1_this = t1_in;
-    t1_in = T1;
     const __nv_bfloat16* res = net->buf[cur];
     if (has_ds) {
       const ConvSpec& d = sp[i + 3];
@@ -939,9 +567,7 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x, int l1_mode) {
       // junction with the next bottleneck: its conv1 consumes this block's output at the same resolution
       const size_t nxt = i + (has_ds ? 4 : 3);
       net->chains[i + 2].valid = false;
-      const int max_n1 = net->chain_level >= 2 ? 1024 : 512;
-      if (net->chain_level > 0 && nxt < sp.size() && c3.cout <= max_n1 &&
-          chain_supported(c3.cin, c3.cout, sp[nxt].cout)) {
+      if (nxt < sp.size() && c3.cout <= kChainMaxCout && chain_supported(c3.cin, c3.cout, sp[nxt].cout)) {
         const ConvSpec& n1 = sp[nxt];
         IRP_TRY(plan_chain(&net->chains[i + 2], net->buf[T2], net->weights[i + 2], net->biases[i + 2], res,
                            net->buf[other], net->weights[nxt], net->biases[nxt], net->buf[T1],
@@ -949,23 +575,11 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x, int l1_mode) {
       }
       // the same junction with the stride-1 shortcut conv computed inside GEMM1 (no DS tensor, no residual read)
       net->chains_ds[i + 2].valid = false;
-      if (net->ds_fuse && net->chains[i + 2].valid && has_ds && static_cast<int>(i + 3) == net->cat_ds &&
-          sp[i + 3].cin % 64 == 0) {
+      if (net->chains[i + 2].valid && has_ds && static_cast<int>(i + 3) == net->cat_ds && sp[i + 3].cin % 64 == 0) {
         IRP_TRY(plan_chain(&net->chains_ds[i + 2], net->buf[T2], net->wcat, net->bcat, nullptr, net->buf[other],
                            net->weights[nxt], net->biases[nxt], net->buf[T1],
                            static_cast<long long>(B) * c3.H * c3.W, c3.H * c3.W, c3.cin, c3.cout, sp[nxt].cout,
                            net->buf[cur], sp[i + 3].cin));
-      }
-      // layer1 blocks: conv2 + conv3 + next conv1 in one kernel; T1' ping-pongs between T1 and T1B because the
-      // kernel reads its own conv1 input (with halo) while it writes the next one
-      net->l1blocks[i + 1].valid = false;
-      if (l1_mode > 0 && nxt < sp.size() && c2.cin == 64 && c2.cout == 64 && c2.ksize == 3 && c2.stride == 1 &&
-          c3.cout == kL1N1 && (sp[nxt].cout == 64 || sp[nxt].cout == 128)) {
-        const int alt = t1_this == T1 ? T1B : T1;
-        IRP_TRY(plan_l1_block(&net->l1blocks[i + 1], net->buf[t1_this], net->weights[i + 1], net->biases[i + 1],
-                              net->weights[i + 2], net->biases[i + 2], res, net->buf[other], net->weights[nxt],
-                              net->biases[nxt], net->buf[alt], B, c2.H, c2.W, sp[nxt].cout));
-        t1_in = alt;
       }
     }
     const int t = cur;
@@ -975,7 +589,6 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x, int l1_mode) {
   }
   net->planned_input = d_x;
   net->planned = true;
-  net->planned_l1 = l1_mode;
   return IRP_OK;
 }
 
@@ -999,43 +612,29 @@ int irp_resnet50_create(irp_resnet50** out, int max_batch) {
   if (!net) return IRP_ERR_NOMEM;
   const auto& sp = specs();
   net->max_batch = max_batch;
-  net->micro = max_batch;
-  if (const char* mb = getenv("IRP_MICRO_BATCH")) {
-    const int v = atoi(mb);
-    if (v > 0 && v < max_batch) net->micro = v;
-  }
-  const char* mode = getenv("IRP_STEM_MODE");
-  net->stem_mode = mode ? atoi(mode) : 3;
-  if (net->stem_mode < 0 || net->stem_mode > 3) net->stem_mode = 3;
   net->plans.resize(sp.size());
   net->chains.resize(sp.size());
-  net->l1blocks.resize(sp.size());
   net->chains_ds.resize(sp.size());
-  if (const char* nf = getenv("IRP_NO_DS_FUSE")) net->ds_fuse = atoi(nf) == 0;
   for (size_t i = 0; i < sp.size(); ++i)
     if (sp[i].role == 4 && sp[i].stride == 1 && net->cat_ds < 0) {  // conv order in a block: conv1, conv2, conv3, ds
       net->cat_ds = static_cast<int>(i);
       net->cat_c3 = static_cast<int>(i) - 1;
     }
-  if (const char* lf = getenv("IRP_L1_FUSE")) net->l1_level = atoi(lf);
-  if (const char* cl = getenv("IRP_CHAIN")) net->chain_level = atoi(cl);
   net->weights.assign(sp.size(), nullptr);
   net->biases.assign(sp.size(), nullptr);
   net->out_buf.assign(sp.size(), -1);
-  const size_t per_img[7] = {56 * 56 * 256, 56 * 56 * 256, 56 * 56 * 128, 56 * 56 * 64, 56 * 56 * 256,
-                             112 * 112 * 64, 56 * 56 * 128};
+  // activation arena (NHWC bf16 elements per image): A, B (block outputs, ping-pong), T1, T2, DS
+  const size_t per_img[5] = {56 * 56 * 256, 56 * 56 * 256, 56 * 56 * 128, 56 * 56 * 64, 56 * 56 * 256};
   cudaError_t e = cudaSuccess;
-  for (int i = 0; i < 7 && e == cudaSuccess; ++i)
-    e = cudaMalloc(reinterpret_cast<void**>(&net->buf[i]), per_img[i] * net->micro * sizeof(__nv_bfloat16));
-  if (e == cudaSuccess && net->stem_mode == 1)
-    e = cudaMalloc(reinterpret_cast<void**>(&net->im2col),
-                   static_cast<size_t>(net->micro) * 112 * 112 * 192 * sizeof(__nv_bfloat16));
-  for (size_t i = 0; i < sp.size() && e == cudaSuccess; ++i) {
+  for (int i = 0; i < 5 && e == cudaSuccess; ++i)
+    e = cudaMalloc(reinterpret_cast<void**>(&net->buf[i]), per_img[i] * max_batch * sizeof(__nv_bfloat16));
+  for (size_t i = 1; i < sp.size() && e == cudaSuccess; ++i) {
     e = cudaMalloc(reinterpret_cast<void**>(&net->weights[i]),
-                   weight_elems(sp[i], net->stem_mode) * sizeof(__nv_bfloat16));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&net->biases[i]), sp[i].cout * sizeof(float));
+                   static_cast<size_t>(sp[i].cout) * sp[i].ksize * sp[i].ksize * sp[i].cin * sizeof(__nv_bfloat16));
   }
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&net->stem2_w), kStemWeightBytes);
+  for (size_t i = 0; i < sp.size() && e == cudaSuccess; ++i)
+    e = cudaMalloc(reinterpret_cast<void**>(&net->biases[i]), sp[i].cout * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&net->stem_w), kStemWeightBytes);
   if (e == cudaSuccess && net->cat_ds >= 0) {
     const ConvSpec &c3 = sp[net->cat_c3], &d = sp[net->cat_ds];
     e = cudaMalloc(reinterpret_cast<void**>(&net->wcat),
@@ -1056,8 +655,7 @@ int irp_resnet50_create(irp_resnet50** out, int max_batch) {
 void irp_resnet50_destroy(irp_resnet50* net) {
   if (!net) return;
   for (auto& b : net->buf) cudaFree(b);
-  cudaFree(net->im2col);
-  cudaFree(net->stem2_w);
+  cudaFree(net->stem_w);
   cudaFree(net->wcat);
   cudaFree(net->bcat);
   for (auto* w : net->weights) cudaFree(w);
@@ -1071,34 +669,15 @@ int irp_resnet50_load_conv(irp_resnet50* net, int index, const float* d_weight_o
   IRP_REQUIRE(net != nullptr && index >= 0 && index < static_cast<int>(sp.size()), "load_conv: bad index %d", index);
   const ConvSpec& s = sp[index];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int kw_pad = s.ksize, cin_pad = s.cin;
   if (s.role == 0) {
     stem_fold_kernel<<<grid_for(kStemWeightBytes / 2, 256), 256, 0, st>>>(d_weight_oihw, d_gamma, d_beta, d_mean,
-                                                                          d_var, eps, net->stem2_w, net->biases[0]);
+                                                                          d_var, eps, net->stem_w, net->biases[0]);
     IRP_CUDA_OK(cudaGetLastError());
-    if (net->stem_mode >= 2) return IRP_OK;
-  }
-  if (s.role == 0 && net->stem_mode == 0) {
-    kw_pad = 8;
-    cin_pad = 4;
-  }
-  if (s.role == 0 && net->stem_mode == 1) {
-    // [64][192]: first 147 = (r,s,c) order, rest zero -> fold into [64][7][7][3] then pad on the device
-    IRP_CUDA_OK(cudaMemsetAsync(net->weights[0], 0, 64 * 192 * sizeof(__nv_bfloat16), st));
-    __nv_bfloat16* tmp = nullptr;
-    IRP_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&tmp), 64 * 147 * sizeof(__nv_bfloat16)));
-    fold_bn_kernel<<<grid_for(64 * 147, 256), 256, 0, st>>>(d_weight_oihw, d_gamma, d_beta, d_mean, d_var, eps, 64,
-                                                             3, 7, 7, 7, 3, tmp, net->biases[0]);
-    IRP_CUDA_OK(cudaGetLastError());
-    IRP_CUDA_OK(cudaMemcpy2DAsync(net->weights[0], 192 * sizeof(__nv_bfloat16), tmp, 147 * sizeof(__nv_bfloat16),
-                                  147 * sizeof(__nv_bfloat16), 64, cudaMemcpyDeviceToDevice, st));
-    IRP_CUDA_OK(cudaStreamSynchronize(st));
-    cudaFree(tmp);
     return IRP_OK;
   }
-  const long long total = static_cast<long long>(s.cout) * s.ksize * kw_pad * cin_pad;
+  const long long total = static_cast<long long>(s.cout) * s.ksize * s.ksize * s.cin;
   fold_bn_kernel<<<grid_for(total, 256), 256, 0, st>>>(d_weight_oihw, d_gamma, d_beta, d_mean, d_var, eps, s.cout,
-                                                       s.cin, s.ksize, s.ksize, kw_pad, cin_pad, net->weights[index],
+                                                       s.cin, s.ksize, s.ksize, s.ksize, s.cin, net->weights[index],
                                                        net->biases[index]);
   IRP_CUDA_OK(cudaGetLastError());
   if (index == net->cat_c3 || index == net->cat_ds) {
@@ -1115,122 +694,68 @@ int irp_resnet50_load_conv(irp_resnet50* net, int index, const float* d_weight_o
   return IRP_OK;
 }
 
+// One pass of `batch` images through the trunk.  capture_index >= 0 (with d_capture): also copy that convolution's
+// output tensor; every conv then runs as its own launch (the junction kernel that folds layer1's shortcut conv into
+// its accumulator never materialises the shortcut tensor), and index 0 yields the stem output AFTER the fused
+// 3x3/2 max pool, [batch,56,56,64].
 static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float* d_embed, int capture_index,
                             void* d_capture, size_t capture_capacity, cudaStream_t st) {
   IRP_REQUIRE(net != nullptr && d_x != nullptr && d_embed != nullptr, "embed: null argument");
   IRP_REQUIRE(batch > 0 && batch <= net->max_batch, "embed: batch %d not in [1,%d]", batch, net->max_batch);
-  // the fused layer1 kernel never materialises conv2's output: a capture of one of those layers runs unfused
-  int l1_mode = net->l1_level;
-  if (d_capture != nullptr && capture_index >= 0 && capture_index < static_cast<int>(specs().size()) &&
-      specs()[capture_index].role == 2 && specs()[capture_index].cin == 64)
-    l1_mode = 0;
-  if (!net->planned || net->planned_l1 != l1_mode)
-    IRP_TRY(resnet50_plan(net, d_x, l1_mode));
+  if (!net->planned)
+    IRP_TRY(resnet50_plan(net, d_x));
   else if (net->planned_input != d_x)
     IRP_TRY(plan_stem_input(net, d_x));
   const auto& sp = specs();
-  enum { A = 0, STEM = 5 };
-  for (int s0 = 0; s0 < batch; s0 += net->micro) {
-    const int mb = batch - s0 < net->micro ? batch - s0 : net->micro;
-    auto capture = [&](int idx) -> int {
-      if (idx != capture_index || d_capture == nullptr) return IRP_OK;
-      const ConvSpec& s = sp[idx];
-      const int ho = s.role == 0 ? 112 : s.H / s.stride, wo = s.role == 0 ? 112 : s.W / s.stride;
-      const size_t per_img = static_cast<size_t>(ho) * wo * s.cout;
-      IRP_REQUIRE(per_img * batch <= capture_capacity, "capture buffer too small: need %zu elements", per_img * batch);
-      IRP_CUDA_OK(cudaMemcpyAsync(static_cast<__nv_bfloat16*>(d_capture) + per_img * s0, net->buf[net->out_buf[idx]],
-                                  per_img * mb * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st));
-      return IRP_OK;
-    };
-    if (net->stem_mode == 1) {
-      const long long total = static_cast<long long>(mb) * 112 * 112 * (192 / 8);
-      stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(
-          static_cast<const __nv_bfloat16*>(d_x) + static_cast<size_t>(s0) * IRP_PAD_HW * IRP_PAD_HW * 4, net->im2col,
-          mb);
-      IRP_CUDA_OK(cudaGetLastError());
-    }
-    // the fused stem + pool kernel never materialises the stem output: a capture of conv 0 takes the unfused path
-    const bool fused_pool = net->stem_mode == 3 && !(capture_index == 0 && d_capture != nullptr);
-    if (fused_pool) {
-      StemPoolParams sp3 = net->stem3;
-      sp3.n_base = s0;
-      sp3.num_tiles = mb * 64;
-      static bool sp_cfg = false;
-      if (!sp_cfg) {
-        IRP_CUDA_OK(cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmemBytes));
-        sp_cfg = true;
-      }
-      const int grid = sp3.num_tiles < num_sms() ? sp3.num_tiles : num_sms();
-      stem_pool_kernel<<<grid, kSpThreads, kSpSmemBytes, st>>>(sp3);
-      IRP_CUDA_OK(cudaGetLastError());
-    } else if (net->stem_mode >= 2) {
-      StemParams sp2 = net->stem2;
-      sp2.batch = mb;
-      sp2.n_base = s0;
-      sp2.num_tiles = mb * 98;
-      static bool stem_cfg = false;
-      if (!stem_cfg) {
-        IRP_CUDA_OK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kStemSmemBytes));
-        stem_cfg = true;
-      }
-      const int grid = sp2.num_tiles < num_sms() ? sp2.num_tiles : num_sms();
-      stem_conv_kernel<<<grid, kStemThreads, kStemSmemBytes, st>>>(sp2);
-      IRP_CUDA_OK(cudaGetLastError());
-    } else {
-      IRP_TRY(launch_conv(net->plans[0], mb, st, s0));
-    }
-    IRP_TRY(capture(0));
-    if (!fused_pool) {
-      const long long total = static_cast<long long>(mb) * 56 * 56 * (64 / 8);
-      maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(net->buf[STEM], net->buf[A], mb, 112, 112, 64, 56, 56);
-      IRP_CUDA_OK(cudaGetLastError());
-    }
-    size_t i = 1;
-    int last = 0;
-    bool conv1_done = false;  // this block's conv1 was already produced by the previous block's chained conv3
-    int blocks_left = -1;     // debugging: run only the first IRP_TRUNK_BLOCKS bottleneck blocks (timing experiments)
-    if (const char* e = getenv("IRP_TRUNK_BLOCKS")) blocks_left = atoi(e);
-    while (i < sp.size()) {
-      if (blocks_left == 0) break;
-      if (blocks_left > 0) --blocks_left;
-      const bool has_ds = (i + 3 < sp.size()) && sp[i + 3].role == 4;
-      if (!conv1_done) IRP_TRY(launch_conv(net->plans[i], mb, st));
-      IRP_TRY(capture(static_cast<int>(i)));
-      const L1Plan& l1 = net->l1blocks[i + 1];
-      if (!l1.valid) {
-        IRP_TRY(launch_conv(net->plans[i + 1], mb, st));
-        IRP_TRY(capture(static_cast<int>(i + 1)));
-      }
-      // shortcut conv folded into the junction kernel (not when a layer output is being captured: the DS tensor
-      // does not exist then, and the per-layer parity test wants every conv on its own)
-      const bool ds_folded = has_ds && !l1.valid && net->chains_ds[i + 2].valid && d_capture == nullptr;
-      if (has_ds && !ds_folded) {
-        IRP_TRY(launch_conv(net->plans[i + 3], mb, st));
-        IRP_TRY(capture(static_cast<int>(i + 3)));
-      }
-      const ChainPlan& ch = ds_folded ? net->chains_ds[i + 2] : net->chains[i + 2];
-      if (l1.valid) {
-        IRP_TRY(launch_l1_block(l1, mb, st));
-        conv1_done = true;
-      } else if (ch.valid) {
-        IRP_TRY(launch_chain(ch, static_cast<long long>(mb) * ch.rows_per_image, st));
-        conv1_done = true;
-      } else {
-        IRP_TRY(launch_conv(net->plans[i + 2], mb, st));
-        conv1_done = false;
-      }
-      IRP_TRY(capture(static_cast<int>(i + 2)));
-      last = static_cast<int>(i + 2);
-      i += has_ds ? 4 : 3;
-    }
-    if (blocks_left < 0) {
-      const long long total = static_cast<long long>(mb) * (2048 / 2);
-      avgpool_kernel<<<grid_for(total, 128), 128, 0, st>>>(net->buf[net->out_buf[last]],
-                                                          d_embed + static_cast<size_t>(s0) * 2048, mb, 49, 2048);
-      IRP_CUDA_OK(cudaGetLastError());
-    }
+  auto capture = [&](int idx) -> int {
+    if (idx != capture_index || d_capture == nullptr) return IRP_OK;
+    const ConvSpec& s = sp[idx];
+    const int ho = s.role == 0 ? 56 : s.H / s.stride, wo = s.role == 0 ? 56 : s.W / s.stride;
+    const size_t per_img = static_cast<size_t>(ho) * wo * s.cout;
+    IRP_REQUIRE(per_img * batch <= capture_capacity, "capture buffer too small: need %zu elements", per_img * batch);
+    IRP_CUDA_OK(cudaMemcpyAsync(d_capture, net->buf[net->out_buf[idx]], per_img * batch * sizeof(__nv_bfloat16),
+                                cudaMemcpyDeviceToDevice, st));
+    return IRP_OK;
+  };
+  {
+    StemPoolParams sp3 = net->stem;
+    sp3.n_base = 0;
+    sp3.num_tiles = batch * 64;
+    IRP_TRY(ensure_smem(stem_pool_kernel, kSpSmemBytes));
+    const int grid = sp3.num_tiles < num_sms() ? sp3.num_tiles : num_sms();
+    stem_pool_kernel<<<grid, kSpThreads, kSpSmemBytes, st>>>(sp3);
+    IRP_CUDA_OK(cudaGetLastError());
   }
+  IRP_TRY(capture(0));
+  size_t i = 1;
+  int last = 0;
+  bool conv1_done = false;  // this block's conv1 was already produced by the previous block's chained conv3
+  while (i < sp.size()) {
+    const bool has_ds = (i + 3 < sp.size()) && sp[i + 3].role == 4;
+    if (!conv1_done) IRP_TRY(launch_conv(net->plans[i], batch, st));
+    IRP_TRY(capture(static_cast<int>(i)));
+    IRP_TRY(launch_conv(net->plans[i + 1], batch, st));
+    IRP_TRY(capture(static_cast<int>(i + 1)));
+    const bool ds_folded = has_ds && net->chains_ds[i + 2].valid && d_capture == nullptr;
+    if (has_ds && !ds_folded) {
+      IRP_TRY(launch_conv(net->plans[i + 3], batch, st));
+      IRP_TRY(capture(static_cast<int>(i + 3)));
+    }
+    const ChainPlan& ch = ds_folded ? net->chains_ds[i + 2] : net->chains[i + 2];
+    if (ch.valid) {
+      IRP_TRY(launch_chain(ch, static_cast<long long>(batch) * ch.rows_per_image, st));
+      conv1_done = true;
+    } else {
+      IRP_TRY(launch_conv(net->plans[i + 2], batch, st));
+      conv1_done = false;
+    }
+    IRP_TRY(capture(static_cast<int>(i + 2)));
+    last = static_cast<int>(i + 2);
+    i += has_ds ? 4 : 3;
+  }
+  const long long total = static_cast<long long>(batch) * (2048 / 2);
+  avgpool_kernel<<<grid_for(total, 128), 128, 0, st>>>(net->buf[net->out_buf[last]], d_embed, batch, 49, 2048);
+  IRP_CUDA_OK(cudaGetLastError());
   return IRP_OK;
 }
 
@@ -1261,24 +786,6 @@ int irp_conv1x1_chain_ds(const void* d_t2, const void* d_x, const void* d_wcat, 
   ChainPlan plan;
   IRP_TRY(plan_chain(&plan, d_t2, d_wcat, d_bias, nullptr, d_y, d_w1, d_b1, d_t1, rows, 1, K1, N1, N2, d_x, K2));
   return launch_chain(plan, rows, static_cast<cudaStream_t>(stream));
-}
-
-int irp_debug_trap_record(uint32_t* out5) {
-  IRP_REQUIRE(out5 != nullptr, "debug_trap_record: null argument");
-  for (int i = 0; i < 5; ++i) out5[i] = g_trap_host ? g_trap_host[i] : 0u;
-  return IRP_OK;
-}
-
-int irp_l1_block(const void* d_t1, const void* d_w2, const float* d_b2, const void* d_w3, const float* d_b3,
-                 const void* d_residual, void* d_y, const void* d_w1, const float* d_b1, void* d_t1_next, int B, int H,
-                 int W, int N2, void* stream) {
-  IRP_REQUIRE(d_t1 && d_w2 && d_b2 && d_w3 && d_b3 && d_residual && d_y && d_w1 && d_b1 && d_t1_next && B > 0 &&
-                  H > 0 && W > 0,
-              "l1 block: bad argument");
-  IRP_REQUIRE(d_t1 != d_t1_next, "l1 block: the next conv1 output must not alias the conv1 input");
-  L1Plan plan;
-  IRP_TRY(plan_l1_block(&plan, d_t1, d_w2, d_b2, d_w3, d_b3, d_residual, d_y, d_w1, d_b1, d_t1_next, B, H, W, N2));
-  return launch_l1_block(plan, B, static_cast<cudaStream_t>(stream));
 }
 
 int irp_conv2d_nhwc(const void* d_x, const void* d_w, const float* d_bias, const void* d_residual, void* d_out,

@@ -16,7 +16,7 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue.
 #pragma once
-#include "conv_gemm.cuh"
+#include "conv_params.cuh"
 
 namespace irp {
 

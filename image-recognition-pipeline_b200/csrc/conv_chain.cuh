@@ -37,10 +37,10 @@ struct alignas(64) ChainParams {
   CUtensorMap tmA;     // T2  [M, K1]  dims (K1, M), box (64, 128)
   CUtensorMap tmB1;    // W3  [N1, K1] dims (K1, N1), box (64, 64)  (half of a pass per CTA)
   CUtensorMap tmRes;   // R   [M, N1]  dims (N1, M), box (64, 128)
-  CUtensorMap tmY;     // Y   [M, N1]  same geometry
   CUtensorMap tmB2;    // W1' [N2, N1] dims (N1, N2), box (64, N2/2)
-  CUtensorMap tmOut2;  // T1' [M, N2]  dims (N2, M), box (64, 128)
   CUtensorMap tmA2;    // X   [M, K2]  optional second GEMM1 operand (see k2_blocks)
+  CUtensorMap tmYW;    // Y   [M, N1]  dims (N1, M), box (64, 32): one epilogue warp's rows of a chunk
+  CUtensorMap tmOut2W; // T1' [M, N2]  dims (N2, M), box (64, 32)
   const float* bias1;  // [N1]
   const float* bias2;  // [N2]
   int k1_blocks;       // K1 / 64
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
   uint64_t* acc2_full = acc1_empty + 2;      // [1]
   uint64_t* acc2_empty = acc2_full + 1;      // [1] leader's is used
   uint64_t* res_full = acc2_empty + 1;       // [R]
-  uint64_t* stg_empty = res_full + R;        // [R] two arrivals per use: TMA store read + GEMM2 completion
-  uint64_t* ychunk_full = stg_empty + R;     // [R] leader's is used: one arrival per CTA
+  uint64_t* stg_empty = res_full + R;        // [R] five arrivals per use: four warp stores read + GEMM2 completion
+  uint64_t* ychunk_full = stg_empty + R;     // [R] leader's is used: one arrival per epilogue warp of both CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ychunk_full + R);
   float* sbias1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + S::kBarrierBytes);  // [n1]
   float* sbias2 = sbias1 + kChainMaxN1;                                                           // [N2]
@@ -134,9 +134,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB1);
     tma_prefetch_desc(&p.tmRes);
-    tma_prefetch_desc(&p.tmY);
+    tma_prefetch_desc(&p.tmYW);
     tma_prefetch_desc(&p.tmB2);
-    tma_prefetch_desc(&p.tmOut2);
+    tma_prefetch_desc(&p.tmOut2W);
     if (p.k2_blocks > 0) tma_prefetch_desc(&p.tmA2);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full1[i], 1);
@@ -151,11 +151,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       mbar_init(&acc1_empty[i], 16);
     }
     mbar_init(acc2_full, 1);
-    mbar_init(acc2_empty, 16);
+    mbar_init(acc2_empty, kOutChunks >= 2 ? 16 : 8);  // the epilogue warps (both CTAs) that read acc2 of a tile
     for (int i = 0; i < R; ++i) {
       mbar_init(&res_full[i], 1);
-      mbar_init(&stg_empty[i], 2);
-      mbar_init(&ychunk_full[i], 2);
+      mbar_init(&stg_empty[i], 5);    // four warp stores read + (GEMM2 completion | one extra arrival for T1' chunks)
+      mbar_init(&ychunk_full[i], 8);  // four warps of each CTA
     }
     fence_barrier_init();
   }
@@ -291,77 +291,66 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     }
   } else {
     // ============================ epilogue (warps 2..9, both CTAs) ============================
+    // Barrier-free "warp store" epilogue (see conv_gemm2.cuh): the two groups of four warps take the ring chunks of
+    // even / odd q; a warp owns 32 rows x 64 channels of its chunk and stores them with its own (64, 32)-box TMA store.
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
-    const bool leader = (threadIdx.x == 64);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t swz = static_cast<uint32_t>(row & 7);
-    const int piece0 = half * 4;
-    const uint32_t lane_base = (static_cast<uint32_t>(quarter * 32) << 16) + half * 32;
-    int g = 0;  // global pass counter
-    int i = 0;  // local tile counter
-    // leader bookkeeping: hand ring buffer of chunk q-2 back once its store has finished reading
-    // (ring indices are not consecutive at the very end, so the last two processed chunks are remembered)
-    int hist0 = -1, hist1 = -1;  // hist1 = most recent chunk whose store was committed, hist0 = the one before
-    auto release = [&](int q) {
-      tma_store_wait_read<1>();  // every committed store except the most recent one has finished reading
-      if (hist0 >= 0) {
-        mbar_arrive(&stg_empty[hist0 % R]);
-        if (is_out_chunk(hist0)) mbar_arrive(&stg_empty[hist0 % R]);  // T1' chunks have no GEMM2 consumer
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const bool has_res = p.has_res != 0;
+    int g = 0;        // global pass counter
+    int i = 0;        // local tile counter
+    int prev_q = -1;  // this warp's previously stored chunk: its ring buffer is handed back once that store was read
+    // lane 0, right after committing the store of chunk q
+    auto after_store = [&](int q) {
+      tma_store_wait_read<1>();  // every store of this warp but the one just committed has finished reading
+      if (prev_q >= 0) {
+        mbar_arrive(&stg_empty[prev_q % R]);
+        // T1' chunks have no GEMM2 consumer: one warp supplies the fifth arrival
+        if (quarter == 0 && is_out_chunk(prev_q)) mbar_arrive(&stg_empty[prev_q % R]);
       }
-      hist0 = hist1;
-      hist1 = q;
+      prev_q = q;
+    };
+    // everything after the chunk's rows are in the staging buffer
+    auto publish = [&](int q, const void* tmap, int col0, int trow0, bool out_chunk) {
+      const int b = q % R;
+      fence_proxy_async();  // generic-proxy writes -> visible to the TMA store and to the GEMM2 MMAs
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmap, smem_ring + b * kStgChunkBytes + quarter * 4096, col0, trow0 + quarter * 32);
+        tma_store_commit();
+        mbar_arrive_cluster(mapa_u32(&ychunk_full[b], 0));  // this warp's 32 rows of the chunk are in place
+        // a T1' use of the buffer has no residual prefetch: complete that phase by hand so every barrier of
+        // buffer b advances exactly once per use
+        if (out_chunk && quarter == 0) mbar_arrive(&res_full[b]);
+        after_store(q);
+      }
     };
     // epilogue2 of tile ti (rows trow0): acc2 + bias, ReLU -> ring chunks -> TMA store to T1'
     auto epilogue2 = [&](int ti, int trow0) {
+      int last_j = -1;
+#pragma unroll
+      for (int j = 0; j < kOutChunks; ++j)
+        if ((q_out(ti, j) & 1) == grp) last_j = j;
+      if (last_j < 0) return;
       mbar_wait(acc2_full, ti & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < kOutChunks; ++c) {
-        const int q = q_out(ti, c);
+      for (int j = 0; j < kOutChunks; ++j) {
+        const int q = q_out(ti, j);
+        if ((q & 1) != grp) continue;
         const int b = q % R;
-        uint8_t* chunk = smem_ring + b * kStgChunkBytes + row_off;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + kAcc2Col + c * 64 + lane_base, v);
         if (q >= R) mbar_wait(&stg_empty[b], ((q / R) - 1) & 1);
-        const float4* bp = reinterpret_cast<const float4*>(sbias2 + c * 64 + half * 32);
-        float4 bv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bv[j] = bp[j];
-        tmem_ld_wait();
-        if (c == kOutChunks - 1) {
+        epi_row64<false>(tmem_base + kAcc2Col + j * 64 + lane_base, smem_ring + b * kStgChunkBytes + row_off, swz,
+                         sbias2 + j * 64, true, nullptr, 0);
+        if (j == last_j) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(acc2_empty, 0));
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1];
-          float x[8];
-          x[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.f);
-          x[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.f);
-          x[2] = fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.f);
-          x[3] = fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.f);
-          x[4] = fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, 0.f);
-          x[5] = fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, 0.f);
-          x[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.f);
-          x[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.f);
-          *reinterpret_cast<uint4*>(chunk + (((piece0 + j) ^ swz) << 4)) =
-              make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                         pack_bf16x2(x[6], x[7]));
-        }
-        fence_proxy_async();
-        if (leader) release(q);
-        named_bar_sync(1, kChainEpiThreads);
-        if (leader) {
-          tma_store_2d(&p.tmOut2, smem_ring + b * kStgChunkBytes, c * 64, trow0);
-          tma_store_commit();
-          // this use of the ring buffer has no residual and no GEMM2 consumer: complete the corresponding phases
-          // anyway so that every barrier of buffer b advances exactly once per use
-          mbar_arrive(&res_full[b]);
-          mbar_arrive_cluster(mapa_u32(&ychunk_full[b], 0));
-        }
+        publish(q, &p.tmOut2W, j * 64, trow0, true);
       }
     };
     int prev_row0 = 0;
@@ -369,69 +358,33 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const int row0 = (mt * 2 + static_cast<int>(rank)) * kTileM;
       for (int ps = 0; ps < P; ++ps, ++g) {
         const int a1 = g & 1;
+        // exactly one of the pass's two chunks is this warp's
+        const int c = ((q_pass(i, ps, 0) & 1) == grp) ? 0 : 1;
+        const int q = q_pass(i, ps, c);
+        const int b = q % R;
         mbar_wait(&acc1_full[a1], (g >> 1) & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const int q = q_pass(i, ps, c);
-          const int b = q % R;
-          uint8_t* chunk = smem_ring + b * kStgChunkBytes + row_off;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + a1 * kChainBN1 + c * 64 + lane_base, v);
-          uint4 rv[4];
-          if (p.has_res) {
-            mbar_wait(&res_full[b], (q / R) & 1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rv[j] = *reinterpret_cast<const uint4*>(chunk + (((piece0 + j) ^ swz) << 4));
-          } else {
-            // nothing was prefetched into the buffer: wait for its previous use (store read + GEMM2) ourselves
-            if (q >= R) mbar_wait(&stg_empty[b], ((q / R) - 1) & 1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rv[j] = make_uint4(0u, 0u, 0u, 0u);
-          }
-          const float4* bp = reinterpret_cast<const float4*>(sbias1 + ps * kChainBN1 + c * 64 + half * 32);
-          float4 bv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) bv[j] = bp[j];
-          tmem_ld_wait();
-          if (c == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc1_empty[a1], 0));
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1];
-            const uint32_t* r32 = reinterpret_cast<const uint32_t*>(&rv[j]);
-            float x[8];
-            x[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x + bf16_lo(r32[0]), 0.f);
-            x[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y + bf16_hi(r32[0]), 0.f);
-            x[2] = fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z + bf16_lo(r32[1]), 0.f);
-            x[3] = fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w + bf16_hi(r32[1]), 0.f);
-            x[4] = fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x + bf16_lo(r32[2]), 0.f);
-            x[5] = fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y + bf16_hi(r32[2]), 0.f);
-            x[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z + bf16_lo(r32[3]), 0.f);
-            x[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w + bf16_hi(r32[3]), 0.f);
-            *reinterpret_cast<uint4*>(chunk + (((piece0 + j) ^ swz) << 4)) =
-                make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                           pack_bf16x2(x[6], x[7]));
-          }
-          fence_proxy_async();  // generic-proxy writes -> visible to the TMA store and to the GEMM2 MMAs
-          if (leader) release(q);
-          named_bar_sync(1, kChainEpiThreads);
-          if (leader) {
-            tma_store_2d(&p.tmY, smem_ring + b * kStgChunkBytes, ps * kChainBN1 + c * 64, row0);
-            tma_store_commit();
-            mbar_arrive_cluster(mapa_u32(&ychunk_full[b], 0));  // this CTA's 128 rows of the chunk are in place
-          }
+        uint8_t* chunk_row = smem_ring + b * kStgChunkBytes + row_off;
+        const uint32_t taddr = tmem_base + a1 * kChainBN1 + c * 64 + lane_base;
+        const float* bias = sbias1 + ps * kChainBN1 + c * 64;
+        if (has_res) {
+          epi_row64<true>(taddr, chunk_row, swz, bias, true, &res_full[b], (q / R) & 1);
+        } else {
+          // nothing was prefetched into the buffer: wait for its previous use (stores read + GEMM2) ourselves
+          if (q >= R) mbar_wait(&stg_empty[b], ((q / R) - 1) & 1);
+          epi_row64<false>(taddr, chunk_row, swz, bias, true, nullptr, 0);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc1_empty[a1], 0));
+        publish(q, &p.tmYW, ps * kChainBN1 + c * 64, row0, false);
         // deferred T1' epilogue of the previous tile: its last GEMM2 ran while this tile's first pass drained
         if (ps == 0 && i > 0) epilogue2(i - 1, prev_row0);
       }
       prev_row0 = row0;
     }
     if (i > 0) epilogue2(i - 1, prev_row0);
-    if (leader) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

@@ -16,10 +16,17 @@
 //     With a residual, the producer warp prefetches the residual chunk by TMA into the staging buffer the
 //     epilogue then overwrites in place.
 //
+//   * flat convolutions (1x1, stride 1: M is a plain row index) use the barrier-free "warp store" epilogue (WS):
+//     the eight epilogue warps form two groups that take alternate chunks; a warp owns 32 rows x 64 channels of its
+//     chunk (one whole 128-byte swizzled row per thread), and stores them with its OWN TMA store of a (64, 32)
+//     box, so no CTA-wide barrier sits between the chunks and a warp's TMEM / shared-memory latencies overlap the
+//     other warps' arithmetic.  ncu on the round-1 kernel: 20-27 % of the epilogue warps' samples were the per-chunk
+//     named barrier.
+//
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner (+ MMA issuer in the leader), warps 2..9 =
 // epilogue.
 #pragma once
-#include "conv_gemm.cuh"
+#include "conv_params.cuh"
 
 namespace irp {
 
@@ -27,14 +34,17 @@ constexpr int kConv2Threads = 320;
 constexpr int kConv2EpiThreads = 256;
 constexpr int kConv2BK = 64;
 
-template <int BN, bool RES>
+constexpr int kConv2MaxCout = 2048;  // WS epilogue: the whole bias vector is staged in shared memory once
+
+template <int BN, bool RES, bool WS>
 struct Conv2Smem {
   static constexpr int kABytes = kTileM * kConv2BK * 2;    // this CTA's 128 rows
   static constexpr int kBBytes = (BN / 2) * kConv2BK * 2;  // this CTA's half of the weight rows
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRing = RES ? 6 : 4;  // staging chunk buffers (residual prefetch needs look-ahead)
   static constexpr int kStgBytes = kRing * kStgChunkBytes;
-  static constexpr int kBarrierBytes = 512 + BN * 4;  // mbarriers + TMEM slot, then the tile's bias slice (fp32)
+  // mbarriers + TMEM slot, then the bias (fp32): the tile's slice, or the whole vector for the WS epilogue
+  static constexpr int kBarrierBytes = 512 + (WS ? kConv2MaxCout : BN) * 4;
   static constexpr int kBudget = 227 * 1024 - 1024 - kBarrierBytes - kStgBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -42,9 +52,54 @@ struct Conv2Smem {
   static_assert(kStages >= 3, "not enough shared memory for a pipeline");
 };
 
-template <int BN, bool RES>
+// one epilogue warp's share of a 64-channel chunk: 32 rows x 64 fp32 accumulator columns (+ bias, + residual read
+// from the staging row it then overwrites, ReLU) -> bf16 -> the thread's 128-byte row of the swizzled staging chunk
+template <bool RES>
+__device__ __forceinline__ void epi_row64(uint32_t taddr, uint8_t* chunk_row, uint32_t swz, const float* sbias64,
+                                          bool relu, uint64_t* res_bar, uint32_t res_parity) {
+  uint32_t v[64];
+  tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+  tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+  uint4 rv[8];
+  if (RES) {
+    mbar_wait(res_bar, res_parity);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rv[i] = *reinterpret_cast<const uint4*>(chunk_row + ((static_cast<uint32_t>(i) ^ swz) << 4));
+  }
+  tmem_ld_wait();
+  const float4* bp = reinterpret_cast<const float4*>(sbias64);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b0 = bp[2 * i], b1 = bp[2 * i + 1];
+    float x[8];
+    x[0] = __uint_as_float(v[8 * i + 0]) + b0.x;
+    x[1] = __uint_as_float(v[8 * i + 1]) + b0.y;
+    x[2] = __uint_as_float(v[8 * i + 2]) + b0.z;
+    x[3] = __uint_as_float(v[8 * i + 3]) + b0.w;
+    x[4] = __uint_as_float(v[8 * i + 4]) + b1.x;
+    x[5] = __uint_as_float(v[8 * i + 5]) + b1.y;
+    x[6] = __uint_as_float(v[8 * i + 6]) + b1.z;
+    x[7] = __uint_as_float(v[8 * i + 7]) + b1.w;
+    if (RES) {
+      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(&rv[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        x[2 * j] += bf16_lo(r32[j]);
+        x[2 * j + 1] += bf16_hi(r32[j]);
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+    }
+    *reinterpret_cast<uint4*>(chunk_row + ((static_cast<uint32_t>(i) ^ swz) << 4)) =
+        make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+  }
+}
+
+template <int BN, bool RES, bool WS>
 __global__ void __launch_bounds__(kConv2Threads, 1) conv_gemm2_kernel(const __grid_constant__ ConvParams p) {
-  using S = Conv2Smem<BN, RES>;
+  using S = Conv2Smem<BN, RES, WS>;
   constexpr int kStages = S::kStages;
   constexpr int kRing = S::kRing;
   constexpr int BK = kConv2BK;
@@ -87,17 +142,22 @@ __global__ void __launch_bounds__(kConv2Threads, 1) conv_gemm2_kernel(const __gr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 16);  // one arrival per epilogue warp of both CTAs
+      // one arrival per epilogue warp of both CTAs that reads the accumulator (WS with a single chunk per tile:
+      // only one of the two warp groups touches a tile)
+      mbar_init(&tempty_bar[i], (WS && kChunks == 1) ? 8 : 16);
     }
     for (int i = 0; i < kRing; ++i) {
       mbar_init(&res_full[i], 1);
-      mbar_init(&stg_empty[i], 1);
+      mbar_init(&stg_empty[i], WS ? 4 : 1);  // WS: the four warps that stored the chunk hand the buffer back
     }
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc_cg2(tmem_slot, kTmemCols);
     tmem_relinquish_cg2();
+  }
+  if (WS) {
+    for (int i = threadIdx.x; i < p.cout; i += kConv2Threads) sbias[i] = __ldg(p.bias + i);
   }
   tc_fence_before();
   __syncthreads();
@@ -184,6 +244,63 @@ __global__ void __launch_bounds__(kConv2Threads, 1) conv_gemm2_kernel(const __gr
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if (WS) {
+    // ============================ warp-store epilogue (warps 2..9, both CTAs; flat convs) ============================
+    const int quarter = warp & 3;      // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2;   // chunks with (q & 1) == grp are this warp's
+    const int row = quarter * 32 + lane;
+    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+    const uint32_t swz = static_cast<uint32_t>(row & 7);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int q = 0;        // chunk counter (same sequence as the producer's)
+    int prev_b = -1;  // staging buffer of this warp's previous store (RES: handed back once that store has been read)
+    for (int g = pair; g < num_groups; g += num_pairs) {
+      const int n_tile = g % p.n_tiles_n;
+      const int m_tile = (g / p.n_tiles_n) * 2 + static_cast<int>(rank);
+      const int last_cc = kChunks == 1 ? 0 : kChunks - 2 + grp;  // this warp's last chunk of the tile
+      bool acc_ready = false;
+#pragma unroll 1
+      for (int cc = 0; cc < kChunks; ++cc, ++q) {
+        if ((q & 1) != grp) continue;
+        if (!acc_ready) {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          acc_ready = true;
+        }
+        const int b = q % kRing;
+        uint8_t* chunk = smem_stg + b * kStgChunkBytes;
+        if (!RES) {
+          // this warp's previous store out of the same buffer (kRing / 2 of its stores ago) must have been read
+          if (lane == 0) tma_store_wait_read<kRing / 2 - 1>();
+          __syncwarp();
+        }
+        const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16) + cc * 64;
+        epi_row64<RES>(taddr, chunk + row_off, swz, sbias + n_tile * BN + cc * 64, p.relu != 0, &res_full[b],
+                       (q / kRing) & 1);
+        if (cc == last_cc) {
+          // accumulator drained by this warp -> one arrival on the leader's barrier (the TMEM reads completed at
+          // the tcgen05.wait::ld inside epi_row64)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
+        }
+        fence_proxy_async();  // this thread's staging writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&p.tmOutW, chunk + quarter * 4096, n_tile * BN + cc * 64, m_tile * kTileM + quarter * 32, 0, 0);
+          tma_store_commit();
+          if (RES) {
+            tma_store_wait_read<1>();  // every store of this warp but the one just committed has been read
+            if (prev_b >= 0) mbar_arrive(&stg_empty[prev_b]);
+            prev_b = b;
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
   } else {
     // ============================ epilogue (warps 2..9, both CTAs) ============================
     const int quarter = warp & 3;         // TMEM lane quarter this warp may read

@@ -307,7 +307,7 @@ __global__ void gather_sorted_kernel(const float* __restrict__ z, const int32_t*
 // ------------------------------------------------------------------------------------------------------------
 // Filtered search (default): the 64 x 128 x dpad distance block is evaluated in fp32 (FFMA, 4 x 8 register tiles)
 // and used only as a CONSERVATIVE FILTER: a candidate is re-evaluated in fp64 -- with exactly the arithmetic of
-// knn_resident_kernel, so results are bit-identical -- iff  d2_fp32 <= tau + E (|q|^2 + |c|^2), where tau is the
+// an exhaustive fp64 search, so the neighbour sets are identical -- iff  d2_fp32 <= tau + E (|q|^2 + |c|^2), where tau is the
 // query's current k-th best squared distance and E bounds the fp32 evaluation error of |q|^2 + |c|^2 - 2 q.c
 // (inputs are exact: the rows ARE float32; the dot product contributes at most dpad 2^-24 sum|q_j c_j| <=
 // dpad 2^-25 (|q|^2+|c|^2), the norms and the final three operations a few ulps of |q|^2+|c|^2; E = 4 (dpad+8)
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kKnnThreads, 2) knn_filter_kernel(const double
         double dc = INFINITY;
         const int qi = q0 + ql, ci = c0 + cl;
         if (ql >= 0 && qi < g1 && ci < g1 && ci != qi) {
-          // same arithmetic as knn_resident_kernel: sequential fma over the (zero padded) features.  The rows are
+          // exact fp64 distance: sequential fma over the (zero padded) features.  The rows are
           // float32 values, so the fp32 tiles already in shared memory convert to the fp64 operands exactly.
           double acc = 0.0;
 #pragma unroll 4
@@ -637,142 +637,6 @@ __global__ void __launch_bounds__(kKnnThreads, 2) knn_filter_kernel(const double
       knn_d[out + rank] = sqrt(d);
       knn_i[out + rank] = ix;
       if (rank == K - 1) kdist[q0 + ql] = sqrt(d);
-    }
-  }
-}
-
-// dynamic smem: Qs[dpad][64], Cs[dpad][64], Dt[64][65], ld[64][k], li[64][k]
-__global__ void __launch_bounds__(kKnnThreads) knn_resident_kernel(const double* __restrict__ zs,
-                                                                   const int32_t* __restrict__ gstart, int n_groups,
-                                                                   int dpad, int k, const double* __restrict__ sq,
-                                                                   int part, int n_parts, double* __restrict__ knn_d,
-                                                                   int32_t* __restrict__ knn_i,
-                                                                   double* __restrict__ kdist) {
-  extern __shared__ double shk[];
-  double* Qs = shk;
-  double* Cs = Qs + dpad * kKnnTile;
-  double* Dt = Cs + dpad * kKnnTile;
-  double* ld = Dt + kKnnTile * (kKnnTile + 1);
-  int32_t* li = reinterpret_cast<int32_t*>(ld + kKnnTile * k);
-
-  if (static_cast<int>(blockIdx.x % n_parts) != part) return;
-  int tile = blockIdx.x;
-  int g = 0, g0 = 0, g1 = 0;
-  for (; g < n_groups; ++g) {
-    g0 = gstart[g];
-    g1 = gstart[g + 1];
-    const int tiles = (g1 - g0 + kKnnTile - 1) / kKnnTile;
-    if (tile < tiles) break;
-    tile -= tiles;
-  }
-  if (g >= n_groups) return;
-  const int ng = g1 - g0;
-  const int q0 = g0 + tile * kKnnTile;
-  const int K = max(1, min(k, ng - 1));  // _lof.py:293
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < kKnnTile * k; i += kKnnThreads) {
-    ld[i] = INFINITY;
-    li[i] = -1;
-  }
-  // tile loads: thread (r = tid % 64, jp = tid / 64 + 4u) moves features 2jp, 2jp+1 of row r
-  const int lr = tid & 63, ljp = tid >> 6;
-  const int n_u = dpad >> 3;  // double2 loads per thread per tile (dpad is a multiple of 8)
-  constexpr int kMaxU = kKnnMaxResidentDim / 8;
-  {
-    const double* row = zs + static_cast<size_t>(min(q0 + lr, g1 - 1)) * dpad;
-    for (int u = 0; u < n_u; ++u) {
-      const int jp = ljp + 4 * u;
-      const double2 v = *reinterpret_cast<const double2*>(row + 2 * jp);
-      Qs[(2 * jp) * kKnnTile + lr] = v.x;
-      Qs[(2 * jp + 1) * kKnnTile + lr] = v.y;
-    }
-  }
-  double2 pre[kMaxU];
-  auto prefetch = [&](int c0) {
-    const double* row = zs + static_cast<size_t>(min(c0 + lr, g1 - 1)) * dpad;
-#pragma unroll
-    for (int u = 0; u < kMaxU; ++u)
-      if (u < n_u) pre[u] = __ldg(reinterpret_cast<const double2*>(row + 2 * (ljp + 4 * u)));
-  };
-  prefetch(g0);
-  const int ty = tid >> 4, tx = tid & 15;
-  double sqq[4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a) sqq[a] = sq[min(q0 + ty * 4 + a, g1 - 1)];
-
-  for (int c0 = g0; c0 < g1; c0 += kKnnTile) {
-    __syncthreads();  // the previous tile's selection is done with Dt, its FMA block with Cs
-#pragma unroll
-    for (int u = 0; u < kMaxU; ++u)
-      if (u < n_u) {
-        const int jp = ljp + 4 * u;
-        Cs[(2 * jp) * kKnnTile + lr] = pre[u].x;
-        Cs[(2 * jp + 1) * kKnnTile + lr] = pre[u].y;
-      }
-    __syncthreads();
-    if (c0 + kKnnTile < g1) prefetch(c0 + kKnnTile);
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll 8
-    for (int jj = 0; jj < dpad; ++jj) {
-      const double2 qa = *reinterpret_cast<const double2*>(&Qs[jj * kKnnTile + ty * 4]);
-      const double2 qb = *reinterpret_cast<const double2*>(&Qs[jj * kKnnTile + ty * 4 + 2]);
-      const double2 ca = *reinterpret_cast<const double2*>(&Cs[jj * kKnnTile + tx * 4]);
-      const double2 cb = *reinterpret_cast<const double2*>(&Cs[jj * kKnnTile + tx * 4 + 2]);
-      const double q[4] = {qa.x, qa.y, qb.x, qb.y};
-      const double c[4] = {ca.x, ca.y, cb.x, cb.y};
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fma(q[a], c[b], acc[a][b]);
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int ci = c0 + tx * 4 + b;
-      const double sqc = ci < g1 ? sq[ci] : 0.0;
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int qi = q0 + ty * 4 + a;
-        double d2 = INFINITY;
-        if (qi < g1 && ci < g1 && ci != qi) d2 = fmax(sqq[a] + sqc - 2.0 * acc[a][b], 0.0);
-        Dt[(ty * 4 + a) * (kKnnTile + 1) + tx * 4 + b] = d2;
-      }
-    }
-    __syncthreads();
-    // selection: warp w owns queries w*8 .. w*8+7
-    for (int qq = 0; qq < 8; ++qq) {
-      const int ql = warp * 8 + qq;
-      if (q0 + ql >= g1) break;
-      double* qld = ld + ql * k;
-      int32_t* qli = li + ql * k;
-      double tau = qld[K - 1];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const double dc = Dt[ql * (kKnnTile + 1) + half * 32 + lane];
-        unsigned pending = __ballot_sync(0xffffffffu, dc < tau);
-        while (pending) {
-          const int src = __ffs(pending) - 1;
-          pending &= pending - 1;
-          const double dv = __shfl_sync(0xffffffffu, dc, src);
-          if (dv < tau) {
-            list_insert(qld, qli, K, dv, c0 + half * 32 + src, lane);
-            tau = qld[K - 1];
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < kKnnTile * k; i += kKnnThreads) {
-    const int ql = i / k, s = i % k;
-    if (q0 + ql < g1) {
-      knn_d[static_cast<size_t>(q0 + ql) * k + s] = s < K ? sqrt(ld[ql * k + s]) : INFINITY;
-      knn_i[static_cast<size_t>(q0 + ql) * k + s] = s < K ? li[ql * k + s] : -1;
-      if (s == K - 1) kdist[q0 + ql] = sqrt(ld[ql * k + s]);
     }
   }
 }
@@ -1198,29 +1062,13 @@ int irp_lof_knn_part(const float* d_z, int64_t n_rows, int dim, const int32_t* d
                                         reinterpret_cast<unsigned long long*>(max_sq));
   IRP_CUDA_OK(cudaMemsetAsync(d_kdist, 0, n * sizeof(double), st));  // rows of other parts stay 0
   const unsigned knn_grid = static_cast<unsigned>((n + kKnnTile - 1) / kKnnTile + n_groups);
-  static int force_generic = -1;
-  if (force_generic < 0) {
-    const char* e = getenv("IRP_KNN_GENERIC");
-    force_generic = (e && atoi(e) != 0) ? 1 : 0;
-  }
-  if (dim <= kKnnMaxResidentDim && !force_generic) {
+  if (dim <= kKnnMaxResidentDim) {
     const int dpad = (dim + 7) / 8 * 8;
     const long long total = static_cast<long long>(n) * dpad;
     const unsigned gblocks = static_cast<unsigned>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
     float* zs32 = reinterpret_cast<float*>(w.zs + n * dpad);
     gather_sorted_kernel<<<gblocks, 256, 0, st>>>(d_z, w.sr.order, n_rows, dim, dpad, w.zs, zs32);
-    static int exhaustive = -1;  // IRP_KNN_EXHAUSTIVE=1: fp64 evaluation of every pair (A/B runs)
-    if (exhaustive < 0) {
-      const char* e = getenv("IRP_KNN_EXHAUSTIVE");
-      exhaustive = (e && atoi(e) != 0) ? 1 : 0;
-    }
-    if (exhaustive) {
-      const size_t smem = (2 * static_cast<size_t>(dpad) * kKnnTile + kKnnTile * (kKnnTile + 1) +
-                           static_cast<size_t>(kKnnTile) * k) * 8 + static_cast<size_t>(kKnnTile) * k * 4;
-      IRP_TRY(ensure_smem(knn_resident_kernel, smem));
-      knn_resident_kernel<<<knn_grid, kKnnThreads, smem, st>>>(w.zs, w.sr.gstart, n_groups, dpad, k, w.sq, part,
-                                                               n_parts, w.knn_d, w.knn_i, d_kdist);
-    } else {
+    {
       const size_t lists = static_cast<size_t>(kKnnTile) * k * 12 + 8;
       const size_t smem = lists + (static_cast<size_t>(dpad) * (kKnnTile + kFltCand) + kFltCand + kKnnTile) * 4 +
                           8 * kFltCap * 2 + 64 + kKnnTile * 16 + 64;

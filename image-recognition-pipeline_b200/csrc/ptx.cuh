@@ -60,27 +60,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Debug variant: before trapping, the first thread to time out records where it was waiting in MAPPED HOST memory
-// (the context is unusable after the trap, host memory is not): {tag = source line, blockIdx.x, threadIdx.x,
-// parity, user value}.  The record pointer is set by the host (irp_debug_trap_record reads it back).
-static __device__ uint32_t* g_irp_trap_rec = nullptr;
-__device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, uint32_t tag, uint32_t user = 0) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      uint32_t* rec = g_irp_trap_rec;
-      if (rec != nullptr && atomicCAS(rec, 0u, tag) == 0u) {
-        rec[1] = blockIdx.x;
-        rec[2] = threadIdx.x;
-        rec[3] = parity;
-        rec[4] = user;
-        __threadfence_system();
-      }
-      __trap();
-    }
-  }
-}
-
 // ----------------------------------------------------------------------------------------------
 // TMA tiled loads (global -> shared), completion signalled on an mbarrier (complete_tx::bytes)
 // ----------------------------------------------------------------------------------------------

@@ -21,27 +21,7 @@
 
 namespace irp {
 
-constexpr int kStemThreads = 192;
-constexpr int kStemTileW = 8, kStemTileH = 16;             // output pixels per tile (8 x 16 = 128 GEMM rows)
-constexpr int kStemPatchW = 2 * kStemTileW + 6;             // 22 input pixels
-constexpr int kStemPatchH = 2 * kStemTileH + 5;             // 37 input rows
-constexpr int kStemPitch = kStemPatchW * 8;                 // 176 bytes per patch row
-constexpr int kStemPatchBytes = kStemPatchH * kStemPitch;   // 6512
-constexpr int kStemPatchStride = 6656;                      // 128-byte aligned slot
-constexpr int kStemSlots = 6;
 constexpr int kStemWeightBytes = 7 * 2 * 8 * 256;           // (filter row, pixel group) x 8 n-groups x 256 B = 28672
-constexpr int kStemStgBytes = 128 * 128;                    // 128 rows x 64 channels bf16
-constexpr int kStemSmemBytes = kStemWeightBytes + kStemSlots * kStemPatchStride + 2 * kStemStgBytes + 512 + 1024;
-
-struct alignas(64) StemParams {
-  CUtensorMap tmIn;   // (920 elements per row, 230 rows, B images), box (88, 37, 1), no swizzle
-  CUtensorMap tmOut;  // (64, 112, 112, B), box (64, 8, 16, 1), 128B swizzle
-  const __nv_bfloat16* weights;  // kStemWeightBytes, core-matrix order (see stem_fold_kernel)
-  const float* bias;             // [64]
-  int batch;                     // images in this launch
-  int n_base;                    // first image inside tmIn
-  int num_tiles;                 // batch * 14 * 7
-};
 
 // no-swizzle K-major descriptor: LBO = byte distance between the two 16-byte K chunks, SBO = between 8-row groups
 __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -60,161 +40,6 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* desc, ui
       : "memory");
 }
 
-__global__ void __launch_bounds__(kStemThreads, 1) stem_conv_kernel(const __grid_constant__ StemParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* smem_w = smem;                                   // 28 KB weights
-  uint8_t* smem_patch = smem_w + kStemWeightBytes;          // kStemSlots patches
-  uint8_t* smem_stg = smem_patch + kStemSlots * kStemPatchStride;  // 2 staging tiles (1024-aligned: 28672+39936)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + 2 * kStemStgBytes);
-  uint64_t* full_bar = bars;                    // [kStemSlots]
-  uint64_t* empty_bar = bars + kStemSlots;      // [kStemSlots]
-  uint64_t* tfull_bar = bars + 2 * kStemSlots;  // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  constexpr uint32_t kTmemCols = 128;  // 2 x 64 fp32 columns
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmIn);
-    tma_prefetch_desc(&p.tmOut);
-    for (int i = 0; i < kStemSlots; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
-  }
-  // resident weights: plain coalesced copy, then make them visible to the tensor-core (async) proxy
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.weights);
-    uint4* dst = reinterpret_cast<uint4*>(smem_w);
-    for (int i = threadIdx.x; i < kStemWeightBytes / 16; i += kStemThreads) dst[i] = __ldg(src + i);
-    fence_proxy_async();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int tw = tile % 14, th = (tile / 14) % 7, n = tile / 98;
-        mbar_wait(&empty_bar[slot], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[slot], kStemPatchBytes);
-        tma_load_3d(smem_patch + slot * kStemPatchStride, &p.tmIn, &full_bar[slot], 2 * kStemTileW * tw * 4,
-                    2 * kStemTileH * th, n + p.n_base);
-        if (++slot == kStemSlots) {
-          slot = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-      const uint32_t w_addr = smem_u32(smem_w);
-      int slot = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        mbar_wait(&full_bar[slot], phase);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * 64;
-        const uint32_t patch = smem_u32(smem_patch + slot * kStemPatchStride);
-#pragma unroll
-        for (int r = 0; r < 7; ++r) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint64_t da = umma_desc_noswz(patch + r * kStemPitch + h * 32, 16, 2 * kStemPitch);
-            const uint64_t db = umma_desc_noswz(w_addr + (r * 2 + h) * 2048, 128, 256);
-            umma_bf16(tmem_d, da, db, idesc, (r | h) != 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(&empty_bar[slot]);
-        umma_commit(&tfull_bar[acc]);
-        if (++slot == kStemSlots) {
-          slot = 0;
-          phase ^= 1;
-        }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  } else {
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;  // GEMM row = ho_local * 8 + wo_local, also the TMA-store box order
-    const bool leader = (threadIdx.x == 64);
-    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
-    const uint32_t swz = static_cast<uint32_t>(row & 7);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int j = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
-      const int tw = tile % 14, th = (tile / 14) % 7, n = tile / 98;
-      uint8_t* stg = smem_stg + (j & 1) * kStemStgBytes;
-      if (leader) tma_store_wait_read<1>();
-      named_bar_sync(1, 128);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 64 + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32b_x32(taddr + c, v);
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + c);
-        const int piece0 = c >> 3;
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 b0 = __ldg(bp + 2 * i), b1 = __ldg(bp + 2 * i + 1);
-          const float x0 = fmaxf(__uint_as_float(v[8 * i + 0]) + b0.x, 0.f);
-          const float x1 = fmaxf(__uint_as_float(v[8 * i + 1]) + b0.y, 0.f);
-          const float x2 = fmaxf(__uint_as_float(v[8 * i + 2]) + b0.z, 0.f);
-          const float x3 = fmaxf(__uint_as_float(v[8 * i + 3]) + b0.w, 0.f);
-          const float x4 = fmaxf(__uint_as_float(v[8 * i + 4]) + b1.x, 0.f);
-          const float x5 = fmaxf(__uint_as_float(v[8 * i + 5]) + b1.y, 0.f);
-          const float x6 = fmaxf(__uint_as_float(v[8 * i + 6]) + b1.z, 0.f);
-          const float x7 = fmaxf(__uint_as_float(v[8 * i + 7]) + b1.w, 0.f);
-          *reinterpret_cast<uint4*>(stg + row_off + (((piece0 + i) ^ swz) << 4)) =
-              make_uint4(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3), pack_bf16x2(x4, x5), pack_bf16x2(x6, x7));
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
-      fence_proxy_async();
-      named_bar_sync(2, 128);
-      if (leader) {
-        tma_store_4d(&p.tmOut, stg, 0, kStemTileW * tw, kStemTileH * th, n);
-        tma_store_commit();
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-    if (leader) tma_store_wait_all<0>();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // Stem + 3x3/2 max pool fused (conv1/bn1/relu/maxpool of torchvision/models/resnet.py:197-200).

@@ -54,8 +54,6 @@ SIGNATURES = {
     "irp_conv2d_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "irp_conv1x1_chain": (_i, [_vp] * 8 + [_i64, _i, _i, _i, _vp]),
     "irp_conv1x1_chain_ds": (_i, [_vp] * 8 + [_i64, _i, _i, _i, _i, _vp]),
-    "irp_debug_trap_record": (_i, [_vp]),
-    "irp_l1_block": (_i, [_vp] * 10 + [_i, _i, _i, _i, _vp]),
     "irp_cov_workspace_bytes": (_sz, [_i64, _i]),
     "irp_cov_accumulate": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "irp_pca_fit_workspace_bytes": (_sz, [_i, _i]),

@@ -110,7 +110,10 @@ int irp_resnet50_load_conv(irp_resnet50* net, int index, const float* d_weight_o
 /* d_x: IRP_LAYOUT_NHWC4P bf16 batch; d_embed: fp32 [batch,2048] pooled embeddings (the `.squeeze()` of :677). */
 int irp_resnet50_embed(irp_resnet50* net, const void* d_x_nhwc4p, int batch, float* d_embed, void* stream);
 /* Same as irp_resnet50_embed, and additionally copies the NHWC bf16 output of conv `capture_index` (after its
- * fused epilogue) into d_capture_bf16 (parity hook for the per-layer tests). */
+ * fused epilogue) into d_capture_bf16 (parity hook for the per-layer tests).  Index 0 (the stem) yields the tensor
+ * AFTER the 3x3/2 max pool fused into the stem kernel, [batch,56,56,64] (the unpooled stem output never exists).
+ * With a capture every convolution runs as its own launch, including layer1's first shortcut convolution, which
+ * the product path folds into the junction kernel's accumulator (irp_conv1x1_chain_ds has its own parity test). */
 int irp_resnet50_embed_capture(irp_resnet50* net, const void* d_x_nhwc4p, int batch, float* d_embed,
                                int capture_index, void* d_capture_bf16, size_t capacity_elems, void* stream);
 
@@ -138,18 +141,6 @@ int irp_conv1x1_chain(const void* d_t2, const void* d_w3, const float* d_b3, con
 int irp_conv1x1_chain_ds(const void* d_t2, const void* d_x, const void* d_wcat, const float* d_bias, void* d_y,
                          const void* d_w1, const float* d_b1, void* d_t1, int64_t rows, int K1, int K2, int N1, int N2,
                          void* stream);
-
-/* The fused tail of a layer1 bottleneck + head of the next one (l1_block.cuh), exposed for parity tests:
- *   t2 = relu(conv3x3(t1 [B,H,W,64], w2 [64,3,3,64]) + b2)      (kept on chip)
- *   y  [B,H,W,256] = relu(t2 . w3[256,64]^T + b3 + residual [B,H,W,256])
- *   t1_next [B,H,W,N2] = relu(y . w1[N2,256]^T + b1),  N2 in {64,128};  t1_next must not alias t1. */
-int irp_l1_block(const void* d_t1, const void* d_w2, const float* d_b2, const void* d_w3, const float* d_b3,
-                 const void* d_residual, void* d_y, const void* d_w1, const float* d_b1, void* d_t1_next, int B, int H,
-                 int W, int N2, void* stream);
-
-/* Debugging aid: {source line, blockIdx.x, threadIdx.x, parity, user} of the first mbarrier wait that timed out in
- * an instrumented kernel (zeros if none).  Host call, valid even after the launch failure it explains. */
-int irp_debug_trap_record(uint32_t* out5);
 
 /* ------------------------------------------------------------------------------------------------------------
  * A3  PCA  --  replaces PCA(n_components).fit_transform at functions/data_curation.py:700-701 with the exact

@@ -229,42 +229,6 @@ def test_conv1x1_chain_with_folded_shortcut_matches_torch(lib, rows, K1, K2, N1,
     assert ((t1.float() - t1_ref).abs().max() / t1_ref.abs().max()).item() < 6e-3
 
 
-@pytest.mark.parametrize("B,H,N2", [
-    (1, 16, 64),      # one 8x16 tile pair
-    (1, 24, 64),      # 3x2 tiles: ragged bottom row of tiles
-    (3, 56, 64),      # 84 tiles, layer1 geometry
-    (2, 56, 128),     # layer1 -> layer2 junction
-    (37, 56, 64),     # 1036 tiles: seven tile pairs per CTA pair (ring / accumulator recycling)
-    (37, 56, 128),    # same with the 4-buffer ring of the N2 = 128 variant (once a producer/MMA deadlock)
-])
-def test_l1_block_matches_torch(lib, B, H, N2):
-    """conv2 (3x3) + conv3 + residual + next conv1 in one launch (l1_block.cuh) against fp32 torch; the on-chip
-    intermediates are rounded to bf16 where the kernel rounds them."""
-    from irp_b200 import _lib
-    g = torch.Generator(device="cuda").manual_seed(B * 100 + H + N2)
-    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
-    t1 = rn(B, H, H, 64).relu().bfloat16()
-    w2 = (rn(64, 3, 3, 64) / 24).bfloat16()
-    b2 = rn(64) * 0.5
-    w3 = (rn(256, 64) / 8).bfloat16()
-    b3 = rn(256) * 0.5
-    res = rn(B, H, H, 256).bfloat16()
-    w1 = (rn(N2, 256) / 16).bfloat16()
-    b1 = rn(N2) * 0.5
-    y = torch.full((B, H, H, 256), float("nan"), device="cuda").bfloat16()
-    t1n = torch.full((B, H, H, N2), float("nan"), device="cuda").bfloat16()
-    _lib.check(lib.irp_l1_block(_ptr(t1), _ptr(w2), _ptr(b2), _ptr(w3), _ptr(b3), _ptr(res), _ptr(y), _ptr(w1),
-                                _ptr(b1), _ptr(t1n), B, H, H, N2, _stream()), "irp_l1_block")
-    torch.cuda.synchronize()
-    t2 = F.conv2d(t1.float().permute(0, 3, 1, 2), w2.float().permute(0, 3, 1, 2), b2, padding=1).relu()
-    t2 = t2.permute(0, 2, 3, 1).bfloat16().float()                       # the kernel keeps T2 as bf16
-    y_ref = (t2 @ w3.float().t() + b3 + res.float()).relu()
-    assert not torch.isnan(y.float()).any() and not torch.isnan(t1n.float()).any()
-    assert ((y.float() - y_ref).abs().max() / y_ref.abs().max()).item() < 8e-3
-    t1_ref = (y.float() @ w1.float().t() + b1).relu()                      # from the kernel's own bf16 Y
-    assert ((t1n.float() - t1_ref).abs().max() / t1_ref.abs().max()).item() < 6e-3
-
-
 def test_conv2d_rejects_unsupported_shapes(lib):
     x = torch.zeros(1, 8, 8, 48, device="cuda", dtype=torch.bfloat16)
     st = lib.irp_conv2d_nhwc(_ptr(x), _ptr(x), _ptr(x), None, _ptr(x), 1, 8, 8, 48, 64, 1, 1, 0, _stream())
@@ -298,7 +262,11 @@ def test_embeddings_match_reference_golden(trunk):
 
 
 def test_trunk_matches_torchvision_per_layer(lib, trunk):
-    """Every conv's fused output (bias/ReLU/residual epilogue) against torchvision evaluated in fp32 on the GPU."""
+    """Every conv's fused output (bias/ReLU/residual epilogue) against torchvision evaluated in fp32 on the GPU.
+    Index 0 is compared after the max pool (the stem kernel fuses it; the unpooled tensor never exists).  With a
+    capture every conv runs as its own launch: layer1's first shortcut conv, which the product path folds into the
+    junction kernel, is covered by test_conv1x1_chain_with_folded_shortcut_matches_torch and, end to end, by the
+    golden-embedding test."""
     from irp_b200 import _lib
     from irp_b200.stage import conv_bn_pairs
     m = stage_ref.full_resnet50(seed=1234).cuda()
@@ -309,9 +277,8 @@ def test_trunk_matches_torchvision_per_layer(lib, trunk):
     xp[:, 3:227, 3:227, :3] = x.permute(0, 2, 3, 1)
     feats = {}
     with torch.no_grad():
-        t = m.relu(m.bn1(m.conv1(x.float())))
+        t = m.maxpool(m.relu(m.bn1(m.conv1(x.float()))))
         feats[0] = t
-        t = m.maxpool(t)
         idx = 1
         for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
             for blk in layer:
