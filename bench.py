@@ -192,7 +192,6 @@ def make_workload(n, seed, device):
     from oracle import synth
 
     hw = synth.mixed_resolution_sizes(n, seed=seed)
-    hw = np.minimum(hw, 1200)  # keep the rare large images bounded so the step stays seconds long
     ids = synth.class_assignment(n, seed=seed)
     nbytes = hw[:, 0].astype(np.int64) * hw[:, 1] * 3
     padded = (nbytes + ALIGN - 1) // ALIGN * ALIGN

@@ -40,6 +40,7 @@ SIGNATURES = {
     "irp_preprocess_geometry": (_i, [_i, _i] + [C.POINTER(_i)] * 5),
     "irp_preprocess_workspace_bytes": (_sz, [_i, _i]),
     "irp_preprocess": (_i, [_vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _i, _vp]),
+    "irp_preprocess_status": (_i, [_vp, _i, _i, _vp]),
     "irp_preprocess_ex": (_i, [_vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _i, _i, _vp]),
     "irp_preprocess_geometry_ex": (_i, [_i, _i, _i] + [C.POINTER(_i)] * 5),
     "irp_classifier_head_workspace_bytes": (_sz, [_i, _i]),

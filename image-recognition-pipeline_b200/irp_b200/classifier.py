@@ -63,7 +63,10 @@ class B200Classifier:
     def predict_packed(self, packed: PackedImages, from_host: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """Decoded uint8 images (stage.pack_images(images, transform=_lib.TRANSFORM_VAL_256)) -> (logits, argmax):
         val_transform + backbone + head, every step a libirp_b200 kernel."""
+        from .stage import taps_for
         n = len(packed)
+        # the tap bound of THIS transform (a PackedImages built for the embedding transform carries a smaller one)
+        taps = max((taps_for(int(h), int(w), _lib.TRANSFORM_VAL_256) for h, w in packed.hw_np), default=3)
         logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
         pred = torch.empty((n,), dtype=torch.int32, device=self.device)
         for lo in range(0, n, self.max_batch):
@@ -71,7 +74,7 @@ class B200Classifier:
             part = packed.slice(lo, hi)
             if from_host or not part.pixels.is_cuda:
                 part = part.to(self.device)
-            x = ops.preprocess_ex(part.pixels, part.offsets, part.hw, packed.max_taps, _lib.LAYOUT_NHWC4P,
+            x = ops.preprocess_ex(part.pixels, part.offsets, part.hw, taps, _lib.LAYOUT_NHWC4P,
                                   _lib.TRANSFORM_VAL_256)
             lg, pr = self.head(self.trunk.embed(x))
             logits[lo:hi] = lg

@@ -66,9 +66,15 @@ enum { IRP_CROP = 224, IRP_RESIZE = 232, IRP_PAD_HW = 230 };
 /* Host-only helper: resized size, crop offsets and the tap bound (2*ceil(max(scale,1))+1) for one h x w image. */
 int irp_preprocess_geometry(int h, int w, int* out_h, int* out_w, int* top, int* left, int* taps);
 size_t irp_preprocess_workspace_bytes(int n_images, int max_taps);
+/* d_pixels must be 16-byte aligned, every d_offsets[i] a multiple of 16, and the buffer readable up to the next
+ * 16-byte boundary after each image's last byte (source rows are staged with 16-byte copies). */
 int irp_preprocess(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
                    int max_taps, void* d_workspace, size_t workspace_bytes, void* d_out, int out_layout,
                    void* stream);
+
+/* Synchronises `stream` and returns IRP_ERR_INVALID if the preceding irp_preprocess(_ex) call on the same
+ * workspace found max_taps too small for an image (such a call writes NaN instead of truncated-filter pixels). */
+int irp_preprocess_status(const void* d_workspace, int n_images, int max_taps, void* stream);
 
 /* The same kernels with the resize geometry selected by `transform`:
  *   IRP_TRANSFORM_WEIGHTS_DEFAULT  ResNet50_Weights.DEFAULT.transforms() (above; what irp_preprocess uses)

@@ -868,10 +868,10 @@ def test_wds_lanczos_resize_bit_exact(ops_mod, lib):
     assert np.array_equal(np.asarray(got), pil_resample.wds_transform_u8(np.asarray(bg)))
 
 
-def test_bilinear_images_with_7_to_16_taps_take_the_two_pass_path_bit_exact(ops_mod):
-    """Downscales by 2.5x-7x (7 to 16 taps) used to go through the band kernel; up to 16 taps / 640 source rows they
-    now run on the two-pass path, beyond that still the band kernel -- all bit-exact with the reference transform."""
-    sizes = [(600, 640), (650, 900), (700, 700), (1200, 1210), (1700, 1650), (233, 3000)]
+def test_bilinear_many_tap_images_bit_exact(ops_mod):
+    """Downscales by 2.5x-13x (7 to 27 horizontal / vertical taps): the fused kernel's generic horizontal loop and
+    its narrower bands (16 ... 2 output rows per item) -- all bit-exact with the reference transform."""
+    sizes = [(600, 640), (650, 900), (700, 700), (1200, 1210), (1700, 1650), (233, 3000), (2600, 2500), (3000, 240)]
     imgs = [np.random.default_rng(90 + i).integers(0, 256, (h, w, 3), dtype=np.uint8) for i, (h, w) in enumerate(sizes)]
     assert torch.equal(_preprocess(ops_mod, imgs, 0).cpu(), _expected_bf16(imgs))
     assert torch.equal(_preprocess(ops_mod, imgs, 1).cpu()[:, 3:227, 3:227, :3], _expected_bf16(imgs).permute(0, 2, 3, 1))
