@@ -1,13 +1,16 @@
 """Benchmark of the B200 outlier-detection stage (BASELINE.json: images/sec for embed + PCA + outlier-score).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3_strong|cfg4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-One "step" = one pass of the whole hot path over the workload of BASELINE.json configs[1]: 27 000 synthetic
-mixed-resolution uint8 images (~300x400) -> fused preprocess -> ResNet-50 embeddings (batch 256, bf16) -> PCA(50)
--> per-class + global LOF.  With N GPUs every rank processes its own 27 000 images (weak scaling); the PCA
-partial sums are all-reduced once and the projected rows gathered for scoring.
+One "step" = one pass of the whole hot path over the workload.  The default (--config cfg2) is BASELINE.json
+configs[1]: 27 000 synthetic mixed-resolution uint8 images (~300x400, with the rare >= 1500 px ones) -> fused
+preprocess -> ResNet-50 embeddings (batch 256, bf16) -> PCA(50) -> per-class + global LOF.  With N GPUs every rank
+processes its own 27 000 images (weak scaling); the PCA partial sums are all-reduced once and the projected rows
+gathered for scoring.  --config cfg3_strong is configs[2] (the SAME 27 000 images sharded over the N ranks, strong
+scaling); --config cfg4 is configs[3] (125 000 synthetic 224x224 images per GPU = 1 M on 8 GPUs, batch 512,
+PCA(128), global scorer only).  Every line also carries the per-phase times of one extra traced step.
 
 Rank 0 prints ONE JSON line.  `value` is measured with the inputs resident in HBM; `e2e` runs the same step from
 pinned host buffers (H2D of every batch and D2H of features / projection / flags inside the timed region).
@@ -59,13 +62,8 @@ import torch  # noqa: E402
 
 METRIC = "images/sec embed+PCA+outlier-score"
 UNIT = "images/s"
-N_IMAGES = 27000
-BATCH = 256
-PCA_K = 50
 N_CLASSES = 10
 FLOPS_PER_IMAGE = 8.1743e9  # 53 convolutions of the ResNet-50 trunk
-WORKLOAD = ("configs[1]: Animals-10-sized synthetic set, 27,000 mixed-resolution uint8 images (~300x400) per GPU -> "
-            "preprocess, ResNet50 embed (bf16, batch 256), PCA(50), LOF per-class(k=30,5%) + global(k=75,3%)")
 
 
 def load_peaks():
@@ -183,29 +181,72 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------------------
-# synthetic workload
+# workload configurations
 # --------------------------------------------------------------------------------------------------------------
-def make_workload(n, seed, device):
-    """Packed uint8 HWC images generated ON THE DEVICE (smooth 8x8 base upsampled + noise + class tint), class ids.
-    Sizes follow oracle/synth.py (mixed resolution around 300x400, ~45 % with a side < 224)."""
-    from irp_b200.stage import ALIGN, PackedImages, taps_for
-    from oracle import synth
+CONFIGS = {
+    # BASELINE.json configs[1] (the line the driver reads): weak scaling, 27 000 images per GPU
+    "cfg2": dict(images_per_gpu=27000, total=None, batch=256, k=50, class_scoring=True, sizes="mixed",
+                 scaling="weak",
+                 workload="configs[1]: Animals-10-sized synthetic set, 27,000 mixed-resolution uint8 images (~300x400, "
+                          "42 % with a side < 224, 0.2 % of 1500-2600 px) per GPU -> preprocess, ResNet50 embed (bf16, "
+                          "batch 256), PCA(50), LOF per-class(k=30,5%) + global(k=75,3%)"),
+    # configs[2]: the same 27 000 images sharded over the ranks
+    "cfg3_strong": dict(images_per_gpu=None, total=27000, batch=256, k=50, class_scoring=True, sizes="mixed",
+                        scaling="strong",
+                        workload="configs[2]: the 27,000-image Animals-10-sized set of configs[1] sharded over the GPUs "
+                                 "(contiguous ranges), one all-reduce of the PCA partial sums, PCA(50), LOF per-class + "
+                                 "global"),
+    # configs[3]: 1 M images on 8 GPUs = 125 000 per GPU
+    "cfg4": dict(images_per_gpu=125000, total=None, batch=512, k=128, class_scoring=False, sizes="224",
+                 scaling="weak",
+                 workload="configs[3]: scale-out, 125,000 synthetic 224x224 uint8 images per GPU (1 M on 8 GPUs) -> "
+                          "preprocess, ResNet50 embed (bf16, batch 512), PCA(128), global LOF(k=75,3%) only"),
+}
 
-    hw = synth.mixed_resolution_sizes(n, seed=seed)
-    ids = synth.class_assignment(n, seed=seed)
+
+def workload_sizes(cfg, n, seed):
+    from oracle import synth
+    if cfg["sizes"] == "224":
+        return np.full((n, 2), 224, np.int32), synth.class_assignment(n, seed=seed)
+    return synth.mixed_resolution_sizes(n, seed=seed), synth.class_assignment(n, seed=seed)
+
+
+def make_workload(n, seed, device, cfg=None, lo=0, hi=None):
+    """Packed uint8 HWC images generated ON THE DEVICE (smooth 8x8 base upsampled + noise + class tint), class ids.
+    Sizes follow oracle/synth.py (mixed resolution around 300x400, ~42 % with a side < 224, 0.2 % of 1500-2600 px)
+    or are all 224x224 (configs[3]).  [lo, hi) selects this rank's contiguous share of the n images."""
+    from irp_b200.stage import ALIGN, PackedImages, taps_for
+
+    cfg = cfg or CONFIGS["cfg2"]
+    hw, ids = workload_sizes(cfg, n, seed)
+    hi = n if hi is None else hi
+    hw, ids = hw[lo:hi], ids[lo:hi]
+    m = hi - lo
     nbytes = hw[:, 0].astype(np.int64) * hw[:, 1] * 3
     padded = (nbytes + ALIGN - 1) // ALIGN * ALIGN
     offsets = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
     total = int(padded.sum())
     pixels = torch.empty(total, dtype=torch.uint8, device=device)
-    g = torch.Generator(device=device).manual_seed(seed)
-    for i in range(n):
-        h, w = int(hw[i, 0]), int(hw[i, 1])
-        base = torch.rand(1, 3, 8, 8, device=device, generator=g) * 255.0
-        img = torch.nn.functional.interpolate(base, size=(h, w), mode="bilinear", align_corners=False)[0]
-        img = img + torch.randn(3, h, w, device=device, generator=g) * 12.0 + 5.0 * float(ids[i])
-        pixels[offsets[i]:offsets[i] + nbytes[i]] = img.clamp_(0, 255).permute(1, 2, 0).reshape(-1).to(torch.uint8)
-    taps = max(taps_for(int(h), int(w)) for h, w in hw)
+    g = torch.Generator(device=device).manual_seed(seed * 1000003 + lo)
+    if cfg["sizes"] == "224":
+        ids_t = torch.from_numpy(ids).to(device)
+        per = 224 * 224 * 3
+        view = pixels.view(m, per)
+        for s in range(0, m, 1024):
+            e = min(m, s + 1024)
+            base = torch.rand(e - s, 3, 8, 8, device=device, generator=g) * 255.0
+            img = torch.nn.functional.interpolate(base, size=(224, 224), mode="bilinear", align_corners=False)
+            img = img + torch.randn(e - s, 3, 224, 224, device=device, generator=g) * 12.0
+            img = img + 5.0 * ids_t[s:e].float().view(-1, 1, 1, 1)
+            view[s:e] = img.clamp_(0, 255).permute(0, 2, 3, 1).reshape(e - s, per).to(torch.uint8)
+    else:
+        for i in range(m):
+            h, w = int(hw[i, 0]), int(hw[i, 1])
+            base = torch.rand(1, 3, 8, 8, device=device, generator=g) * 255.0
+            img = torch.nn.functional.interpolate(base, size=(h, w), mode="bilinear", align_corners=False)[0]
+            img = img + torch.randn(3, h, w, device=device, generator=g) * 12.0 + 5.0 * float(ids[i])
+            pixels[offsets[i]:offsets[i] + nbytes[i]] = img.clamp_(0, 255).permute(1, 2, 0).reshape(-1).to(torch.uint8)
+    taps = max(taps_for(int(h), int(w)) for h, w in np.unique(hw, axis=0))
     packed = PackedImages(pixels, torch.from_numpy(offsets).to(device), torch.from_numpy(hw).to(device), taps,
                           offsets, hw)
     return packed, torch.from_numpy(ids), hw
@@ -218,10 +259,24 @@ def algorithmic_preprocess_bytes(hw):
     return float((window + 3 * 224 * 224 * 2).sum())
 
 
+def config_dict(cfg_name, world):
+    """The `config` object of the JSON line; the reference arm prints the SAME object for the same --config / N."""
+    cfg = CONFIGS[cfg_name]
+    n_total = cfg["total"] if cfg["total"] is not None else cfg["images_per_gpu"] * world
+    return {"workload": cfg["workload"], "name": cfg_name, "images_total": n_total,
+            "images_per_gpu": cfg["images_per_gpu"] if cfg["images_per_gpu"] is not None else f"{n_total}/N (contiguous)",
+            "batch": cfg["batch"], "pca_components": cfg["k"], "classes": N_CLASSES,
+            "scorers": "per-class LOF + global LOF" if cfg["class_scoring"] else "global LOF",
+            "weights": "random-init torchvision resnet50 (seed 1234)",
+            "l2": "inputs (GBs per GPU) and activations larger than the 126 MB L2; no explicit flush",
+            "parallelism": f"dp{world}: images sharded, one all-reduce of the PCA partial sums, all-gather of the "
+                           "projected rows, three all-reduces of the sharded LOF"}
+
+
 # --------------------------------------------------------------------------------------------------------------
 # reference arm (CPU)
 # --------------------------------------------------------------------------------------------------------------
-def cpu_stage_sample(images, labels, k):
+def cpu_stage_sample(images, labels, k, class_scoring=True):
     """The reference route on the host for a bounded sample: embed (batch 32) + PCA + detect_outliers."""
     import warnings
 
@@ -236,36 +291,46 @@ def cpu_stage_sample(images, labels, k):
     return time.perf_counter() - t0
 
 
-def host_sample(n, seed):
+def host_sample(n, seed, cfg=None):
     from oracle import synth
 
+    cfg = cfg or CONFIGS["cfg2"]
     rng = np.random.default_rng(seed)
-    hw = synth.mixed_resolution_sizes(n, seed=seed)
-    ids = synth.class_assignment(n, seed=seed)
+    hw, ids = workload_sizes(cfg, n, seed)
+    hw = np.minimum(hw, 1400)  # host sample only: a 2600 px synthetic image costs seconds to GENERATE on the CPU
     images = [synth.smooth_image(rng, int(h), int(w), int(c)) for (h, w), c in zip(hw, ids)]
     return images, np.array([f"class{c}" for c in ids])
 
 
+REFERENCE_SAMPLE = 1024  # images per step of the CPU arm (time a >= 1 024-image sample)
+
+
 def run_reference(args, rank, world):
+    """The reference's CPU route (oracle/stage_ref.py: the same torchvision / sklearn calls as
+    functions/data_curation.py:654-728) on ALL host cores, whatever launched this process; rank 0 only."""
     if rank != 0:
         return
-    sample = 192
-    images, labels = host_sample(sample, seed=0)
-    cores = torch.get_num_threads()
+    cores = host_cores()
+    torch.set_num_threads(cores)
+    cfg = CONFIGS[args.config]
+    sample = REFERENCE_SAMPLE
+    images, labels = host_sample(sample, seed=0, cfg=cfg)
     warm_labels = np.array([f"class{i % 2}" for i in range(32)])  # two classes of 16: LOF needs >= 2 rows each
-    for _ in range(args.warmup):
-        cpu_stage_sample(images[:32], warm_labels, PCA_K)
-    times = [cpu_stage_sample(images, labels, PCA_K) for _ in range(args.steps)]
+    for _ in range(min(args.warmup, 2)):
+        cpu_stage_sample(images[:32], warm_labels, cfg["k"])
+    times = [cpu_stage_sample(images, labels, cfg["k"]) for _ in range(args.steps)]
     sec = sum(times) / len(times)
     value = sample / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_per_step": sample, "batch": 32, "pca_components": PCA_K},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} images of the same workload per step: PIL transform + torchvision "
-                                   f"ResNet-50 fp32 (batch 32) + sklearn PCA + LocalOutlierFactor on {cores} threads "
+        "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args.config, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "host_cores": cores,
+                         "sample": f"{sample} images of the same workload per step (warm-up steps: 32 images): PIL "
+                                   f"transform + torchvision ResNet-50 fp32 (batch 32) + sklearn PCA({cfg['k']}) + "
+                                   f"LocalOutlierFactor on {sample} rows, {torch.get_num_threads()} threads "
                                    "(oracle/stage_ref.py restates functions/data_curation.py:654-728 with the same "
                                    "library calls; /root/reference is not present on the GPU box)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -288,9 +353,9 @@ class TimedBackend:
         self.enabled = False
 
     def __getattr__(self, name):
-        # everything that is not timed here (cov_accumulate, pca_fit, pca_transform, lof, lof_sharded, ...) is the
-        # product backend's own method -- in particular lof_sharded, without which a multi-rank run would fall back
-        # to every rank searching all rows
+        # everything that is not timed here (cov_accumulate, pca_fit, pca_transform, lof, lof_sharded_multi, ...) is
+        # the product backend's own method -- in particular the sharded LOF, without which a multi-rank run would fall
+        # back to every rank searching all rows
         return getattr(self.inner, name)
 
     def embed(self, part, max_taps):
@@ -307,36 +372,41 @@ class TimedBackend:
         return out
 
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the 46 kernels of ONE irp_resnet50_embed call at batch 256,
-# from the ncu pass committed as profiles/r01_ncu_trunk_traffic_v6.csv (5 411 MB read + 3 282 MB written; the pass
-# captured 49 launches across two calls, profiles/r01_trunk_layer_table_v6.md lists the 46 of one call).
-TRUNK_DRAM_BYTES_PER_CALL = 8.694e9
+def measured_traffic(name):
+    """DRAM bytes per launch group from the committed ncu summary (profiles/r02_traffic.json, written by
+    tools/traffic_summary.py from an ncu dram__bytes_read.sum + dram__bytes_write.sum pass); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f)
+    e = t.get(name)
+    return (e["bytes"], e["source"]) if e else (None, None)
 
 
-def launches_per_step(n_images, batch, dim, max_taps):
+def launches_per_step(n_images, batch, dim, k, class_scoring):
     """Kernels of libirp_b200.so launched per step (counted from the launch sites in csrc/*.cu)."""
     batches = (n_images + batch - 1) // batch
-    pre = 3 + (1 if max_taps > 6 else 0)  # resample_plan + horizontal pass + vertical pass (+ many-tap path)
+    pre = 2                      # resample_plan (taps + band schedule) + resample_fused
     trunk = 46                   # stem+pool, 16 3x3, 3 downsample, 9 conv1, 9 conv3, 7 chained conv3+conv1 (the first
                                  # with the layer1 shortcut conv folded in), avgpool
     per_batch = pre + trunk
-    cov = 3                      # split_transpose, add_count, cov_gemm
-    k = PCA_K
+    cov = 4                      # split_transpose, col_sum_reduce, add_count, cov_gemm
     lanczos_steps = max(3 * k + 10, 96)  # first convergence check; the bench data converges there
-    # assemble, start vector, 5 kernels per step, close, bisect, inverse iteration, mgs, residual, Ritz, sign, clip
-    fit = 2 + 5 * lanczos_steps + 1 + 4 + 2 + 1 if dim >= 512 and 8 * k <= dim else 1 + (dim - 1) + 6
-    transform = 1
+    # assemble, trace, start vector, 5 kernels per step, close, bisect, inverse iteration, mgs, residual, Ritz, sign, clip
+    fit = 3 + 5 * lanczos_steps + 1 + 4 + 2 + 1 if dim >= 512 and 8 * k <= dim else 2 + (dim - 1) + 6
+    transform = 2                # projection operands + tcgen05 projection GEMM
     # iota/count/scan/scatter (grouped only), sort key + radix sort (4 CUB passes + histogram), sqnorm, gather,
     # knn, lrd, score, unsort, percentile, flag
     lof_global = 1 + 1 + 5 + 8
     lof_grouped = 3 + lof_global
-    return batches * per_batch + cov + fit + transform + lof_grouped + lof_global
+    return batches * per_batch + cov + fit + transform + (lof_grouped if class_scoring else 0) + lof_global
 
 
 def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
 
-    from irp_b200.stage import CudaBackend, OutlierStage, ResNet50Trunk
+    from irp_b200.stage import CudaBackend, OutlierStage, ResNet50Trunk, shard_range
     from oracle import stage_ref  # weights only: the seeded random-init torchvision module (no network)
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (the CUDA path has no CPU fallback)"
@@ -345,11 +415,20 @@ def run_ours(args, rank, local_rank, world):
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
+    cfg = CONFIGS[args.config]
+    batch, k = cfg["batch"], cfg["k"]
 
-    packed, ids, hw = make_workload(N_IMAGES, seed=rank, device=dev)
-    trunk = ResNet50Trunk(stage_ref.full_resnet50(seed=1234), dev, max_batch=BATCH)
+    if cfg["total"] is not None:  # strong scaling: this rank's contiguous share of the SAME image set
+        lo, hi = shard_range(cfg["total"], rank, world)
+        packed, ids, hw = make_workload(cfg["total"], seed=0, device=dev, cfg=cfg, lo=lo, hi=hi)
+        n_total = cfg["total"]
+    else:
+        packed, ids, hw = make_workload(cfg["images_per_gpu"], seed=rank, device=dev, cfg=cfg)
+        n_total = cfg["images_per_gpu"] * world
+    n_local = len(packed)
+    trunk = ResNet50Trunk(stage_ref.full_resnet50(seed=1234), dev, max_batch=batch)
     backend = TimedBackend(CudaBackend(trunk))
-    stage = OutlierStage(backend, batch_size=BATCH, pca_components=PCA_K)
+    stage = OutlierStage(backend, batch_size=batch, pca_components=k, class_scoring=cfg["class_scoring"])
 
     def barrier():
         torch.cuda.synchronize()
@@ -360,7 +439,7 @@ def run_ours(args, rank, local_rank, world):
     def step(from_host=False, src=None):
         res = stage.run(src if src is not None else packed, ids, N_CLASSES, from_host=from_host)
         if from_host:  # what process_image_directory / detect_outliers hand back to the host
-            out = (stage.to_host(res.features, "features"), stage.to_host(res.z[: len(packed)], "z"),
+            out = (stage.to_host(res.features, "features"), stage.to_host(res.z, "z"),
                    stage.to_host(res.class_outliers, "class_flags"), stage.to_host(res.global_outliers, "global_flags"))
             return res, out
         # Every step ends with the host waiting for its result (the drop-in returns the flags to the caller).  Without
@@ -371,12 +450,12 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- value: inputs resident in HBM ----
     sampler = ClockSampler(local_rank)
-    if rank == 0 and os.environ.get("IRP_BENCH_NO_SAMPLER", "0") == "0":
+    if rank == 0 and not args.no_clock_sampler:
         sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    backend.enabled = os.environ.get("IRP_BENCH_NO_EVENTS", "0") == "0"
+    backend.enabled = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.begin()
@@ -391,16 +470,12 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     backend.enabled = False
     per_step_ms = [round(a.elapsed_time(b), 2) for a, b in zip(step_marks[:-1], step_marks[1:])]
-    if getattr(stage, "traces", None):
-        for i, tr in enumerate(stage.traces):
-            print(f"[trace rank {rank}] step {i}: {tr}", file=sys.stderr, flush=True)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / args.steps
-    n_total = N_IMAGES * world
     value = n_total / (ms_step * 1e-3)
 
     pre_ms = sum(e[0].elapsed_time(e[1]) for e, _ in backend.events)
@@ -412,11 +487,24 @@ def run_ours(args, rank, local_rank, world):
         mine = torch.tensor([(pre_ms + emb_ms) / args.steps], dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        rank_embed_ms = [round(float(t.item()), 3) for t in allr]
+        rank_embed_ms = [round(float(v.item()), 3) for v in allr]
     n_emb = sum(n for _, n in backend.events)
     calls = len(backend.events)
     conv_tflops = FLOPS_PER_IMAGE * n_emb / (max(emb_ms, 1e-9) * 1e-3) / 1e12
     pre_gbs = algorithmic_preprocess_bytes(hw) * args.steps / (max(pre_ms, 1e-9) * 1e-3) / 1e9
+
+    # ---- one extra traced step (synchronised after every phase; outside every timed region) ----
+    stage.trace = True
+    stage.traces = []
+    step()
+    stage.trace = False
+    phase_ms = dict(stage.traces[-1]) if stage.traces else None
+    if phase_ms is not None and world > 1:  # the slowest rank's view of every phase
+        keys = sorted(phase_ms)
+        v = torch.tensor([phase_ms[q] for q in keys], dtype=torch.float64, device=dev)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        phase_ms = {q: round(float(x), 2) for q, x in zip(keys, v.tolist())}
+    barrier()
 
     # ---- e2e: pinned host buffers, copies inside the timed region ----
     host = None
@@ -448,43 +536,46 @@ def run_ours(args, rank, local_rank, world):
                "d2h_bytes_per_step": d2h}
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sample = 384
-        images, labels = host_sample(sample, seed=0)
-        sec = cpu_stage_sample(images, labels, PCA_K)
+        torch.set_num_threads(host_cores())
+        sample = 1024
+        images, labels = host_sample(sample, seed=0, cfg=cfg)
+        sec = cpu_stage_sample(images, labels, k)
         cpu = {"value": sample / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{sample} images of the same workload, once: PIL transform + torchvision ResNet-50 fp32 "
                          f"(batch 32) + sklearn PCA + LocalOutlierFactor (oracle/stage_ref.py) in {sec:.1f} s"}
+    trunk_traffic, trunk_src = measured_traffic("trunk_call_batch256")
+    pre_traffic, pre_src = measured_traffic("preprocess_call_batch256")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_gpu": N_IMAGES, "batch": BATCH, "pca_components": PCA_K,
-                   "classes": N_CLASSES, "weights": "random-init torchvision resnet50 (seed 1234)",
-                   "l2": f"inputs ({packed.pixels.numel() / 1e9:.1f} GB per GPU) and activations larger than L2; "
-                         "no explicit flush",
-                   "parallelism": f"dp{world}: images sharded, one all-reduce of the PCA partial sums"},
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": config_dict(args.config, world),
         "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": conv_tflops / peaks["tflops_sustained"], "traffic": TRUNK_DRAM_BYTES_PER_CALL,
-                     "traffic_source": "ncu dram__bytes_read+write over the 46 kernels of one trunk call, "
-                                       "profiles/r01_ncu_trunk_traffic_v6.csv",
+                     "frac": conv_tflops / peaks["tflops_sustained"],
+                     "traffic": trunk_traffic if batch == 256 else None, "traffic_source": trunk_src,
                      "kernel": "conv_gemm2_kernel / conv_chain_kernel / conv3x3_c64_kernel / stem_pool_kernel (the 53 "
-                               "convolutions of one irp_resnet50_embed call, batch 256)",
-                     "per_launch": f"{FLOPS_PER_IMAGE:.4e} FLOP/image x {BATCH} images per trunk call; "
+                               f"convolutions of one irp_resnet50_embed call, batch {batch})",
+                     "per_launch": f"{FLOPS_PER_IMAGE:.4e} FLOP/image x {batch} images per trunk call; "
                                    f"{calls} calls timed with CUDA events, mean {emb_ms / max(calls, 1):.3f} ms",
                      "peak_source": f"{peaks['source']} bf16_tflops_sustained"},
         "roofline_preprocess": {"bound": "hbm", "achieved": pre_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                "frac": pre_gbs / peaks["hbm_gbs"], "traffic": None,
-                                "kernel": "hpass_kernel + vpass_kernel (+ resample_plan_kernel)",
-                                "per_launch": "3*ceil(224/232*short)^2 source bytes + 301056 output bytes per image"},
+                                "frac": pre_gbs / peaks["hbm_gbs"],
+                                "traffic": pre_traffic if batch == 256 else None, "traffic_source": pre_src,
+                                "kernel": "resample_fused_kernel (+ resample_plan_kernel)",
+                                "per_launch": "3*ceil(224/232*short)^2 source bytes + 301056 output bytes per image; "
+                                              f"{calls} calls timed with CUDA events, mean "
+                                              f"{pre_ms / max(calls, 1) * 1e3:.1f} us"},
         "stage_ms": {"preprocess": pre_ms / args.steps, "trunk": emb_ms / args.steps,
                      "pca_lof_other": ms_step - (pre_ms + emb_ms) / args.steps,
-                     "embed_per_rank": rank_embed_ms, "per_step": per_step_ms},
+                     "embed_per_rank": rank_embed_ms, "per_step": per_step_ms,
+                     "phases_of_one_traced_step": phase_ms},
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": launches_per_step(N_IMAGES, BATCH, 2048, packed.max_taps) * args.steps,
+        "gpu_launches": launches_per_step(n_local, batch, 2048, k, cfg["class_scoring"]) * args.steps,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -497,7 +588,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -83,7 +83,7 @@ int ensure_smem(const void* func, size_t bytes) {
   // kernel attributes are per device: remember the limit already granted per (device, kernel)
   static std::mutex mu;
   static std::map<std::pair<int, const void*>, size_t> granted;
-  if (bytes <= 48 * 1024) return IRP_OK;
+  if (bytes <= 32 * 1024) return IRP_OK;  // static shared memory counts against the 48 KB default limit too
   int dev = 0;
   IRP_CUDA_OK(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lock(mu);

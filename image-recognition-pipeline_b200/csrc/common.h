@@ -51,7 +51,7 @@ int encode_bf16_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims
 // SM count of the CURRENT device (cached per device).
 int num_sms();
 
-// Opt the kernel `func` in to `bytes` of dynamic shared memory on the CURRENT device (no-op up to 48 KB; cached per
+// Opt the kernel `func` in to `bytes` of dynamic shared memory on the CURRENT device (no-op up to 32 KB; cached per
 // (device, kernel), so a second GPU in the same process gets its own opt-in).
 int ensure_smem(const void* func, size_t bytes);
 template <typename K>

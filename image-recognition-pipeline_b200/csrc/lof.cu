@@ -942,6 +942,14 @@ static int sort_rows(const int32_t* d_group, long long n, int n_groups, uint8_t*
     group_count_kernel<<<1, kSortThreads, 0, st>>>(d_group, n, n_groups, out->counts);
     group_scan_kernel<<<1, kSortThreads, 0, st>>>(out->counts, n_groups, out->gstart);
     group_scatter_kernel<<<1, kSortThreads, 0, st>>>(d_group, n, n_groups, out->counts, out->order);
+    IRP_CUDA_OK(cudaGetLastError());
+    // A group id outside [0, n_groups) would leave rows out of every group while the later kernels still walk all
+    // n rows: refuse the call instead (gstart[n_groups] = number of rows that landed in a group).
+    int32_t placed = 0;
+    IRP_CUDA_OK(cudaMemcpyAsync(&placed, out->gstart + n_groups, sizeof(placed), cudaMemcpyDeviceToHost, st));
+    IRP_CUDA_OK(cudaStreamSynchronize(st));
+    IRP_REQUIRE(placed == static_cast<int32_t>(n), "group ids must lie in [0, %d): %lld of %lld rows do not", n_groups,
+                n - static_cast<long long>(placed), n);
   }
   IRP_CUDA_OK(cudaGetLastError());
   return IRP_OK;

@@ -1018,53 +1018,224 @@ __global__ void clip_evals_kernel(double* evals, int k) {
 }
 
 // ============================================================================================================
-// 8. projection  Z[r][c] = sum_j (x[r][j] - mean[j]) * comps[c][j]   (fp64 accumulate, fp32 out)
+// 8. projection  Z = (X - mean) V^T  as a split-bf16 tensor-core GEMM (fp32 out)
+//    pre-pass : y = float(double(x) - mean) split EXACTLY into three bf16 terms (a + b + c = y), rows K-major;
+//               the components (fp64) are split the same way, padded to N rows
+//    GEMM     : one CTA per 128-row tile, N = 64 or 128 columns; per 64-wide K block the three A tiles and the
+//               three B tiles are loaded ONCE and feed the six products a.va | a.vb + b.va + b.vb + a.vc + c.va
+//               (fp32 accumulation in TMEM; the hi*hi term has its own accumulator so the small terms are not
+//               rounded against its partial sums); the epilogue adds the two accumulators and stores fp32.
 // ============================================================================================================
-constexpr int kProjRows = 32, kProjChunk = 64, kProjThreads = 256;
+__global__ void __launch_bounds__(256) project_split_kernel(const float* __restrict__ x, long long n_rows, int dim,
+                                                            const double* __restrict__ mean,
+                                                            __nv_bfloat16* __restrict__ ya,
+                                                            __nv_bfloat16* __restrict__ yb,
+                                                            __nv_bfloat16* __restrict__ yc, long long n_pad) {
+  // one thread per 4 consecutive features: 16-byte load, three 8-byte stores; rows >= n_rows are written as zeros
+  const long long total = n_pad * (dim / 4);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / (dim / 4);
+    const int c4 = static_cast<int>(i - r * (dim / 4)) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < n_rows) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + r * dim + c4);
+      v[0] = static_cast<float>(static_cast<double>(xv.x) - mean[c4 + 0]);
+      v[1] = static_cast<float>(static_cast<double>(xv.y) - mean[c4 + 1]);
+      v[2] = static_cast<float>(static_cast<double>(xv.z) - mean[c4 + 2]);
+      v[3] = static_cast<float>(static_cast<double>(xv.w) - mean[c4 + 3]);
+    }
+    __nv_bfloat16 a[4], b[4], c[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      a[t] = __float2bfloat16_rn(v[t]);
+      const float ra = v[t] - __bfloat162float(a[t]);
+      b[t] = __float2bfloat16_rn(ra);
+      c[t] = __float2bfloat16_rn(ra - __bfloat162float(b[t]));
+    }
+    const size_t o = static_cast<size_t>(r) * dim + c4;
+    *reinterpret_cast<uint2*>(ya + o) = *reinterpret_cast<const uint2*>(a);
+    *reinterpret_cast<uint2*>(yb + o) = *reinterpret_cast<const uint2*>(b);
+    *reinterpret_cast<uint2*>(yc + o) = *reinterpret_cast<const uint2*>(c);
+  }
+}
 
-__global__ void __launch_bounds__(kProjThreads) project_kernel(const float* __restrict__ x, long long n_rows, int dim,
-                                                               const double* __restrict__ mean,
-                                                               const double* __restrict__ comps, int k,
-                                                               float* __restrict__ z) {
-  extern __shared__ double shp[];
-  double* xs = shp;                            // [kProjRows][kProjChunk+1]
-  double* vs = shp + kProjRows * (kProjChunk + 1);  // [k][kProjChunk+1]
-  const long long r0 = static_cast<long long>(blockIdx.x) * kProjRows;
-  const int r = threadIdx.x >> 3;   // 0..31
-  const int cg = threadIdx.x & 7;   // component group
-  double acc[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-  for (int j0 = 0; j0 < dim; j0 += kProjChunk) {
-    for (int i = threadIdx.x; i < kProjRows * kProjChunk; i += kProjThreads) {
-      const int rr = i / kProjChunk, jj = i % kProjChunk;
-      const long long row = r0 + rr;
-      xs[rr * (kProjChunk + 1) + jj] =
-          row < n_rows ? static_cast<double>(x[row * dim + j0 + jj]) - mean[j0 + jj] : 0.0;
+__global__ void __launch_bounds__(256) project_split_comps_kernel(const double* __restrict__ comps, int k, int dim,
+                                                                  int n_cols, __nv_bfloat16* __restrict__ va,
+                                                                  __nv_bfloat16* __restrict__ vb,
+                                                                  __nv_bfloat16* __restrict__ vc) {
+  const int total = n_cols * dim;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / dim;
+    const double v = r < k ? comps[i] : 0.0;
+    const __nv_bfloat16 a = __double2bfloat16(v);
+    const double ra = v - static_cast<double>(__bfloat162float(a));
+    const __nv_bfloat16 b = __double2bfloat16(ra);
+    const double rb = ra - static_cast<double>(__bfloat162float(b));
+    va[i] = a;
+    vb[i] = b;
+    vc[i] = __double2bfloat16(rb);
+  }
+}
+
+constexpr int kPjBK = 64, kPjThreads = 192;
+constexpr int kPjABytes = 128 * kPjBK * 2;
+
+template <int N>
+struct PjSmem {
+  static constexpr int kBBytes = N * kPjBK * 2;
+  static constexpr int kStageBytes = 3 * (kPjABytes + kBBytes);
+  static constexpr int kStages = (220 * 1024) / kStageBytes;
+  static constexpr int kTotal = kStages * kStageBytes + 256 + 1024;
+  static_assert(kStages >= 2, "projection GEMM needs two pipeline stages");
+};
+
+struct alignas(64) ProjParams {
+  CUtensorMap tmY[3];  // y terms [n_pad][dim] bf16, box (64, 128)
+  CUtensorMap tmV[3];  // component terms [N][dim] bf16, box (64, N)
+  float* z;            // [n_rows][k]
+  long long n_rows;
+  int k, k_blocks, n_tiles;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kPjThreads, 1) proj_gemm_kernel(const __grid_constant__ ProjParams p) {
+  using S = PjSmem<N>;
+  constexpr int kStages = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  constexpr uint32_t kTmemCols = 4 * N;  // two buffers x (hi*hi | corrections)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 3; ++i) {
+      tma_prefetch_desc(&p.tmY[i]);
+      tma_prefetch_desc(&p.tmV[i]);
     }
-    for (int i = threadIdx.x; i < k * kProjChunk; i += kProjThreads) {
-      const int cc = i / kProjChunk, jj = i % kProjChunk;
-      vs[cc * (kProjChunk + 1) + jj] = comps[static_cast<size_t>(cc) * dim + j0 + jj];
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
     }
-    __syncthreads();
-#pragma unroll 4
-    for (int jj = 0; jj < kProjChunk; ++jj) {
-      const double xv = xs[r * (kProjChunk + 1) + jj];
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          uint8_t* st = smem + stage * S::kStageBytes;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int c = cg + 8 * i;
-        if (c < k) acc[i] += xv * vs[c * (kProjChunk + 1) + jj];
+          for (int i = 0; i < 3; ++i) {
+            tma_load_2d(st + i * kPjABytes, &p.tmY[i], &full_bar[stage], kb * kPjBK, t * 128);
+            tma_load_2d(st + 3 * kPjABytes + i * S::kBBytes, &p.tmV[i], &full_bar[stage], kb * kPjBK, 0);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
       }
     }
-    __syncthreads();
-  }
-  const long long row = r0 + r;
-  if (row < n_rows) {
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+      // (A term, B term) of the six products; the first one accumulates alone
+      const int pa[6] = {0, 0, 1, 1, 0, 2};
+      const int pb[6] = {0, 1, 0, 1, 2, 0};
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_big = tmem_base + acc * 2 * N;
+        const uint32_t tmem_small = tmem_big + N;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * S::kStageBytes);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int c = cg + 8 * i;
-      if (c < k) z[row * k + c] = static_cast<float>(acc[i]);
+          for (int c = 0; c < 6; ++c) {
+            const uint32_t a_addr = st + pa[c] * kPjABytes;
+            const uint32_t b_addr = st + 3 * kPjABytes + pb[c] * S::kBBytes;
+#pragma unroll
+            for (int k = 0; k < kPjBK / 16; ++k) {
+              const uint32_t accum = c == 0 ? ((kb | k) != 0 ? 1u : 0u) : ((kb != 0 || c > 1 || k != 0) ? 1u : 0u);
+              umma_bf16(c == 0 ? tmem_big : tmem_small, umma_smem_desc<128>(a_addr + k * 32),
+                        umma_smem_desc<128>(b_addr + k * 32), idesc, accum);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
+  } else {
+    const int quarter = warp & 3;
+    const long long row_in_tile = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 2 * N + (static_cast<uint32_t>(quarter * 32) << 16);
+      const long long row = static_cast<long long>(t) * 128 + row_in_tile;
+      float* dst = p.z + row * p.k;
+#pragma unroll 1
+      for (int c = 0; c < N; c += 32) {
+        uint32_t v[32], s[32];
+        __syncwarp();
+        tmem_ld_32x32b_x32(taddr + c, v);
+        tmem_ld_32x32b_x32(taddr + N + c, s);
+        tmem_ld_wait();
+        if (row < p.n_rows) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < p.k) dst[c + i] = __uint_as_float(v[i]) + __uint_as_float(s[i]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -1121,7 +1292,6 @@ int irp_cov_accumulate(const float* d_x, int64_t n_rows, int dim, const float* d
   p.k_blocks_total = static_cast<int>(n_pad / kCovBK);
   // 512 samples per fp32 accumulation chain: measured 9e-5 rad subspace error at k=50 (32 blocks: 5e-4)
   p.k_blocks_per_chunk = 8;
-  if (const char* e = getenv("IRP_COV_CHUNK")) p.k_blocks_per_chunk = atoi(e) > 0 ? atoi(e) : 8;
   p.n_chunks = ceil_div(p.k_blocks_total, p.k_blocks_per_chunk);
   p.dim = dim;
   p.scatter = d_scatter;
@@ -1151,20 +1321,11 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-static bool lanczos_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("IRP_PCA_HOUSEHOLDER");
-    v = (e && atoi(e) != 0) ? 0 : 1;
-  }
-  return v == 1;
-}
-
 // Top-k eigenpairs by Lanczos (section 4b).  *done = false asks the caller for the exact Householder path
 // (breakdown, or no convergence within dim/2 steps).  Synchronises the stream once per convergence check.
 static int lanczos_topk(const double* A, int n, int k, double* Q, double* diag, double* off, double* tnorm,
                         double* work, double* Z, double* d_eigenvalues, double* d_components, cudaStream_t st,
-                        bool* done) {
+                        int first_check, int* steps_out, int* checks_out, bool* done) {
   *done = false;
   double* w0 = work;
   double* w1 = w0 + n;
@@ -1174,7 +1335,7 @@ static int lanczos_topk(const double* A, int n, int k, double* Q, double* diag, 
   double* out = h2 + n;
   const double *cQ = Q, *cw0 = w0, *cw1 = w1, *cw2 = w2, *ch1 = h1, *ch2 = h2;
   int m_target = 3 * k + 10 > 96 ? 3 * k + 10 : 96;
-  if (const char* e = getenv("IRP_PCA_LANCZOS_M0")) m_target = atoi(e) > k ? atoi(e) : m_target;
+  if (first_check > k) m_target = first_check;  // caller-chosen first convergence check (tests force an early one)
   const int m_cap = n / 2;
   if (m_target > m_cap) m_target = m_cap;
   int m = 0;
@@ -1210,9 +1371,8 @@ static int lanczos_topk(const double* A, int n, int k, double* Q, double* diag, 
     IRP_CUDA_OK(cudaStreamSynchronize(st));
     const double tn = host[2] > 0.0 ? host[2] : 1.0;
     ++checks;
-    if (getenv("IRP_PCA_DEBUG"))
-      fprintf(stderr, "[irp] lanczos n=%d k=%d m=%d check %d: residual %.3e, min beta %.3e (||T|| %.3e)\n", n, k, m,
-              checks, host[0], host[1], tn);
+    *steps_out = m;
+    *checks_out = checks;
     if (!(host[1] > 1e-10 * tn) || !(host[0] == host[0])) return IRP_OK;  // breakdown (invariant subspace) or NaN
     if (host[0] <= 1e-12 * tn) {
       const size_t ritz_smem = static_cast<size_t>(m) * sizeof(double);
@@ -1246,6 +1406,15 @@ size_t irp_pca_fit_workspace_bytes(int dim, int k) {
 int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scatter, const float* d_shift, int dim,
                 int k, double* d_mean, double* d_components, double* d_eigenvalues, void* d_workspace,
                 size_t workspace_bytes, void* stream) {
+  return irp_pca_fit_ex(d_count, d_sum, d_scatter, d_shift, dim, k, d_mean, d_components, d_eigenvalues, d_workspace,
+                        workspace_bytes, IRP_PCA_SOLVER_AUTO, 0, nullptr, stream);
+}
+
+int irp_pca_fit_ex(const double* d_count, const double* d_sum, const double* d_scatter, const float* d_shift, int dim,
+                   int k, double* d_mean, double* d_components, double* d_eigenvalues, void* d_workspace,
+                   size_t workspace_bytes, int solver, int lanczos_first_check, int32_t* h_info, void* stream) {
+  IRP_REQUIRE(solver == IRP_PCA_SOLVER_AUTO || solver == IRP_PCA_SOLVER_LANCZOS || solver == IRP_PCA_SOLVER_HOUSEHOLDER,
+              "pca_fit: unknown solver %d", solver);
   IRP_REQUIRE(d_count && d_sum && d_scatter && d_shift && d_mean && d_components && d_eigenvalues && d_workspace,
               "pca_fit: null argument");
   IRP_REQUIRE(dim >= 4 && dim <= 4096 && k >= 1 && k <= dim && k <= 512, "pca_fit: dim %d / k %d unsupported", dim, k);
@@ -1270,8 +1439,19 @@ int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scat
   IRP_CUDA_OK(cudaGetLastError());
 
   bool done = false;
-  if (lanczos_enabled() && n >= 512 && k * 8 <= n && k >= 5)
-    IRP_TRY(lanczos_topk(A, n, k, V, diag, off, scal + 1, work, Z, d_eigenvalues, d_components, st, &done));
+  int lz_steps = 0, lz_checks = 0;
+  const bool lanczos_fits = n >= 512 && k * 8 <= n && k >= 5;
+  IRP_REQUIRE(solver != IRP_PCA_SOLVER_LANCZOS || lanczos_fits,
+              "pca_fit: the Lanczos solver needs dim >= 512 and 5 <= k <= dim / 8 (dim %d, k %d)", dim, k);
+  if (solver != IRP_PCA_SOLVER_HOUSEHOLDER && lanczos_fits)
+    IRP_TRY(lanczos_topk(A, n, k, V, diag, off, scal + 1, work, Z, d_eigenvalues, d_components, st,
+                         lanczos_first_check, &lz_steps, &lz_checks, &done));
+  if (h_info) {
+    h_info[0] = done ? IRP_PCA_SOLVER_LANCZOS : IRP_PCA_SOLVER_HOUSEHOLDER;
+    h_info[1] = lz_steps;
+    h_info[2] = lz_checks;
+    h_info[3] = 0;
+  }
   if (!done) {
   // ---- tridiagonalisation: launches j = -1 .. n-3 ----
   const size_t tri_smem = 3 * static_cast<size_t>(n) * sizeof(double);
@@ -1314,18 +1494,80 @@ int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scat
   return IRP_OK;
 }
 
+constexpr long long kPjChunkRows = 32768;  // rows per pass through the workspace
+
+size_t irp_pca_transform_workspace_bytes(int64_t n_rows, int dim, int k) {
+  if (n_rows <= 0 || dim <= 0 || k <= 0) return 0;
+  const size_t rows = static_cast<size_t>(n_rows < kPjChunkRows ? (n_rows + 127) / 128 * 128 : kPjChunkRows);
+  const size_t n_cols = k <= 64 ? 64 : 128;
+  return 3 * align_up(rows * dim * sizeof(__nv_bfloat16), 1024) + 3 * align_up(n_cols * dim * sizeof(__nv_bfloat16), 1024) +
+         1024;
+}
+
+}  // extern "C"
+
+template <int N>
+static int launch_proj(const ProjParams& p, cudaStream_t st) {
+  IRP_TRY(ensure_smem(proj_gemm_kernel<N>, PjSmem<N>::kTotal));
+  const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+  proj_gemm_kernel<N><<<grid, kPjThreads, PjSmem<N>::kTotal, st>>>(p);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
+}
+
+extern "C" {
+
 int irp_pca_transform(const float* d_x, int64_t n_rows, int dim, const double* d_mean, const double* d_components,
-                      int k, float* d_z, void* stream) {
-  IRP_REQUIRE(d_x && d_mean && d_components && d_z, "pca_transform: null argument");
-  IRP_REQUIRE(n_rows > 0 && dim > 0 && dim % kProjChunk == 0 && k >= 1 && k <= 128,
+                      int k, float* d_z, void* d_workspace, size_t workspace_bytes, void* stream) {
+  IRP_REQUIRE(d_x && d_mean && d_components && d_z && d_workspace, "pca_transform: null argument");
+  IRP_REQUIRE(n_rows > 0 && dim > 0 && dim % kPjBK == 0 && k >= 1 && k <= 128,
               "pca_transform: n_rows %lld dim %d k %d unsupported (k <= 128, dim %% 64 == 0)",
               static_cast<long long>(n_rows), dim, k);
-  const size_t smem = (static_cast<size_t>(kProjRows) + k) * (kProjChunk + 1) * sizeof(double);
-  IRP_TRY(ensure_smem(project_kernel, smem));
-  const unsigned grid = static_cast<unsigned>(ceil_div64(n_rows, kProjRows));
-  project_kernel<<<grid, kProjThreads, smem, static_cast<cudaStream_t>(stream)>>>(d_x, n_rows, dim, d_mean,
-                                                                                  d_components, k, d_z);
+  IRP_REQUIRE(workspace_bytes >= irp_pca_transform_workspace_bytes(n_rows, dim, k), "pca_transform: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t rows_cap = static_cast<size_t>(n_rows < kPjChunkRows ? (n_rows + 127) / 128 * 128 : kPjChunkRows);
+  const int n_cols = k <= 64 ? 64 : 128;
+  const size_t y_bytes = align_up(rows_cap * dim * sizeof(__nv_bfloat16), 1024);
+  const size_t v_bytes = align_up(static_cast<size_t>(n_cols) * dim * sizeof(__nv_bfloat16), 1024);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(d_workspace), 1024));
+  __nv_bfloat16* y[3];
+  __nv_bfloat16* v[3];
+  for (int i = 0; i < 3; ++i) {
+    y[i] = reinterpret_cast<__nv_bfloat16*>(ws + i * y_bytes);
+    v[i] = reinterpret_cast<__nv_bfloat16*>(ws + 3 * y_bytes + i * v_bytes);
+  }
+  project_split_comps_kernel<<<num_sms(), 256, 0, st>>>(d_components, k, dim, n_cols, v[0], v[1], v[2]);
   IRP_CUDA_OK(cudaGetLastError());
+  ProjParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < 3; ++i) {
+    uint64_t vd[2] = {static_cast<uint64_t>(dim), static_cast<uint64_t>(n_cols)};
+    uint64_t vs[1] = {static_cast<uint64_t>(dim) * 2};
+    uint32_t vbox[2] = {kPjBK, static_cast<uint32_t>(n_cols)};
+    IRP_TRY(encode_bf16_map(&p.tmV[i], v[i], 2, vd, vs, vbox, 128));
+  }
+  p.k = k;
+  p.k_blocks = dim / kPjBK;
+  for (long long r0 = 0; r0 < n_rows; r0 += kPjChunkRows) {
+    const long long rows = n_rows - r0 < kPjChunkRows ? n_rows - r0 : kPjChunkRows;
+    const long long n_pad = (rows + 127) / 128 * 128;
+    const long long total = n_pad * (dim / 4);
+    const unsigned blocks = static_cast<unsigned>(total / 256 < static_cast<long long>(num_sms()) * 32
+                                                      ? (total + 255) / 256
+                                                      : static_cast<long long>(num_sms()) * 32);
+    project_split_kernel<<<blocks, 256, 0, st>>>(d_x + r0 * dim, rows, dim, d_mean, y[0], y[1], y[2], n_pad);
+    IRP_CUDA_OK(cudaGetLastError());
+    for (int i = 0; i < 3; ++i) {
+      uint64_t yd[2] = {static_cast<uint64_t>(dim), static_cast<uint64_t>(n_pad)};
+      uint64_t ys[1] = {static_cast<uint64_t>(dim) * 2};
+      uint32_t ybox[2] = {kPjBK, 128};
+      IRP_TRY(encode_bf16_map(&p.tmY[i], y[i], 2, yd, ys, ybox, 128));
+    }
+    p.z = d_z + r0 * k;
+    p.n_rows = rows;
+    p.n_tiles = static_cast<int>(n_pad / 128);
+    IRP_TRY(n_cols == 64 ? launch_proj<64>(p, st) : launch_proj<128>(p, st));
+  }
   return IRP_OK;
 }
 

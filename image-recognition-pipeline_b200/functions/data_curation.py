@@ -113,19 +113,18 @@ def process_image_directory(root_dir, device, transform, batch_size=32, model=No
     fused = isinstance(transform, B200Transform)
 
     def flush():
+        # Skip-and-print is a PER-IMAGE contract (:681-682) and covers what can fail per image: decode, convert and
+        # the host-side transform, all handled in the loop below.  A failure of the batched device path (IrpError,
+        # a CUDA error) is not an image problem: it propagates instead of silently dropping up to a whole batch.
         if not pend_imgs:
             return
-        try:
-            if fused:
-                feats = stage.embed_packed(pack_images(pend_imgs), from_host=True)
-            else:
-                feats = model.trunk.embed_nchw(torch.stack(pend_imgs))
-            features.append(np.array(stage.to_host(feats, "batch").numpy()))  # pinned staging buffer, then an owned copy
-            labels.extend(pend_labels)
-            paths.extend(pend_paths)
-        except Exception as e:  # keep the reference's skip-and-continue contract at batch granularity
-            for p in pend_paths:
-                print(f"Skipped {p}: {str(e)}")
+        if fused:
+            feats = stage.embed_packed(pack_images(pend_imgs), from_host=True)
+        else:
+            feats = model.trunk.embed_nchw(torch.stack(pend_imgs))
+        features.append(np.array(stage.to_host(feats, "batch").numpy()))  # pinned staging buffer, then an owned copy
+        labels.extend(pend_labels)
+        paths.extend(pend_paths)
         pend_imgs.clear()
         pend_labels.clear()
         pend_paths.clear()
@@ -139,6 +138,8 @@ def process_image_directory(root_dir, device, transform, batch_size=32, model=No
             try:
                 img = Image.open(img_path).convert('RGB')
                 item = np.asarray(img, dtype=np.uint8) if fused else transform(img)
+                if fused and (item.ndim != 3 or item.shape[2] != 3 or item.shape[0] < 1 or item.shape[1] < 1):
+                    raise ValueError(f"unexpected decoded shape {item.shape}")
                 pend_imgs.append(item)
                 pend_labels.append(class_name)
                 pend_paths.append(img_path)

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libirp_b200.so"))
 
 IRP_OK = 0
+PCA_SOLVER_AUTO, PCA_SOLVER_LANCZOS, PCA_SOLVER_HOUSEHOLDER = 0, 1, 2
 LAYOUT_NCHW = 0
 TRANSFORM_WEIGHTS_DEFAULT = 0  # ResNet50_Weights.DEFAULT.transforms() (resize 232, crop 224)
 TRANSFORM_VAL_256 = 1          # functions/dataload.py:51-56 (Resize((256,256)), CenterCrop(224))
@@ -59,7 +60,9 @@ SIGNATURES = {
     "irp_cov_accumulate": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "irp_pca_fit_workspace_bytes": (_sz, [_i, _i]),
     "irp_pca_fit": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "irp_pca_transform": (_i, [_vp, _i64, _i, _vp, _vp, _i, _vp, _vp]),
+    "irp_pca_fit_ex": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _i, C.POINTER(C.c_int32), _vp]),
+    "irp_pca_transform_workspace_bytes": (_sz, [_i64, _i, _i]),
+    "irp_pca_transform": (_i, [_vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "irp_lof_workspace_bytes": (_sz, [_i64, _i, _i]),
     "irp_lof": (_i, [_vp, _i64, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
     "irp_lof_knn_part": (_i, [_vp, _i64, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),

@@ -162,6 +162,25 @@ def pca_fit(count: torch.Tensor, total: torch.Tensor, scatter: torch.Tensor, shi
     return mean, comps, evals
 
 
+@_on_device_of(0)
+def pca_fit_ex(count: torch.Tensor, total: torch.Tensor, scatter: torch.Tensor, shift: torch.Tensor, k: int,
+               solver: int = 0, lanczos_first_check: int = 0):
+    """pca_fit with the eigensolver forced (_lib.PCA_SOLVER_*) and the library's report:
+    -> (mean, components, eigenvalues, {"solver", "lanczos_steps", "checks"})."""
+    lib = _lib_for(scatter)
+    d = scatter.shape[0]
+    mean = torch.empty(d, dtype=torch.float64, device=scatter.device)
+    comps = torch.empty((k, d), dtype=torch.float64, device=scatter.device)
+    evals = torch.empty(k + 1, dtype=torch.float64, device=scatter.device)
+    ws_bytes = lib.irp_pca_fit_workspace_bytes(d, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=scatter.device)
+    info = (C.c_int32 * 4)()
+    _lib.check(lib.irp_pca_fit_ex(_ptr(count), _ptr(total), _ptr(scatter), _ptr(shift), d, k, _ptr(mean), _ptr(comps),
+                                  _ptr(evals), _ptr(ws), ws_bytes, int(solver), int(lanczos_first_check), info,
+                                  _stream(count)), "irp_pca_fit_ex")
+    return mean, comps, evals, {"solver": info[0], "lanczos_steps": info[1], "checks": info[2]}
+
+
 @pca_fit.register_fake
 def _(count, total, scatter, shift, k):
     d = scatter.shape[0]
@@ -171,14 +190,16 @@ def _(count, total, scatter, shift, k):
 @torch.library.custom_op("irp_b200::pca_transform", mutates_args=())
 @_on_device_of(0)
 def pca_transform(x: torch.Tensor, mean: torch.Tensor, components: torch.Tensor) -> torch.Tensor:
-    """(x - mean) @ components^T with fp64 accumulation -> fp32 [n,k]."""
+    """(x - mean) @ components^T on the tensor cores (split-bf16 operands, fp32 accumulation) -> fp32 [n,k]."""
     lib = _lib_for(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
     n, d = x.shape
     k = components.shape[0]
     z = torch.empty((n, k), dtype=torch.float32, device=x.device)
-    _lib.check(lib.irp_pca_transform(_ptr(x), n, d, _ptr(mean), _ptr(components), k, _ptr(z), _stream(x)),
-               "irp_pca_transform")
+    ws_bytes = lib.irp_pca_transform_workspace_bytes(n, d, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    _lib.check(lib.irp_pca_transform(_ptr(x), n, d, _ptr(mean), _ptr(components.contiguous()), k, _ptr(z), _ptr(ws),
+                                     ws_bytes, _stream(x)), "irp_pca_transform")
     return z
 
 
@@ -216,34 +237,53 @@ def _(z, group, n_groups, n_neighbors, contamination):
 
 
 @_on_device_of(0)
-def lof_sharded(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: int, n_neighbors: int,
-                contamination: float, part: int, n_parts: int, all_reduce) -> Tuple[torch.Tensor, torch.Tensor,
-                                                                                   torch.Tensor]:
-    """irp_lof with the O(n^2) neighbour search sharded over `n_parts` ranks (irp_lof_knn_part / _lrd_part /
-    _score_part / _finish).  Every rank passes the same `z` / `group` (all rows); `all_reduce(t)` must sum the fp64
-    vector `t` in place over the ranks.  Returns the same (scores, offsets, flags) on every rank."""
+def lof_sharded_multi(z: torch.Tensor, problems, part: int, n_parts: int, all_reduce):
+    """Several irp_lof problems over the SAME rows (e.g. per-class and global scoring) with the O(n^2) neighbour
+    search sharded over `n_parts` ranks (irp_lof_knn_part / _lrd_part / _score_part / _finish).
+
+    `problems` is a list of (group or None, n_groups, n_neighbors, contamination).  Every rank passes the same `z`
+    / groups (all rows); `all_reduce(t)` must sum the fp64 tensor `t` in place over the ranks.  The problems advance
+    in lockstep, so each of the three exchange steps is ONE all-reduce of a [len(problems), n] buffer.  Returns a
+    list of (scores, offsets, flags), identical on every rank."""
     lib = _lib_for(z)
     assert z.dtype == torch.float32 and z.is_contiguous()
     n, d = z.shape
-    k = int(n_neighbors)
-    ws_bytes = lib.irp_lof_workspace_bytes(n, d, k)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
-    vec = lambda: torch.empty(n, dtype=torch.float64, device=z.device)
-    kdist, lrd, score = vec(), vec(), vec()
-    _lib.check(lib.irp_lof_knn_part(_ptr(z), n, d, _ptr(group), n_groups, k, part, n_parts, _ptr(kdist), _ptr(ws),
-                                    ws_bytes, _stream(z)), "irp_lof_knn_part")
+    np_ = len(problems)
+    ws = []
+    for (_, _, k, _) in problems:
+        nbytes = lib.irp_lof_workspace_bytes(n, d, int(k))
+        ws.append((torch.empty(nbytes, dtype=torch.uint8, device=z.device), nbytes))
+    buf = lambda: torch.empty((np_, n), dtype=torch.float64, device=z.device)
+    kdist, lrd, score = buf(), buf(), buf()
+    st = _stream(z)
+    for i, (group, n_groups, k, _) in enumerate(problems):
+        _lib.check(lib.irp_lof_knn_part(_ptr(z), n, d, _ptr(group), n_groups, int(k), part, n_parts, _ptr(kdist[i]),
+                                        _ptr(ws[i][0]), ws[i][1], st), "irp_lof_knn_part")
     all_reduce(kdist)
-    _lib.check(lib.irp_lof_lrd_part(n, n_groups, k, part, n_parts, _ptr(kdist), _ptr(lrd), _ptr(ws), ws_bytes,
-                                    _stream(z)), "irp_lof_lrd_part")
+    for i, (_, n_groups, k, _) in enumerate(problems):
+        _lib.check(lib.irp_lof_lrd_part(n, n_groups, int(k), part, n_parts, _ptr(kdist[i]), _ptr(lrd[i]),
+                                        _ptr(ws[i][0]), ws[i][1], st), "irp_lof_lrd_part")
     all_reduce(lrd)
-    _lib.check(lib.irp_lof_score_part(n, n_groups, k, part, n_parts, _ptr(lrd), _ptr(score), _ptr(ws), ws_bytes,
-                                      _stream(z)), "irp_lof_score_part")
+    for i, (_, n_groups, k, _) in enumerate(problems):
+        _lib.check(lib.irp_lof_score_part(n, n_groups, int(k), part, n_parts, _ptr(lrd[i]), _ptr(score[i]),
+                                          _ptr(ws[i][0]), ws[i][1], st), "irp_lof_score_part")
     all_reduce(score)
-    scores, offsets, flags = vec(), torch.empty(n_groups, dtype=torch.float64, device=z.device), \
-        torch.empty(n, dtype=torch.uint8, device=z.device)
-    _lib.check(lib.irp_lof_finish(n, n_groups, k, C.c_double(contamination), _ptr(score), _ptr(scores), _ptr(offsets),
-                                  _ptr(flags), _ptr(ws), ws_bytes, _stream(z)), "irp_lof_finish")
-    return scores, offsets, flags
+    out = []
+    for i, (_, n_groups, k, contamination) in enumerate(problems):
+        scores = torch.empty(n, dtype=torch.float64, device=z.device)
+        offsets = torch.empty(n_groups, dtype=torch.float64, device=z.device)
+        flags = torch.empty(n, dtype=torch.uint8, device=z.device)
+        _lib.check(lib.irp_lof_finish(n, n_groups, int(k), C.c_double(contamination), _ptr(score[i]), _ptr(scores),
+                                      _ptr(offsets), _ptr(flags), _ptr(ws[i][0]), ws[i][1], st), "irp_lof_finish")
+        out.append((scores, offsets, flags))
+    return out
+
+
+def lof_sharded(z: torch.Tensor, group: Optional[torch.Tensor], n_groups: int, n_neighbors: int,
+                contamination: float, part: int, n_parts: int, all_reduce) -> Tuple[torch.Tensor, torch.Tensor,
+                                                                                   torch.Tensor]:
+    """One irp_lof problem with the neighbour search sharded over `n_parts` ranks (see lof_sharded_multi)."""
+    return lof_sharded_multi(z, [(group, n_groups, n_neighbors, contamination)], part, n_parts, all_reduce)[0]
 
 
 @torch.library.custom_op("irp_b200::centroid_zscore", mutates_args=())

@@ -216,6 +216,7 @@ class CudaBackend:
     pca_transform = staticmethod(ops.pca_transform)
     lof = staticmethod(ops.lof)
     lof_sharded = staticmethod(ops.lof_sharded)
+    lof_sharded_multi = staticmethod(ops.lof_sharded_multi)
 
 
 class OutlierStage:
@@ -226,7 +227,8 @@ class OutlierStage:
 
     def __init__(self, backend, batch_size: int = 256, pca_components: int = 50, class_n_neighbors: int = 30,
                  class_contamination: float = 0.05, global_n_neighbors: int = 75,
-                 global_contamination: float = 0.03, process_group=None, embed_dim: int = _lib.EMBED_DIM):
+                 global_contamination: float = 0.03, process_group=None, embed_dim: int = _lib.EMBED_DIM,
+                 class_scoring: bool = True, trace: bool = False):
         if isinstance(backend, ResNet50Trunk):
             backend = CudaBackend(backend)
         self.backend = backend
@@ -239,6 +241,8 @@ class OutlierStage:
         self.class_nn, self.class_cont = int(class_n_neighbors), float(class_contamination)
         self.global_nn, self.global_cont = int(global_n_neighbors), float(global_contamination)
         self.pg = process_group
+        self.class_scoring = bool(class_scoring)  # False: global scorer only (BASELINE configs[3])
+        self.trace = bool(trace)                  # per-phase wall-clock times in self.traces (synchronises)
         self.copy_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self._pinned = {}
 
@@ -337,40 +341,55 @@ class OutlierStage:
         return self.backend.pca_transform(feats, pca.mean, pca.components)
 
     # ---- scoring ----
-    def gather_rows(self, local: torch.Tensor) -> torch.Tensor:
-        """All ranks' rows concatenated in rank order (identity on one rank)."""
+    def gather_rows(self, z_local: torch.Tensor, ids_local: torch.Tensor):
+        """All ranks' projected rows and class ids, concatenated in rank order (identity on one rank).
+
+        ONE all-gather of the row counts and ONE of a padded [rows, k + 1] fp32 block (ids ride along as an exactly
+        representable float column), instead of separate exchanges for z and ids."""
         dist = self._dist()
         if not dist or self.world_size == 1:
-            return local
+            return z_local, ids_local
         ws = self.world_size
-        n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=self.device)
-        sizes = [torch.zeros_like(n_local) for _ in range(ws)]
-        dist.all_gather(sizes, n_local, group=self.pg)
-        sizes = [int(s.item()) for s in sizes]
+        n_local = torch.tensor([z_local.shape[0]], dtype=torch.int64, device=self.device)
+        sizes_t = torch.empty(ws, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(sizes_t, n_local, group=self.pg)
+        sizes = [int(v) for v in sizes_t.cpu().tolist()]
         mx = max(sizes)
-        pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=self.device)
-        pad[: local.shape[0]] = local
-        outs = [torch.empty_like(pad) for _ in range(ws)]
-        dist.all_gather(outs, pad, group=self.pg)
-        return torch.cat([o[:s] for o, s in zip(outs, sizes)], 0)
+        k = z_local.shape[1]
+        pad = torch.zeros((mx, k + 1), dtype=torch.float32, device=self.device)
+        pad[: z_local.shape[0], :k] = z_local
+        pad[: z_local.shape[0], k] = ids_local.to(torch.float32)  # class ids < 2^24: exact
+        out = torch.empty((ws * mx, k + 1), dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(out, pad, group=self.pg)
+        if all(sz == mx for sz in sizes):
+            rows = out
+        else:
+            rows = torch.cat([out[r * mx: r * mx + sizes[r]] for r in range(ws)], 0)
+        return rows[:, :k].contiguous(), rows[:, k].to(torch.int32).contiguous()
 
     def detect(self, z_all: torch.Tensor, class_ids_all: torch.Tensor, n_classes: int):
         """Per-class + global LOF over ALL rows.  On several ranks the O(n^2) neighbour search is sharded: rank r
-        searches the query tiles r, r+W, r+2W, ... and three length-n vectors are summed across ranks."""
+        searches the query tiles r, r+W, r+2W, ... and three [problems, n] fp64 buffers are summed across ranks (one
+        all-reduce per LOF phase for both scorers together)."""
         dist = self._dist()
-        if dist is not None and self.world_size > 1 and hasattr(self.backend, "lof_sharded"):
+        problems = []
+        if self.class_scoring:
+            problems.append((class_ids_all, n_classes, self.class_nn, self.class_cont))
+        problems.append((None, 1, self.global_nn, self.global_cont))
+        if dist is not None and self.world_size > 1 and hasattr(self.backend, "lof_sharded_multi"):
             rank, ws = dist.get_rank(self.pg), self.world_size
 
             def all_reduce(t):
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
 
-            cs, _, cf = self.backend.lof_sharded(z_all, class_ids_all, n_classes, self.class_nn, self.class_cont,
-                                                 rank, ws, all_reduce)
-            gs, _, gf = self.backend.lof_sharded(z_all, None, 1, self.global_nn, self.global_cont, rank, ws,
-                                                 all_reduce)
+            res = self.backend.lof_sharded_multi(z_all, problems, rank, ws, all_reduce)
         else:
-            cs, _, cf = self.backend.lof(z_all, class_ids_all, n_classes, self.class_nn, self.class_cont)
-            gs, _, gf = self.backend.lof(z_all, None, 1, self.global_nn, self.global_cont)
+            res = [self.backend.lof(z_all, g, ng, k, c) for (g, ng, k, c) in problems]
+        gs, _, gf = res[-1]
+        if self.class_scoring:
+            cs, _, cf = res[0]
+        else:
+            cs, cf = torch.zeros_like(gs), torch.zeros_like(gf)
         return cf.bool(), gf.bool(), cs, gs
 
     # ---- whole stage ----
@@ -384,16 +403,16 @@ class OutlierStage:
         self._trace(trace, "fit_pca")
         z_local = self.transform(feats, pca)
         ids_local = class_ids.to(self.device, non_blocking=True).to(torch.int32)
-        z_all = self.gather_rows(z_local)
-        ids_all = self.gather_rows(ids_local)
-        self._trace(trace, "transform+gather")
+        self._trace(trace, "transform")
+        z_all, ids_all = self.gather_rows(z_local, ids_local)
+        self._trace(trace, "gather")
         cf, gf, cs, gs = self.detect(z_all.contiguous(), ids_all.contiguous(), n_classes)
         self._trace(trace, "detect")
         return StageResult(feats, z_all, pca, cf, gf, cs, gs)
 
-    # ---- optional per-phase wall-clock trace (IRP_STAGE_TRACE=1; synchronises after every phase) ----
+    # ---- optional per-phase wall-clock trace (OutlierStage(trace=True); synchronises after every phase) ----
     def _trace_begin(self):
-        if os.environ.get("IRP_STAGE_TRACE", "0") == "0":
+        if not self.trace:
             return None
         import time
         torch.cuda.synchronize(self.device)

@@ -159,7 +159,7 @@ int irp_conv1x1_chain_ds(const void* d_t2, const void* d_x, const void* d_wcat, 
  *   irp_pca_fit        : mean, covariance, fp64 symmetric eigensolve of the top k pairs (Lanczos with full
  *                        re-orthogonalisation, or Householder tridiagonalisation for small / rank-deficient
  *                        problems; bisection + inverse iteration on the tridiagonal), sklearn's sign convention;
- *   irp_pca_transform  : Z = (X - mean) V^T.
+ *   irp_pca_transform  : Z = (X - mean) V^T  (split-bf16 tcgen05 GEMM, fp32 accumulate).
  * ---------------------------------------------------------------------------------------------------------- */
 size_t irp_cov_workspace_bytes(int64_t n_rows, int dim);
 int irp_cov_accumulate(const float* d_x, int64_t n_rows, int dim, const float* d_shift, double* d_count,
@@ -173,8 +173,19 @@ size_t irp_pca_fit_workspace_bytes(int dim, int k);
 int irp_pca_fit(const double* d_count, const double* d_sum, const double* d_scatter, const float* d_shift,
                 int dim, int k, double* d_mean, double* d_components, double* d_eigenvalues, void* d_workspace,
                 size_t workspace_bytes, void* stream);
+/* irp_pca_fit with the eigensolver chosen by the caller and a host-side report.  solver: AUTO = Lanczos when it
+ * applies (dim >= 512, 5 <= k <= dim/8) with the Householder path as its fallback (breakdown / no convergence);
+ * LANCZOS / HOUSEHOLDER force one.  lanczos_first_check > k moves the first convergence check (0 = 3k+10 steps).
+ * h_info (host, may be NULL) receives {solver that produced the result, Lanczos steps, convergence checks, 0}. */
+enum { IRP_PCA_SOLVER_AUTO = 0, IRP_PCA_SOLVER_LANCZOS = 1, IRP_PCA_SOLVER_HOUSEHOLDER = 2 };
+int irp_pca_fit_ex(const double* d_count, const double* d_sum, const double* d_scatter, const float* d_shift,
+                   int dim, int k, double* d_mean, double* d_components, double* d_eigenvalues, void* d_workspace,
+                   size_t workspace_bytes, int solver, int lanczos_first_check, int32_t* h_info, void* stream);
+/* Z = (X - mean) V^T as a tensor-core GEMM: y = float(double(x) - mean) and the components are split exactly
+ * into three bf16 terms each and the six leading products accumulate in fp32 (k <= 128, dim % 64 == 0). */
+size_t irp_pca_transform_workspace_bytes(int64_t n_rows, int dim, int k);
 int irp_pca_transform(const float* d_x, int64_t n_rows, int dim, const double* d_mean, const double* d_components,
-                      int k, float* d_z, void* stream);
+                      int k, float* d_z, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * A4  outlier scoring  --  replaces detect_outliers (functions/data_curation.py:709-728):
@@ -183,7 +194,10 @@ int irp_pca_transform(const float* d_x, int64_t n_rows, int dim, const double* d
  * group, reachability / LRD / LOF, np.percentile threshold, strict `<` flag.
  *
  *   d_group[i] in [0, n_groups): rows are scored only against rows of their own group (per-class pass);
- *   pass d_group = NULL and n_groups = 1 for the global pass.
+ *   pass d_group = NULL and n_groups = 1 for the global pass.  An id outside the range fails the call with
+ *   IRP_ERR_INVALID (checked on the host: the grouped calls synchronise `stream` once).  n_neighbors is clipped
+ *   to group size - 1 like sklearn (_lof.py:286-293); a group with a single member has no neighbours, where
+ *   sklearn raises: its row gets score -1 and is never flagged.
  *   d_scores: negative_outlier_factor_ per row (fp64); d_offsets: threshold per group (fp64 [n_groups]);
  *   d_flags: 1 where score < threshold of the row's group.
  *

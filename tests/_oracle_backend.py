@@ -70,46 +70,59 @@ class OracleBackend:
         return torch.from_numpy(scores), torch.from_numpy(offsets), torch.from_numpy(flags)
 
     @staticmethod
-    def lof_sharded(z, group, n_groups, k, contamination, part, n_parts, all_reduce):
-        """Same protocol as ops.lof_sharded (irp_lof_knn_part / _lrd_part / _score_part / _finish): this rank does
-        the neighbour search for the rows it owns (row position % n_parts inside its group) and the three
-        length-n vectors are summed across ranks."""
+    def lof_sharded_multi(z, problems, part, n_parts, all_reduce):
+        """Same protocol as ops.lof_sharded_multi (irp_lof_knn_part / _lrd_part / _score_part / _finish): this rank
+        does the neighbour search for the rows it owns (row position % n_parts inside its group); the problems
+        advance in lockstep and each of the three [problems, n] fp64 buffers is summed across ranks ONCE."""
         zn = z.numpy()
         n = len(zn)
-        g = np.zeros(n, np.int64) if group is None else group.numpy().astype(np.int64)
-        own = np.zeros(n, bool)
-        nbr = {}
-        kdist, lrd, score = (torch.zeros(n, dtype=torch.float64) for _ in range(3))
-        for c in range(n_groups):
-            rows = np.flatnonzero(g == c)
-            if len(rows) < 2:
-                continue
-            kk = max(1, min(k, len(rows) - 1))
-            mine = rows[np.arange(len(rows)) % n_parts == part]
-            own[mine] = True
-            dist, idx = lof_ref.knn_bruteforce(zn[rows], kk)
-            if zn.dtype == np.float32:
-                dist = dist.astype(np.float32).astype(np.float64)
-            sel = np.arange(len(rows)) % n_parts == part
-            nbr[c] = (rows, kk, dist[sel], rows[idx[sel]], mine)
-            kdist[mine] = torch.from_numpy(dist[sel, kk - 1])
+        npb = len(problems)
+        kdist, lrd, score = (torch.zeros((npb, n), dtype=torch.float64) for _ in range(3))
+        groups, nbrs = [], []
+        for pi, (group, n_groups, k, _) in enumerate(problems):
+            g = np.zeros(n, np.int64) if group is None else group.numpy().astype(np.int64)
+            groups.append(g)
+            nbr = {}
+            for c in range(n_groups):
+                rows = np.flatnonzero(g == c)
+                if len(rows) < 2:
+                    continue
+                kk = max(1, min(k, len(rows) - 1))
+                sel = np.arange(len(rows)) % n_parts == part
+                mine = rows[sel]
+                dist, idx = lof_ref.knn_bruteforce(zn[rows], kk)
+                if zn.dtype == np.float32:
+                    dist = dist.astype(np.float32).astype(np.float64)
+                nbr[c] = (rows, kk, dist[sel], rows[idx[sel]], mine)
+                kdist[pi, mine] = torch.from_numpy(dist[sel, kk - 1])
+            nbrs.append(nbr)
         all_reduce(kdist)
-        kd = kdist.numpy()
-        for c, (rows, kk, dist, idx, mine) in nbr.items():
-            reach = np.maximum(dist, kd[idx])
-            lrd[mine] = torch.from_numpy(1.0 / (reach.mean(axis=1) + 1e-10))
+        for pi, nbr in enumerate(nbrs):
+            kd = kdist[pi].numpy()
+            for c, (rows, kk, dist, idx, mine) in nbr.items():
+                reach = np.maximum(dist, kd[idx])
+                lrd[pi, mine] = torch.from_numpy(1.0 / (reach.mean(axis=1) + 1e-10))
         all_reduce(lrd)
-        lr = lrd.numpy()
-        for c, (rows, kk, dist, idx, mine) in nbr.items():
-            score[mine] = torch.from_numpy(-(lr[idx] / lr[mine][:, None]).mean(axis=1))
+        for pi, nbr in enumerate(nbrs):
+            lr = lrd[pi].numpy()
+            for c, (rows, kk, dist, idx, mine) in nbr.items():
+                score[pi, mine] = torch.from_numpy(-(lr[idx] / lr[mine][:, None]).mean(axis=1))
         all_reduce(score)
-        sc = score.numpy()
-        offsets = np.zeros(n_groups)
-        flags = np.zeros(n, np.uint8)
-        for c in range(n_groups):
-            m = g == c
-            if m.sum() < 2:
-                continue
-            offsets[c] = np.percentile(sc[m], 100.0 * contamination)
-            flags[m] = sc[m] < offsets[c]
-        return torch.from_numpy(sc.copy()), torch.from_numpy(offsets), torch.from_numpy(flags)
+        out = []
+        for pi, (group, n_groups, k, contamination) in enumerate(problems):
+            sc = score[pi].numpy()
+            g = groups[pi]
+            offsets = np.zeros(n_groups)
+            flags = np.zeros(n, np.uint8)
+            for c in range(n_groups):
+                m = g == c
+                if m.sum() < 2:
+                    continue
+                offsets[c] = np.percentile(sc[m], 100.0 * contamination)
+                flags[m] = sc[m] < offsets[c]
+            out.append((torch.from_numpy(sc.copy()), torch.from_numpy(offsets), torch.from_numpy(flags)))
+        return out
+
+    @classmethod
+    def lof_sharded(cls, z, group, n_groups, k, contamination, part, n_parts, all_reduce):
+        return cls.lof_sharded_multi(z, [(group, n_groups, k, contamination)], part, n_parts, all_reduce)[0]

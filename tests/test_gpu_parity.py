@@ -341,16 +341,21 @@ def test_model_callable_like_the_reference(lib):
 
 
 # =============================================================================================== A3 PCA
-def _gpu_pca(ops_mod, x, k):
+def _gpu_pca(ops_mod, x, k, solver=None, first_check=0, want_info=False):
     xt = torch.from_numpy(x).cuda()
     n, d = xt.shape
     shift = xt[: min(256, n)].mean(0).contiguous()
     acc = torch.zeros(1 + d + d * d, dtype=torch.float64, device="cuda")
     count, total, scatter = acc[:1], acc[1:1 + d], acc[1 + d:].view(d, d)
     ops_mod.cov_accumulate(xt, shift, count, total, scatter)
-    mean, comps, evals = ops_mod.pca_fit(count, total, scatter, shift, k)
+    info = None
+    if solver is None:
+        mean, comps, evals = ops_mod.pca_fit(count, total, scatter, shift, k)
+    else:
+        mean, comps, evals, info = ops_mod.pca_fit_ex(count, total, scatter, shift, k, solver, first_check)
     z = ops_mod.pca_transform(xt, mean, comps)
-    return mean.cpu().numpy(), comps.cpu().numpy(), evals.cpu().numpy(), z.cpu().numpy()
+    out = (mean.cpu().numpy(), comps.cpu().numpy(), evals.cpu().numpy(), z.cpu().numpy())
+    return out + (info,) if want_info else out
 
 
 def test_pca_matches_golden(ops_mod):
@@ -430,58 +435,52 @@ def test_pca_full_size_properties(ops_mod):
     np.testing.assert_allclose(z.double().var(0, unbiased=True).cpu().numpy(), ev.cpu().numpy(), rtol=1e-3)
 
 
-def test_pca_lanczos_extends_until_converged_and_matches_eigh(ops_mod, monkeypatch, capfd):
+def test_pca_lanczos_extends_until_converged_and_matches_eigh(ops_mod):
     """Power-law spectrum (lambda_i ~ 1/i, 2 % gaps around the 50th) with the first convergence check forced too
     early (56 steps for 50 pairs): the Krylov iteration must extend itself, and the result must still agree with a
-    dense fp64 eigendecomposition; bitwise repeatable."""
+    dense fp64 eigendecomposition; bitwise repeatable (every reduction on the path has a fixed order)."""
+    from irp_b200 import _lib
     rng = np.random.default_rng(77)
     d, n, k = 2048, 6000, 50
     scale = (np.arange(1, d + 1, dtype=np.float64) ** -0.5).astype(np.float32)
     x = (rng.standard_normal((n, d), dtype=np.float32) * scale)[:, rng.permutation(d)].copy()
-    monkeypatch.setenv("IRP_PCA_DEBUG", "1")
-    monkeypatch.setenv("IRP_PCA_LANCZOS_M0", "56")
-    mean, comps, evals, _ = _gpu_pca(ops_mod, x, k)
-    err = capfd.readouterr().err
-    monkeypatch.delenv("IRP_PCA_DEBUG")
-    assert "lanczos" in err and "check 2" in err, err
+    mean, comps, evals, _, info = _gpu_pca(ops_mod, x, k, _lib.PCA_SOLVER_LANCZOS, 56, want_info=True)
+    assert info["solver"] == _lib.PCA_SOLVER_LANCZOS and info["checks"] >= 2 and info["lanczos_steps"] > 56, info
     ref = pca_ref.pca_fit(x, k)
     assert pca_ref.subspace_angle(comps, ref.components) <= ANGLE_MAX
     assert np.abs(comps @ comps.T - np.eye(k)).max() < 1e-9
     np.testing.assert_allclose(evals[:k], ref.explained_variance, rtol=2e-4)
-    mean2, comps2, evals2, _ = _gpu_pca(ops_mod, x, k)
-    assert np.array_equal(comps, comps2) and np.array_equal(evals, evals2)
+    for _ in range(3):
+        mean2, comps2, evals2, _ = _gpu_pca(ops_mod, x, k, _lib.PCA_SOLVER_LANCZOS, 56)
+        assert np.array_equal(mean, mean2) and np.array_equal(comps, comps2) and np.array_equal(evals, evals2)
 
 
 def test_pca_lanczos_and_householder_agree(ops_mod):
     """The Krylov path and the exact Householder path (taken for small / rank-deficient problems) on one input."""
-    import subprocess, sys, textwrap
-    code = textwrap.dedent("""
-        import sys, numpy as np, torch
-        sys.path.insert(0, %r); sys.path.insert(0, %r)
-        from irp_b200 import ops
-        from oracle import synth
-        x = torch.from_numpy(synth.embedding_like(1200, 2048, seed=3)).cuda()
-        d = 2048
-        shift = x[:256].mean(0).contiguous()
+    from irp_b200 import _lib
+    x = synth.embedding_like(1200, 2048, seed=3)
+    _, ca, ea, _, ia = _gpu_pca(ops_mod, x, 50, _lib.PCA_SOLVER_LANCZOS, want_info=True)
+    _, cb, eb, _, ib = _gpu_pca(ops_mod, x, 50, _lib.PCA_SOLVER_HOUSEHOLDER, want_info=True)
+    assert ia["solver"] == _lib.PCA_SOLVER_LANCZOS and ib["solver"] == _lib.PCA_SOLVER_HOUSEHOLDER
+    np.testing.assert_allclose(ea, eb, rtol=1e-10)
+    assert (np.abs((ca * cb).sum(1)) > 1 - 1e-10).all()
+    assert ((ca * cb).sum(1) > 0).all()  # same sign convention
+
+
+def test_cov_accumulate_is_bitwise_repeatable_and_chunk_ordered(ops_mod):
+    """The scatter matrix, the column sums and the trace are reduced in a fixed order (no floating-point atomics):
+    ten accumulations of the same rows give bit-identical fp64 accumulators and eigenvalues."""
+    x = torch.from_numpy(synth.embedding_like(5000, 2048, seed=21)).cuda()
+    d = 2048
+    shift = x[:256].mean(0).contiguous()
+    ref_acc, ref_ev = None, None
+    for _ in range(10):
         acc = torch.zeros(1 + d + d * d, dtype=torch.float64, device="cuda")
-        ops.cov_accumulate(x, shift, acc[:1], acc[1:1 + d], acc[1 + d:].view(d, d))
-        mean, comps, ev = ops.pca_fit(acc[:1], acc[1:1 + d], acc[1 + d:].view(d, d), shift, 50)
-        np.savez(sys.argv[1], comps=comps.cpu().numpy(), ev=ev.cpu().numpy())
-    """) % (os.path.join(ROOT, "image-recognition-pipeline_b200"), ROOT)
-    import tempfile
-    out = {}
-    with tempfile.TemporaryDirectory() as tmp:
-        for mode in ("lanczos", "householder"):
-            env = dict(os.environ)
-            if mode == "householder":
-                env["IRP_PCA_HOUSEHOLDER"] = "1"
-            path = os.path.join(tmp, mode + ".npz")
-            subprocess.run([sys.executable, "-c", code, path], env=env, check=True, timeout=300)
-            out[mode] = dict(np.load(path))
-    a, b = out["lanczos"], out["householder"]
-    np.testing.assert_allclose(a["ev"], b["ev"], rtol=1e-10)
-    assert (np.abs((a["comps"] * b["comps"]).sum(1)) > 1 - 1e-10).all()
-    assert ((a["comps"] * b["comps"]).sum(1) > 0).all()  # same sign convention
+        ops_mod.cov_accumulate(x, shift, acc[:1], acc[1:1 + d], acc[1 + d:].view(d, d))
+        _, _, ev = ops_mod.pca_fit(acc[:1], acc[1:1 + d], acc[1 + d:].view(d, d), shift, 50)
+        if ref_acc is None:
+            ref_acc, ref_ev = acc.clone(), ev.clone()
+        assert torch.equal(acc, ref_acc) and torch.equal(ev, ref_ev)
 
 
 # =============================================================================================== A4 scoring

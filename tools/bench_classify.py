@@ -19,7 +19,7 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=3)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
-N, B, C = bench.N_IMAGES, bench.BATCH, 10
+N, B, C = 27000, 256, 10
 packed, ids, hw = bench.make_workload(N, seed=0, device=dev)
 taps = max(taps_for(int(h), int(w), _lib.TRANSFORM_VAL_256) for h, w in hw)
 packed = PackedImages(packed.pixels, packed.offsets, packed.hw, taps, packed.offsets_np, packed.hw_np)
