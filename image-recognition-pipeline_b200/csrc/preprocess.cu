@@ -57,6 +57,12 @@ __host__ __device__ inline Geometry compute_geometry(int h, int w, int transform
     g.top = g.left = round_half_even_div2(IRP_VAL_RESIZE - kCrop);
     return g;
   }
+  if (transform == IRP_TRANSFORM_HASH_64) {
+    // functions/data_curation.py:283-292 compute_image_hash: img.resize((64, 64)), aspect ratio not kept, no crop
+    g.out_h = g.out_w = IRP_HASH_SIZE;
+    g.top = g.left = 0;
+    return g;
+  }
   if (transform == IRP_TRANSFORM_WDS_LANCZOS) {
     // functions/data_curation.py:896-913 resize_and_crop_image: smaller side -> 224, the other one
     // int(side * (224 / smaller)) (Python float arithmetic), crop offsets by floor division
@@ -98,6 +104,26 @@ __device__ __forceinline__ double lanczos3_weight(double x) {
   if (-3.0 <= x && x < 3.0) return __dmul_rn(sinc_weight(x), sinc_weight(__ddiv_rn(x, 3.0)));
   return 0.0;
 }
+// bicubic_filter with a = -0.5, Pillow's expression order
+__device__ __forceinline__ double bicubic_weight(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0)
+    return __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(__dadd_rn(a, 2.0), x), __dadd_rn(a, 3.0)), x), x), 1.0);
+  if (x < 2.0)
+    return __dmul_rn(__dsub_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dsub_rn(x, 5.0), x), 8.0), x), 4.0), a);
+  return 0.0;
+}
+// filter of a transform: 0 triangle (support 1), 1 Lanczos (support 3), 2 bicubic (support 2)
+__host__ __device__ inline int transform_filter(int transform) {
+  return transform == IRP_TRANSFORM_WDS_LANCZOS ? 1 : (transform == IRP_TRANSFORM_HASH_64 ? 2 : 0);
+}
+__host__ __device__ inline int transform_out_size(int transform) {
+  return transform == IRP_TRANSFORM_HASH_64 ? IRP_HASH_SIZE : kCrop;
+}
+__device__ __forceinline__ double filter_weight(int filt, double x) {
+  return filt == 1 ? lanczos3_weight(x) : (filt == 2 ? bicubic_weight(x) : triangle_weight(x));
+}
 
 // One CTA (448 threads) per image: thread (axis, o) computes the taps of output index o; the CTA then chooses the
 // fused kernel's band height for the image and appends one 64-byte work record per band to the heavy / normal list.
@@ -129,11 +155,12 @@ __global__ void __launch_bounds__(2 * kCrop) resample_plan_kernel(const int32_t*
   if (j < 4) s_red[j] = 0;
   const int axis = j / kCrop;  // 0: horizontal (x), 1: vertical (y)
   const int o = j % kCrop;
+  const int n_out = transform_out_size(transform);  // outputs per axis; the tables keep 224 entries, the rest is empty
   const int h = hw[2 * img], w = hw[2 * img + 1];
   const Geometry g = compute_geometry(h, w, transform);
   const int in_size = axis == 0 ? w : h;
   const int out_size = axis == 0 ? g.out_w : g.out_h;
-  const int xx = o + (axis == 0 ? g.left : g.top);
+  const int xx = (o < n_out ? o : n_out - 1) + (axis == 0 ? g.left : g.top);
 
   int32_t* base = plan + (static_cast<size_t>(img) * 2 + axis) * plan_ints_per_axis(max_taps);
   int32_t* first = base;
@@ -146,10 +173,10 @@ __global__ void __launch_bounds__(2 * kCrop) resample_plan_kernel(const int32_t*
   } else {
     // Pillow precompute_coeffs (bilinear: support 1.0, Lanczos: support 3.0), evaluated in fp64 without FMA
     // contraction.
-    const bool lanczos = transform == IRP_TRANSFORM_WDS_LANCZOS;
+    const int filt = transform_filter(transform);
     const double scale = __ddiv_rn(static_cast<double>(in_size), static_cast<double>(out_size));
     const double filterscale = scale < 1.0 ? 1.0 : scale;
-    const double support = lanczos ? __dmul_rn(3.0, filterscale) : filterscale;
+    const double support = filt == 1 ? __dmul_rn(3.0, filterscale) : (filt == 2 ? __dmul_rn(2.0, filterscale) : filterscale);
     const double center = __dmul_rn(__dadd_rn(static_cast<double>(xx), 0.5), scale);
     const double ss = __ddiv_rn(1.0, filterscale);
     xmin = static_cast<int>(__dadd_rn(__dsub_rn(center, support), 0.5));
@@ -164,17 +191,18 @@ __global__ void __launch_bounds__(2 * kCrop) resample_plan_kernel(const int32_t*
     double ww = 0.0;
     for (int x = 0; x < n; ++x) {
       const double a = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
-      ww = __dadd_rn(ww, lanczos ? lanczos3_weight(a) : triangle_weight(a));
+      ww = __dadd_rn(ww, filter_weight(filt, a));
     }
     for (int x = 0; x < n; ++x) {
       const double a = __dmul_rn(__dadd_rn(__dsub_rn(static_cast<double>(x + xmin), center), 0.5), ss);
-      double wgt = lanczos ? lanczos3_weight(a) : triangle_weight(a);
+      double wgt = filter_weight(filt, a);
       if (ww != 0.0) wgt = __ddiv_rn(wgt, ww);
       // normalize_coeffs_8bpc: round half away from zero into 22-bit fixed point
       const double scaled = __dmul_rn(wgt, static_cast<double>(1 << kPrecisionBits));
       coef[x] = wgt < 0.0 ? static_cast<int>(__dadd_rn(-0.5, scaled)) : static_cast<int>(__dadd_rn(0.5, scaled));
     }
   }
+  if (o >= n_out) n = 0;  // table entries past the transform's output size: no taps, nothing is read for them
   first[o] = xmin;
   count[o] = n;
   s_first[axis][o] = xmin;
@@ -185,15 +213,16 @@ __global__ void __launch_bounds__(2 * kCrop) resample_plan_kernel(const int32_t*
   const int nth = s_red[0], ntv = s_red[1];
   // ---- schedule of the fused kernel: the largest band height whose source rows fit its intermediate ----
   const int col_first = s_first[0][0] * 3;
-  const int width = (s_first[0][kCrop - 1] + s_count[0][kCrop - 1]) * 3 - col_first;
+  const int width = (s_first[0][n_out - 1] + s_count[0][n_out - 1]) * 3 - col_first;
   const int pitch = ((width + 31) + 15) & ~15;
+  const bool heavy = transform_filter(transform) != 0 || nth > 6;  // generic horizontal loop: queue first
   if (j < 32) {
     int th = 0;
     if (pitch <= kFStageBytes) {
       for (int cand = kFMaxBand; cand >= 1 && th == 0; cand >>= 1) {
         if (cand * ntv > kFVcoefInts) continue;
         int mx = 0;
-        for (int b = j; b < kCrop / cand; b += 32) {
+        for (int b = j; b < n_out / cand; b += 32) {
           const int y0 = b * cand, y1 = y0 + cand - 1;
           mx = max(mx, s_first[1][y1] + s_count[1][y1] - s_first[1][y0]);
         }
@@ -203,9 +232,8 @@ __global__ void __launch_bounds__(2 * kCrop) resample_plan_kernel(const int32_t*
       }
     }
     if (j == 0) {
-      const bool heavy = transform == IRP_TRANSFORM_WDS_LANCZOS || nth > 6;
       s_red[2] = th;
-      s_red[3] = th > 0 ? atomicAdd(&counters[heavy ? 0 : 1], kCrop / th) : 0;
+      s_red[3] = th > 0 ? atomicAdd(&counters[heavy ? 0 : 1], n_out / th) : 0;
       img_info[4 * img + 0] = th;
       img_info[4 * img + 1] = nth;
       img_info[4 * img + 2] = ntv;
@@ -214,8 +242,7 @@ __global__ void __launch_bounds__(2 * kCrop) resample_plan_kernel(const int32_t*
   }
   __syncthreads();
   const int th = s_red[2];
-  if (th > 0 && j < kCrop / th) {
-    const bool heavy = transform == IRP_TRANSFORM_WDS_LANCZOS || nth > 6;
+  if (th > 0 && j < n_out / th) {
     FusedItem it;
     const int y0 = j * th;
     it.img = img;
@@ -247,10 +274,11 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(const uint8_t* __res
                                                             const int32_t* __restrict__ hw, int max_taps,
                                                             const int32_t* __restrict__ plan,
                                                             const int32_t* __restrict__ img_info,
-                                                            __nv_bfloat16* __restrict__ out) {
+                                                            __nv_bfloat16* __restrict__ out, int n_out) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int T = max_taps;
   if (img_info[4 * blockIdx.y] != 0) return;  // the fused kernel takes this image
+  if (static_cast<int>(blockIdx.x) * kBandRows >= n_out) return;  // band past the transform's output rows
   int32_t* hfirst = reinterpret_cast<int32_t*>(smem);
   int32_t* hcount = hfirst + kCrop;
   int32_t* hcoef = hcount + kCrop;
@@ -342,13 +370,14 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(const uint8_t* __res
 
   // ---- normalise + stage ----
   if (LAYOUT == IRP_LAYOUT_U8_HWC) {
-    uint8_t* o8 = reinterpret_cast<uint8_t*>(out) + (static_cast<size_t>(img) * kCrop + y0) * kRowElems;
+    // uint8 [n, n_out, n_out, 3]
+    uint8_t* o8 = reinterpret_cast<uint8_t*>(out) + (static_cast<size_t>(img) * n_out + y0) * n_out * 3;
 #pragma unroll
     for (int y = 0; y < kBandRows; ++y)
 #pragma unroll
       for (int k = 0; k < kElemsPerThread; ++k) {
         const int e = tid + k * kThreads;
-        if (e < kRowElems) o8[static_cast<size_t>(y) * kRowElems + e] = static_cast<uint8_t>(clip8_fixed(acc[y][k]));
+        if (e < n_out * 3) o8[static_cast<size_t>(y) * n_out * 3 + e] = static_cast<uint8_t>(clip8_fixed(acc[y][k]));
       }
   } else if (LAYOUT == IRP_LAYOUT_NHWC4P) {
     // obuf[8][230][4]; zero everything first (borders + pad channel)
@@ -458,7 +487,7 @@ static int launch_generic(const FusedParams& fp, const int64_t* d_offsets, const
   IRP_TRY(ensure_smem(k, smem));
   dim3 grid(kCrop / kBandRows, n_images);
   k<<<grid, kThreads, smem, st>>>(fp.pixels, d_offsets, d_hw, fp.max_taps, fp.plan, fp.img_info,
-                                  static_cast<__nv_bfloat16*>(fp.out));
+                                  static_cast<__nv_bfloat16*>(fp.out), fp.out_size);
   IRP_CUDA_OK(cudaGetLastError());
   return IRP_OK;
 }
@@ -540,8 +569,10 @@ int irp_preprocess_ex(const uint8_t* d_pixels, const int64_t* d_offsets, const i
                       int transform, void* stream) {
   IRP_REQUIRE(d_pixels && d_offsets && d_hw && d_workspace && d_out, "preprocess: null argument");
   IRP_REQUIRE(transform == IRP_TRANSFORM_WEIGHTS_DEFAULT || transform == IRP_TRANSFORM_VAL_256 ||
-                  transform == IRP_TRANSFORM_WDS_LANCZOS,
+                  transform == IRP_TRANSFORM_WDS_LANCZOS || transform == IRP_TRANSFORM_HASH_64,
               "preprocess: unknown transform %d", transform);
+  IRP_REQUIRE(transform != IRP_TRANSFORM_HASH_64 || out_layout == IRP_LAYOUT_U8_HWC,
+              "preprocess: IRP_TRANSFORM_HASH_64 writes uint8 [n,64,64,3] (IRP_LAYOUT_U8_HWC) only");
   IRP_REQUIRE(n_images > 0 && n_images < (1 << 23), "preprocess: n_images %d", n_images);
   IRP_REQUIRE(max_taps >= 3 && max_taps <= 513, "preprocess: max_taps %d out of range", max_taps);
   IRP_REQUIRE(out_layout == IRP_LAYOUT_NCHW || out_layout == IRP_LAYOUT_NHWC4P || out_layout == IRP_LAYOUT_U8_HWC,
@@ -557,7 +588,7 @@ int irp_preprocess_ex(const uint8_t* d_pixels, const int64_t* d_offsets, const i
                                                        w.status, w.lut, w.img_info, w.counters, w.items_heavy,
                                                        w.items_normal);
   IRP_CUDA_OK(cudaGetLastError());
-  const bool lanczos = transform == IRP_TRANSFORM_WDS_LANCZOS;
+  const bool lanczos = transform_filter(transform) != 0;  // Lanczos / bicubic: negative weights, signed arithmetic
   FusedParams fp;
   fp.pixels = d_pixels;
   fp.plan = w.plan;
@@ -569,6 +600,7 @@ int irp_preprocess_ex(const uint8_t* d_pixels, const int64_t* d_offsets, const i
   fp.lut = w.lut;
   fp.out = d_out;
   fp.max_taps = max_taps;
+  fp.out_size = transform_out_size(transform);
   if (out_layout == IRP_LAYOUT_U8_HWC)
     return lanczos ? launch_fused<IRP_LAYOUT_U8_HWC, true>(fp, d_offsets, d_hw, n_images, st)
                    : launch_fused<IRP_LAYOUT_U8_HWC, false>(fp, d_offsets, d_hw, n_images, st);
@@ -599,7 +631,7 @@ int irp_preprocess_geometry(int h, int w, int* out_h, int* out_w, int* top, int*
 int irp_preprocess_geometry_ex(int h, int w, int transform, int* out_h, int* out_w, int* top, int* left, int* taps) {
   IRP_REQUIRE(h > 0 && w > 0, "geometry: bad size %dx%d", h, w);
   IRP_REQUIRE(transform == IRP_TRANSFORM_WEIGHTS_DEFAULT || transform == IRP_TRANSFORM_VAL_256 ||
-                  transform == IRP_TRANSFORM_WDS_LANCZOS,
+                  transform == IRP_TRANSFORM_WDS_LANCZOS || transform == IRP_TRANSFORM_HASH_64,
               "geometry: unknown transform %d", transform);
   const Geometry g = compute_geometry(h, w, transform);
   if (out_h) *out_h = g.out_h;
@@ -611,6 +643,7 @@ int irp_preprocess_geometry_ex(int h, int w, int transform, int* out_h, int* out
     double s = sx > sy ? sx : sy;
     if (s < 1.0) s = 1.0;
     if (transform == IRP_TRANSFORM_WDS_LANCZOS) s *= 3.0;  // Lanczos support
+    if (transform == IRP_TRANSFORM_HASH_64) s *= 2.0;      // bicubic support
     int c = static_cast<int>(s);
     if (static_cast<double>(c) < s) ++c;
     *taps = 2 * c + 1;

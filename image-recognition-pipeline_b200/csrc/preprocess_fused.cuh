@@ -62,6 +62,7 @@ struct FusedParams {
   const __nv_bfloat16* lut;     // [3][256]
   void* out;
   int max_taps;
+  int out_size;                 // rows = columns of the output (224; 64 for IRP_TRANSFORM_HASH_64)
 };
 
 __host__ __device__ inline size_t fused_plan_ints_per_axis(int max_taps) {
@@ -164,12 +165,14 @@ __device__ __forceinline__ void hpass_generic(const HRowGeom& g, const int32_t* 
 // ------------------------------------------------------------------------------------------------------------
 template <int LAYOUT>
 __device__ __forceinline__ void store_pixel(void* out, int img, int y, int x, uint32_t v0, uint32_t v1, uint32_t v2,
-                                            const uint16_t* __restrict__ lut_s, bool poisoned) {
-  if (LAYOUT == IRP_LAYOUT_U8_HWC) {
-    uint8_t* o8 = static_cast<uint8_t*>(out) + ((static_cast<size_t>(img) * kFCrop + y) * kFCrop + x) * 3;
-    o8[0] = static_cast<uint8_t>(v0);
-    o8[1] = static_cast<uint8_t>(v1);
-    o8[2] = static_cast<uint8_t>(v2);
+                                            const uint16_t* __restrict__ lut_s, bool poisoned, int out_size) {
+  if (LAYOUT == IRP_LAYOUT_U8_HWC) {  // uint8 [n, out_size, out_size, 3]
+    if (x < out_size) {
+      uint8_t* o8 = static_cast<uint8_t*>(out) + ((static_cast<size_t>(img) * out_size + y) * out_size + x) * 3;
+      o8[0] = static_cast<uint8_t>(v0);
+      o8[1] = static_cast<uint8_t>(v1);
+      o8[2] = static_cast<uint8_t>(v2);
+    }
     return;
   }
   uint32_t l0 = lut_s[v0], l1 = lut_s[256 + v1], l2 = lut_s[512 + v2];
@@ -189,7 +192,7 @@ __device__ __forceinline__ void store_pixel(void* out, int img, int y, int x, ui
 template <int LAYOUT, int NTV>
 __device__ __forceinline__ void vpass_fast(const uint32_t* __restrict__ inter, const int32_t* __restrict__ voff,
                                            const int32_t* __restrict__ vcoef, int th, int y0, int x, int rg, int img,
-                                           void* out, const uint16_t* __restrict__ lut_s, bool poisoned) {
+                                           void* out, const uint16_t* __restrict__ lut_s, bool poisoned, int out_size) {
   for (int yl = rg; yl < th; yl += 2) {
     const uint32_t* ip = inter + voff[yl] + x;
     uint32_t w[8];
@@ -203,7 +206,7 @@ __device__ __forceinline__ void vpass_fast(const uint32_t* __restrict__ inter, c
       a1 += __byte_perm(px, 0u, 0x4441u) * w[t];
       a2 += __byte_perm(px, 0u, 0x4442u) * w[t];
     }
-    store_pixel<LAYOUT>(out, img, y0 + yl, x, a0 >> 24, a1 >> 24, a2 >> 24, lut_s, poisoned);
+    store_pixel<LAYOUT>(out, img, y0 + yl, x, a0 >> 24, a1 >> 24, a2 >> 24, lut_s, poisoned, out_size);
   }
 }
 
@@ -212,7 +215,7 @@ template <int LAYOUT, bool SIGNED>
 __device__ __forceinline__ void vpass_generic(const uint32_t* __restrict__ inter, const int32_t* __restrict__ voff,
                                               const int32_t* __restrict__ vcount, const int32_t* __restrict__ vcoef,
                                               int ntv, int th, int y0, int x, int rg, int img, void* out,
-                                              const uint16_t* __restrict__ lut_s, bool poisoned) {
+                                              const uint16_t* __restrict__ lut_s, bool poisoned, int out_size) {
   for (int yl = rg; yl < th; yl += 2) {
     const int vn = vcount[yl];
     const uint32_t* ip = inter + voff[yl] + x;
@@ -243,7 +246,7 @@ __device__ __forceinline__ void vpass_generic(const uint32_t* __restrict__ inter
       v1 = fused_clip8(a1);
       v2 = fused_clip8(a2);
     }
-    store_pixel<LAYOUT>(out, img, y0 + yl, x, v0, v1, v2, lut_s, poisoned);
+    store_pixel<LAYOUT>(out, img, y0 + yl, x, v0, v1, v2, lut_s, poisoned, out_size);
   }
 }
 
@@ -382,11 +385,11 @@ __global__ void __launch_bounds__(kFThreads, 2) resample_fused_kernel(const Fuse
     if (k_next < n_total) issue(geometry(nxt), 0, stage0);
 
     // ---- vertical pass + normalise + store ----
-    if (!vfast) vpass_generic<LAYOUT, SIGNED>(inter, voff, vcount, vcoef, ntv, th, y0, x, rg, img, p.out, lut_s, poisoned);
-    else if (ntv <= 3) vpass_fast<LAYOUT, 3>(inter, voff, vcoef, th, y0, x, rg, img, p.out, lut_s, poisoned);
-    else if (ntv == 4) vpass_fast<LAYOUT, 4>(inter, voff, vcoef, th, y0, x, rg, img, p.out, lut_s, poisoned);
-    else if (ntv <= 6) vpass_fast<LAYOUT, 6>(inter, voff, vcoef, th, y0, x, rg, img, p.out, lut_s, poisoned);
-    else vpass_fast<LAYOUT, 8>(inter, voff, vcoef, th, y0, x, rg, img, p.out, lut_s, poisoned);
+    if (!vfast) vpass_generic<LAYOUT, SIGNED>(inter, voff, vcount, vcoef, ntv, th, y0, x, rg, img, p.out, lut_s, poisoned, p.out_size);
+    else if (ntv <= 3) vpass_fast<LAYOUT, 3>(inter, voff, vcoef, th, y0, x, rg, img, p.out, lut_s, poisoned, p.out_size);
+    else if (ntv == 4) vpass_fast<LAYOUT, 4>(inter, voff, vcoef, th, y0, x, rg, img, p.out, lut_s, poisoned, p.out_size);
+    else if (ntv <= 6) vpass_fast<LAYOUT, 6>(inter, voff, vcoef, th, y0, x, rg, img, p.out, lut_s, poisoned, p.out_size);
+    else vpass_fast<LAYOUT, 8>(inter, voff, vcoef, th, y0, x, rg, img, p.out, lut_s, poisoned, p.out_size);
     if (LAYOUT == IRP_LAYOUT_NHWC4P) {
       // zero borders: 3 pixels left and right of every row of the band, 3 full rows above / below the image
       uint2* base = static_cast<uint2*>(p.out) + static_cast<size_t>(img) * kFPad * kFPad;

@@ -262,6 +262,39 @@ def create_results_dataframe(embedding, labels, paths, class_outliers, global_ou
 
 
 # -----------------------------------------------------------------------------------------------------------------
+# Dataset cleaning: the duplicate hash (reference functions/data_curation.py:283-292,
+# call site :394-399)
+# -----------------------------------------------------------------------------------------------------------------
+def compute_image_hashes(images, device="cuda:0", batch_size=256):
+    """Batch form of `compute_image_hash`: a list of PIL images -> list of md5 hex strings, identical to the
+    reference's.  RGB images take the device path (Pillow-exact bicubic 64x64 resize + MD5, both libirp_b200 kernels).
+    The reference resizes in the image's OWN mode and converts afterwards (:287-288); for the rare non-RGB inputs
+    (the recorded dataset has 1 grayscale and 50 RGBA images in 26 179) that resize stays Pillow's on the host, like
+    the decode, and the device computes the digest."""
+    dev = torch.device(device)
+    out = [None] * len(images)
+    rgb = [i for i, im in enumerate(images) if im.mode == "RGB"]
+    for lo in range(0, len(rgb), batch_size):
+        idx = rgb[lo:lo + batch_size]
+        part = pack_images([np.asarray(images[i]) for i in idx], transform=_lib.TRANSFORM_HASH_64).to(dev)
+        digests = ops.image_hashes(part.pixels, part.offsets, part.hw, part.max_taps).cpu().numpy()
+        for i, d in zip(idx, digests):
+            out[i] = d.tobytes().hex()
+    other = [i for i, im in enumerate(images) if im.mode != "RGB"]
+    if other:
+        small = np.stack([np.asarray(images[i].copy().resize((64, 64)).convert("RGB")) for i in other])
+        data = torch.from_numpy(small.reshape(len(other), -1)).to(dev)
+        for i, d in zip(other, ops.md5_rows(data).cpu().numpy()):
+            out[i] = d.tobytes().hex()
+    return out
+
+
+def compute_image_hash(img, device="cuda:0"):
+    """Compute a hash from image data to detect duplicates (drop-in: same hex digest as the reference)."""
+    return compute_image_hashes([img], device=device)[0]
+
+
+# -----------------------------------------------------------------------------------------------------------------
 # WebDataset curation: the resize step (SURVEY.md section 8f, row N2; reference functions/data_curation.py:883-913)
 # -----------------------------------------------------------------------------------------------------------------
 def _to_rgb(img):

@@ -19,6 +19,8 @@ LAYOUT_NCHW = 0
 TRANSFORM_WEIGHTS_DEFAULT = 0  # ResNet50_Weights.DEFAULT.transforms() (resize 232, crop 224)
 TRANSFORM_VAL_256 = 1          # functions/dataload.py:51-56 (Resize((256,256)), CenterCrop(224))
 TRANSFORM_WDS_LANCZOS = 2      # functions/data_curation.py:883-913 (smaller side -> 224, LANCZOS, center crop)
+TRANSFORM_HASH_64 = 3          # functions/data_curation.py:283-292 (img.resize((64, 64)), BICUBIC) -> uint8 [n,64,64,3]
+HASH_SIZE = 64
 LAYOUT_U8_HWC = 2              # uint8 [n,224,224,3]: the resized pixels themselves (no normalisation)
 LAYOUT_NHWC4P = 1
 CROP = 224
@@ -44,6 +46,7 @@ SIGNATURES = {
     "irp_preprocess_status": (_i, [_vp, _i, _i, _vp]),
     "irp_preprocess_ex": (_i, [_vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _i, _i, _vp]),
     "irp_preprocess_geometry_ex": (_i, [_i, _i, _i] + [C.POINTER(_i)] * 5),
+    "irp_md5_rows": (_i, [_vp, _i, _i64, _vp, _vp]),
     "irp_classifier_head_workspace_bytes": (_sz, [_i, _i]),
     "irp_classifier_head": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "irp_cross_entropy_stats": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -73,9 +73,10 @@ def _(pixels, offsets, hw, max_taps, layout):
     return pixels.new_empty(shape, dtype=torch.bfloat16)
 
 
-def _preprocess_out(n: int, layout: int):
+def _preprocess_out(n: int, layout: int, transform: int = 0):
     if layout == _lib.LAYOUT_U8_HWC:
-        return (n, _lib.CROP, _lib.CROP, 3), torch.uint8
+        side = _lib.HASH_SIZE if transform == _lib.TRANSFORM_HASH_64 else _lib.CROP
+        return (n, side, side, 3), torch.uint8
     if layout == _lib.LAYOUT_NCHW:
         return (n, 3, _lib.CROP, _lib.CROP), torch.bfloat16
     return (n, _lib.PAD_HW, _lib.PAD_HW, 4), torch.bfloat16
@@ -91,7 +92,7 @@ def preprocess_ex(pixels: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor,
     lib = _lib_for(pixels)
     assert pixels.dtype == torch.uint8 and offsets.dtype == torch.int64 and hw.dtype == torch.int32
     n = hw.shape[0]
-    shape, dtype = _preprocess_out(n, layout)
+    shape, dtype = _preprocess_out(n, layout, transform)
     out = torch.empty(shape, dtype=dtype, device=pixels.device)
     ws_bytes = lib.irp_preprocess_workspace_bytes(n, max_taps)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pixels.device)
@@ -102,8 +103,26 @@ def preprocess_ex(pixels: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor,
 
 @preprocess_ex.register_fake
 def _(pixels, offsets, hw, max_taps, layout, transform):
-    shape, dtype = _preprocess_out(hw.shape[0], layout)
+    shape, dtype = _preprocess_out(hw.shape[0], layout, transform)
     return pixels.new_empty(shape, dtype=dtype)
+
+
+@_on_device_of(0)
+def md5_rows(data: torch.Tensor) -> torch.Tensor:
+    """RFC 1321 MD5 of every row of a contiguous uint8 [n, row_bytes] CUDA tensor -> uint8 [n, 16] digests."""
+    lib = _lib_for(data)
+    assert data.dtype == torch.uint8 and data.is_contiguous() and data.dim() == 2
+    n, row_bytes = data.shape
+    digest = torch.empty((n, 16), dtype=torch.uint8, device=data.device)
+    _lib.check(lib.irp_md5_rows(_ptr(data), n, row_bytes, _ptr(digest), _stream(data)), "irp_md5_rows")
+    return digest
+
+
+def image_hashes(pixels: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor, max_taps: int) -> torch.Tensor:
+    """compute_image_hash (functions/data_curation.py:283-292) of a packed batch of RGB images: Pillow-exact bicubic
+    resize to 64x64 and md5 of the 12 288 bytes, both on the device -> uint8 [n, 16]."""
+    small = preprocess_ex(pixels, offsets, hw, max_taps, _lib.LAYOUT_U8_HWC, _lib.TRANSFORM_HASH_64)
+    return md5_rows(small.view(small.shape[0], -1))
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -150,7 +150,7 @@ def taps_for(h: int, w: int, transform: int = 0) -> int:
     transform 0 = short side -> 232, 1 = Resize((256,256)) of the classifier's val_transform."""
     if transform == _lib.TRANSFORM_VAL_256:
         return 2 * int(math.ceil(max(h / 256, w / 256, 1.0))) + 1
-    if transform == _lib.TRANSFORM_WDS_LANCZOS:
+    if transform in (_lib.TRANSFORM_WDS_LANCZOS, _lib.TRANSFORM_HASH_64):
         return _lib.geometry(h, w, transform)[4]
     if w <= h:
         out_w, out_h = 232, int(232 * h / w)

@@ -86,10 +86,16 @@ int irp_preprocess_status(const void* d_workspace, int n_images, int max_taps, v
  *                                  (support 3), the other side int(side * (224 / smaller)), crop offsets by floor
  *                                  division.  Meant for IRP_LAYOUT_U8_HWC: uint8 [n,224,224,3], the bytes of the
  *                                  PIL image the reference returns (any layout / transform pair is accepted).
+ *   IRP_TRANSFORM_HASH_64          the duplicate hash's resize, functions/data_curation.py:283-292:
+ *                                  img.resize((64, 64)) with Pillow's default BICUBIC filter (a = -0.5, support 2),
+ *                                  aspect ratio not kept, no crop.  IRP_LAYOUT_U8_HWC only; the output is
+ *                                  uint8 [n,64,64,3] (irp_md5_rows then hashes the 12 288 bytes of each image).
+ *                                  max_taps: 2*ceil(2*max(1, h/64, w/64))+1.
  * max_taps for VAL_256: 2*ceil(max(1, h/256, w/256))+1; for WDS_LANCZOS: 2*ceil(3*max(1, smaller/224))+1
  * (irp_preprocess_geometry_ex returns it per image). */
-enum { IRP_TRANSFORM_WEIGHTS_DEFAULT = 0, IRP_TRANSFORM_VAL_256 = 1, IRP_TRANSFORM_WDS_LANCZOS = 2 };
-enum { IRP_VAL_RESIZE = 256 };
+enum { IRP_TRANSFORM_WEIGHTS_DEFAULT = 0, IRP_TRANSFORM_VAL_256 = 1, IRP_TRANSFORM_WDS_LANCZOS = 2,
+       IRP_TRANSFORM_HASH_64 = 3 };
+enum { IRP_VAL_RESIZE = 256, IRP_HASH_SIZE = 64 };
 int irp_preprocess_geometry_ex(int h, int w, int transform, int* out_h, int* out_w, int* top, int* left, int* taps);
 int irp_preprocess_ex(const uint8_t* d_pixels, const int64_t* d_offsets, const int32_t* d_hw, int n_images,
                       int max_taps, void* d_workspace, size_t workspace_bytes, void* d_out, int out_layout,
@@ -147,6 +153,14 @@ int irp_conv1x1_chain(const void* d_t2, const void* d_w3, const float* d_b3, con
 int irp_conv1x1_chain_ds(const void* d_t2, const void* d_x, const void* d_wcat, const float* d_bias, void* d_y,
                          const void* d_w1, const float* d_b1, void* d_t1, int64_t rows, int K1, int K2, int N1, int N2,
                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * N3  duplicate-detection hash  --  replaces compute_image_hash (functions/data_curation.py:283-292; call site
+ * :394-399): md5 of the RGB bytes of img.resize((64, 64)).  irp_preprocess_ex(IRP_LAYOUT_U8_HWC,
+ * IRP_TRANSFORM_HASH_64) is the resize; irp_md5_rows is RFC 1321 MD5 of every row of a [n_rows, row_bytes] uint8
+ * matrix (row_bytes = 12 288 for the hash): d_digest uint8 [n_rows, 16], hexdigest = the 16 bytes in order.
+ * ---------------------------------------------------------------------------------------------------------- */
+int irp_md5_rows(const uint8_t* d_data, int n_rows, int64_t row_bytes, uint8_t* d_digest, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * A3  PCA  --  replaces PCA(n_components).fit_transform at functions/data_curation.py:700-701 with the exact

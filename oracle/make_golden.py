@@ -202,6 +202,30 @@ def golden_wds_resize(dc):
     print("wds_resize.npz:", len(sizes), "images")
 
 
+def golden_hash(dc):
+    """the reference's compute_image_hash (data_curation.py:283-292), unmodified, on RGB inputs of
+    assorted sizes (the dataset's smallest 60x57, up- and downscales, one that needs 40+ taps), plus an exact
+    duplicate and a one-pixel-off near-duplicate (the pair the dataset scan at :394-399 must tell apart)."""
+    from PIL import Image
+
+    sizes = [(57, 60), (64, 64), (224, 224), (253, 320), (300, 400), (400, 300), (700, 500), (64, 900),
+             (1000, 1300), (1500, 1400)]
+    seeds, hexes = [], []
+    for i, (h, w) in enumerate(sizes):
+        seed = 5000 + i
+        img = wds_input(seed, h, w, smooth=(i % 2 == 0))
+        hexes.append(dc.compute_image_hash(Image.fromarray(img)))
+        seeds.append(seed)
+    dup = wds_input(5004, 300, 400, smooth=True)           # same pixels as entry 4
+    near = dup.copy()
+    near[150, 200, 1] ^= 0x40                               # one channel of one pixel changed
+    extra = [dc.compute_image_hash(Image.fromarray(dup)), dc.compute_image_hash(Image.fromarray(near))]
+    assert extra[0] == hexes[4] and extra[1] != hexes[4]
+    np.savez_compressed(os.path.join(GOLDEN, "hash.npz"), sizes=np.array(sizes, np.int32),
+                        seeds=np.array(seeds, np.int64), hexdigests=np.array(hexes), near_hex=np.array(extra[1]))
+    print("hash.npz:", len(sizes), "images", hexes[:2])
+
+
 def golden_classifier():
     """the reference's val_transform, AnimalClassifier and evaluate_full, unmodified except that
     ``functions.model.resnet50`` is patched to build the random-init network (no download; the seed is set right
@@ -253,9 +277,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "wds":
         golden_wds_resize(dc)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "hash":
+        golden_hash(dc)
+        sys.exit(0)
     golden_preprocess(dc)
     golden_embeddings(dc)
     golden_pca(dc)
     golden_lof(dc)
     golden_classifier()
     golden_wds_resize(dc)
+    golden_hash(dc)

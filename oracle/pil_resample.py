@@ -66,7 +66,18 @@ def _lanczos3(x: float) -> float:
     return 0.0
 
 
-FILTERS = {"bilinear": (_triangle, 1.0), "lanczos": (_lanczos3, 3.0)}
+def _bicubic(x: float) -> float:
+    """Pillow bicubic_filter (a = -0.5), support 2."""
+    a = -0.5
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+FILTERS = {"bilinear": (_triangle, 1.0), "lanczos": (_lanczos3, 3.0), "bicubic": (_bicubic, 2.0)}
 
 
 def precompute_coeffs(in_size: int, out_size: int, filt: str = "bilinear"):
@@ -204,6 +215,30 @@ def wds_transform_u8(img: np.ndarray) -> np.ndarray:
     r = resize_bilinear_u8(img, out_h, out_w, "lanczos")
     top, left = (out_h - CROP) // 2, (out_w - CROP) // 2
     return np.ascontiguousarray(r[top:top + CROP, left:left + CROP])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the duplicate-detection hash: /root/reference/functions/data_curation.py:283-292
+# compute_image_hash: img.resize((64, 64)) -- Pillow's default filter for RGB images is BICUBIC, aspect ratio not
+# kept, no crop -- then convert("RGB") (a no-op for RGB input), tobytes(), hashlib.md5(...).hexdigest().
+# ---------------------------------------------------------------------------------------------------------------
+HASH_SIZE = 64
+
+
+def hash_max_taps(h: int, w: int) -> int:
+    s = 2.0 * max(h / HASH_SIZE, w / HASH_SIZE, 1.0)
+    return 2 * int(math.ceil(s)) + 1
+
+
+def hash_resize_u8(img: np.ndarray) -> np.ndarray:
+    """Image.resize((64, 64)) of an HWC uint8 RGB array -> uint8 [64,64,3]."""
+    return np.ascontiguousarray(resize_bilinear_u8(img, HASH_SIZE, HASH_SIZE, "bicubic"))
+
+
+def image_hash(img: np.ndarray) -> str:
+    """compute_image_hash of an RGB image given as an HWC uint8 array."""
+    import hashlib
+    return hashlib.md5(hash_resize_u8(img).tobytes()).hexdigest()
 
 
 def to_bf16_bits(x: np.ndarray) -> np.ndarray:

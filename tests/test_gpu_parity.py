@@ -874,3 +874,54 @@ def test_bilinear_many_tap_images_bit_exact(ops_mod):
     imgs = [np.random.default_rng(90 + i).integers(0, 256, (h, w, 3), dtype=np.uint8) for i, (h, w) in enumerate(sizes)]
     assert torch.equal(_preprocess(ops_mod, imgs, 0).cpu(), _expected_bf16(imgs))
     assert torch.equal(_preprocess(ops_mod, imgs, 1).cpu()[:, 3:227, 3:227, :3], _expected_bf16(imgs).permute(0, 2, 3, 1))
+
+
+# =============================================================================================== N3 duplicate hash
+def test_image_hash_matches_reference_golden(ops_mod, lib):
+    """compute_image_hash on the device (bicubic 64x64 resize + MD5) against the hex digests the UNMODIFIED reference
+    function produced (tests/golden/hash.npz), through the batched op and through the PIL drop-in; then sizes that
+    need the narrow bands / the band-kernel fallback (downscales up to 45x), against the oracle restatement."""
+    from PIL import Image
+    from functions import data_curation as dc
+    from irp_b200 import _lib
+    from irp_b200.stage import pack_images
+    from oracle.make_golden import wds_input
+    g = load_golden("hash.npz")
+    imgs = [wds_input(int(s), int(h), int(w), smooth=(i % 2 == 0))
+            for i, ((h, w), s) in enumerate(zip(g["sizes"], g["seeds"]))]
+    part = pack_images(imgs, transform=_lib.TRANSFORM_HASH_64).to("cuda")
+    small = ops_mod.preprocess_ex(part.pixels, part.offsets, part.hw, part.max_taps, _lib.LAYOUT_U8_HWC,
+                                  _lib.TRANSFORM_HASH_64).cpu().numpy()
+    for img, got in zip(imgs, small):
+        assert np.array_equal(got, pil_resample.hash_resize_u8(img)), img.shape
+    digests = ops_mod.image_hashes(part.pixels, part.offsets, part.hw, part.max_taps).cpu().numpy()
+    assert [d.tobytes().hex() for d in digests] == [str(x) for x in g["hexdigests"]]
+    pil = [Image.fromarray(im) for im in imgs]
+    assert dc.compute_image_hashes(pil) == [str(x) for x in g["hexdigests"]]
+    near = imgs[4].copy()
+    near[150, 200, 1] ^= 0x40
+    assert dc.compute_image_hash(Image.fromarray(near)) == str(g["near_hex"])
+    # grayscale / RGBA: resized in their own mode on the host like the reference, digest on the device
+    import hashlib
+    for mode in ("L", "RGBA"):
+        im = Image.fromarray(imgs[3]).convert(mode)
+        want = hashlib.md5(im.copy().resize((64, 64)).convert("RGB").tobytes()).hexdigest()
+        assert dc.compute_image_hash(im) == want
+    big = [np.random.default_rng(70 + i).integers(0, 256, (h, w, 3), dtype=np.uint8)
+           for i, (h, w) in enumerate([(900, 64), (64, 1500), (1400, 1900), (2900, 2400)])]
+    bp = pack_images(big, transform=_lib.TRANSFORM_HASH_64).to("cuda")
+    dg = ops_mod.image_hashes(bp.pixels, bp.offsets, bp.hw, bp.max_taps).cpu().numpy()
+    assert [d.tobytes().hex() for d in dg] == [pil_resample.image_hash(b) for b in big]
+
+
+def test_md5_rows_matches_hashlib(ops_mod):
+    """RFC 1321 on the device: lengths around the 56 / 64-byte padding boundaries, an empty row, the hash's 12 288."""
+    import hashlib
+    rng = np.random.default_rng(3)
+    for nbytes in (0, 1, 55, 56, 57, 63, 64, 65, 119, 120, 128, 1000, 12288):
+        rows = rng.integers(0, 256, (5, nbytes), dtype=np.uint8)
+        if nbytes == 0:
+            got = ops_mod.md5_rows(torch.zeros((5, 0), dtype=torch.uint8, device="cuda")).cpu().numpy()
+        else:
+            got = ops_mod.md5_rows(torch.from_numpy(rows).cuda()).cpu().numpy()
+        assert [g.tobytes().hex() for g in got] == [hashlib.md5(r.tobytes()).hexdigest() for r in rows], nbytes

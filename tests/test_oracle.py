@@ -228,3 +228,31 @@ def test_resample_restatements_against_pillow_on_random_sizes(seed):
     left, top = (ow - 224) // 2, (oh - 224) // 2
     ref = np.asarray(r.crop((left, top, left + 224, top + 224)))
     assert np.array_equal(pil_resample.wds_transform_u8(img), ref), (h, w)
+
+
+# =============================================================================================== N3 duplicate hash
+def test_image_hash_restatement_matches_reference_golden_and_pillow_in_process():
+    """oracle/pil_resample.image_hash (bicubic restatement + hashlib.md5) against tests/golden/hash.npz, produced by
+    the UNMODIFIED reference compute_image_hash, and against Pillow run here on further sizes."""
+    import hashlib
+    from PIL import Image
+    from oracle.make_golden import wds_input
+    g = load_golden("hash.npz")
+    imgs = [wds_input(int(s), int(h), int(w), smooth=(i % 2 == 0))
+            for i, ((h, w), s) in enumerate(zip(g["sizes"], g["seeds"]))]
+    for img, want in zip(imgs, g["hexdigests"]):
+        assert pil_resample.image_hash(img) == str(want), img.shape
+    near = imgs[4].copy()
+    near[150, 200, 1] ^= 0x40
+    assert pil_resample.image_hash(near) == str(g["near_hex"]) != str(g["hexdigests"][4])
+    rng = np.random.default_rng(5)
+    for h, w in [(31, 500), (500, 31), (64, 65), (129, 127), (2000, 90)]:
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = hashlib.md5(Image.fromarray(a).resize((64, 64)).convert("RGB").tobytes()).hexdigest()
+        assert pil_resample.image_hash(a) == want
+        assert _lib_geometry_taps(h, w) == pil_resample.hash_max_taps(h, w)
+
+
+def _lib_geometry_taps(h, w):
+    from irp_b200 import _lib
+    return _lib.geometry(h, w, _lib.TRANSFORM_HASH_64)[4]
