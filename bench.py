@@ -80,7 +80,7 @@ def load_peaks():
 # clocks sampling (nvidia-smi during the timed region)
 # --------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons of one GPU, sampled every 200 ms DURING the timed region.
+    """SM clock and throttle reasons of one GPU, sampled every 250 ms DURING the timed region.
 
     Reads NVML in-process (pynvml: the library behind nvidia-smi).  An `nvidia-smi -lms` child process, which this
     used to be, re-initialises NVML over every GPU of the box and stalled one timed step of a 4-GPU run by
@@ -127,7 +127,7 @@ class ClockSampler:
                 self.rows.append((time.time(), sm, mx, {n for n, b in bits.items() if mask & b}))
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.25)
 
     # ---- nvidia-smi fallback ----
     def _read_smi(self):
@@ -417,6 +417,13 @@ def run_ours(args, rank, local_rank, world):
     peaks = load_peaks()
     cfg = CONFIGS[args.config]
     batch, k = cfg["batch"], cfg["k"]
+    # The clock sampler starts BEFORE the workload is generated: with several ranks on one box, something NVML does
+    # lazily about 1.5 s after a process's first queries stalled rank 0's second timed step by 70-175 ms (12-step
+    # probes at 4 GPUs: present in every run with the sampler started right before warm-up, absent without the
+    # sampler); started here, that happens tens of seconds before the timed region.
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not args.no_clock_sampler:
+        sampler.start()
 
     if cfg["total"] is not None:  # strong scaling: this rank's contiguous share of the SAME image set
         lo, hi = shard_range(cfg["total"], rank, world)
@@ -449,9 +456,12 @@ def run_ours(args, rank, local_rank, world):
         return res, None
 
     # ---- value: inputs resident in HBM ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0 and not args.no_clock_sampler:
-        sampler.start()
+    # No cyclic-GC passes inside the timed regions: a generation-2 collection over the objects the workload set-up
+    # left behind cost rank 0 about 70 ms in its second timed step (every rank then waits for it at the all-reduce).
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     for _ in range(args.warmup):
         step()
     barrier()
@@ -535,6 +545,7 @@ def run_ours(args, rank, local_rank, world):
         e2e = {"value": n_total / (t.item() / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h}
 
+    gc.enable()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
