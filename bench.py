@@ -410,8 +410,8 @@ def launches_per_step(n_images, batch, dim, k, class_scoring):
     """Kernels of libirp_b200.so launched per step (counted from the launch sites in csrc/*.cu)."""
     batches = (n_images + batch - 1) // batch
     pre = 2                      # resample_plan (taps + band schedule) + resample_fused
-    trunk = 46                   # stem+pool, 16 3x3, 3 downsample, 9 conv1, 9 conv3, 7 chained conv3+conv1 (the first
-                                 # with the layer1 shortcut conv folded in), avgpool
+    trunk = 45                   # stem+pool, 16 3x3, 3 downsample, 9 conv1, 8 conv3, 7 chained conv3+conv1 (the first
+                                 # with the layer1 shortcut conv folded in), last conv3 + residual + average pool
     per_batch = pre + trunk
     cov = 4                      # split_transpose, col_sum_reduce, add_count, cov_gemm
     lanczos_steps = max(3 * k + 10, 96)  # first convergence check; the bench data converges there

@@ -12,6 +12,7 @@
 #include "conv_gemm2.cuh"
 #include "conv3x3_c64.cuh"
 #include "conv_chain.cuh"
+#include "conv_pool.cuh"
 #include "stem_conv.cuh"
 
 namespace irp {
@@ -441,6 +442,59 @@ static int launch_chain(const ChainPlan& plan, long long rows, cudaStream_t stre
   }
 }
 
+// the last block's conv3 + residual + ReLU + global average pool (conv_pool.cuh)
+struct PoolPlan {
+  ConvPoolParams p;
+  bool valid = false;
+};
+
+static bool pool_supported(int K, int Cout, int hw) { return K == kCpK && Cout % 128 == 0 && hw == kCpPix; }
+
+static int plan_pool(PoolPlan* plan, const void* t2, const void* w, const float* bias, const void* residual,
+                     int max_batch, int K, int Cout) {
+  IRP_REQUIRE(pool_supported(K, Cout, kCpPix) && residual != nullptr, "conv + pool: unsupported shape K %d Cout %d", K, Cout);
+  ConvPoolParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  const uint64_t M = static_cast<uint64_t>(max_batch) * kCpPix;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(Cout)};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {64, 128};
+    IRP_TRY(encode_bf16_map(&p.tmW, const_cast<void*>(w), 2, dims, strides, box, 128));
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), M};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {64, kCpRows};
+    IRP_TRY(encode_bf16_map(&p.tmX, const_cast<void*>(t2), 2, dims, strides, box, 128));
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(Cout), M};
+    uint64_t strides[1] = {static_cast<uint64_t>(Cout) * 2};
+    uint32_t box[2] = {64, kCpRows};
+    IRP_TRY(encode_bf16_map(&p.tmRes, const_cast<void*>(residual), 2, dims, strides, box, 0));
+  }
+  p.bias = bias;
+  p.cout = Cout;
+  p.n_ctiles = Cout / 128;
+  plan->valid = true;
+  return IRP_OK;
+}
+
+static int launch_pool(const PoolPlan& plan, int batch, float* d_out, cudaStream_t stream) {
+  ConvPoolParams p = plan.p;
+  p.out = d_out;
+  p.batch = batch;
+  p.n_groups = ceil_div(batch, kCpImgs);
+  IRP_TRY(ensure_smem(conv_pool_kernel, kCpSmemBytes));
+  int per_tile = num_sms() / p.n_ctiles;  // CTAs that share one channel tile's image groups
+  if (per_tile < 1) per_tile = 1;
+  if (per_tile > p.n_groups) per_tile = p.n_groups;
+  PairLaunch l(p.n_ctiles * per_tile, kCpThreads, kCpSmemBytes, stream, false);
+  IRP_CUDA_OK(cudaLaunchKernelEx(&l.cfg, conv_pool_kernel, p));
+  return IRP_OK;
+}
+
 static int grid_for(long long total, int threads) {
   long long g = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -500,6 +554,7 @@ struct irp_resnet50 {
   std::vector<ConvPlan> plans;
   std::vector<ChainPlan> chains;     // indexed by the conv3 of the first block of a fused junction
   std::vector<ChainPlan> chains_ds;  // same junction with the block's stride-1 shortcut conv folded into GEMM1
+  PoolPlan pool;                     // the last block's conv3 + residual + ReLU + global average pool
   int cat_c3 = -1, cat_ds = -1;      // conv3 / shortcut conv whose folded weights are also kept concatenated along K
   __nv_bfloat16* wcat = nullptr;     // [cout][cin_c3 + cin_ds]
   float* bcat = nullptr;             // bias_c3 + bias_ds
@@ -582,6 +637,8 @@ static int resnet50_plan(irp_resnet50* net, const void* d_x) {
                            net->buf[cur], sp[i + 3].cin));
       }
     }
+    if (i + (has_ds ? 4 : 3) >= sp.size() && pool_supported(c3.cin, c3.cout, c3.H * c3.W))
+      IRP_TRY(plan_pool(&net->pool, net->buf[T2], net->weights[i + 2], net->biases[i + 2], res, B, c3.cin, c3.cout));
     const int t = cur;
     cur = other;
     other = t;
@@ -695,7 +752,8 @@ int irp_resnet50_load_conv(irp_resnet50* net, int index, const float* d_weight_o
 }
 
 // One pass of `batch` images through the trunk.  capture_index >= 0 (with d_capture): also copy that convolution's
-// output tensor; every conv then runs as its own launch (the junction kernel that folds layer1's shortcut conv into
+// output tensor; every conv then runs as its own launch (and the last block's activation is materialised and pooled
+// by avgpool_kernel instead of the fused conv + pool kernel) (the junction kernel that folds layer1's shortcut conv into
 // its accumulator never materialises the shortcut tensor), and index 0 yields the stem output AFTER the fused
 // 3x3/2 max pool, [batch,56,56,64].
 static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float* d_embed, int capture_index,
@@ -742,6 +800,12 @@ static int resnet50_forward(irp_resnet50* net, const void* d_x, int batch, float
       IRP_TRY(capture(static_cast<int>(i + 3)));
     }
     const ChainPlan& ch = ds_folded ? net->chains_ds[i + 2] : net->chains[i + 2];
+    const bool is_last = i + (has_ds ? 4 : 3) >= sp.size();
+    if (is_last && net->pool.valid && d_capture == nullptr) {
+      // conv3 + residual + ReLU + global average pool in one kernel: the embedding is written directly
+      IRP_TRY(launch_pool(net->pool, batch, d_embed, st));
+      return IRP_OK;
+    }
     if (ch.valid) {
       IRP_TRY(launch_chain(ch, static_cast<long long>(batch) * ch.rows_per_image, st));
       conv1_done = true;
@@ -786,6 +850,14 @@ int irp_conv1x1_chain_ds(const void* d_t2, const void* d_x, const void* d_wcat, 
   ChainPlan plan;
   IRP_TRY(plan_chain(&plan, d_t2, d_wcat, d_bias, nullptr, d_y, d_w1, d_b1, d_t1, rows, 1, K1, N1, N2, d_x, K2));
   return launch_chain(plan, rows, static_cast<cudaStream_t>(stream));
+}
+
+int irp_conv1x1_pool(const void* d_t2, const void* d_w, const float* d_bias, const void* d_residual, float* d_out,
+                     int batch, int K, int Cout, void* stream) {
+  IRP_REQUIRE(d_t2 && d_w && d_bias && d_residual && d_out && batch > 0, "conv + pool: bad argument");
+  PoolPlan plan;
+  IRP_TRY(plan_pool(&plan, d_t2, d_w, d_bias, d_residual, batch, K, Cout));
+  return launch_pool(plan, batch, d_out, static_cast<cudaStream_t>(stream));
 }
 
 int irp_conv2d_nhwc(const void* d_x, const void* d_w, const float* d_bias, const void* d_residual, void* d_out,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "irp_resnet50_embed_capture": (_i, [_vp, _vp, _i, _vp, _i, _vp, _sz, _vp]),
     "irp_conv2d_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "irp_conv1x1_chain": (_i, [_vp] * 8 + [_i64, _i, _i, _i, _vp]),
+    "irp_conv1x1_pool": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "irp_conv1x1_chain_ds": (_i, [_vp] * 8 + [_i64, _i, _i, _i, _i, _vp]),
     "irp_cov_workspace_bytes": (_sz, [_i64, _i]),
     "irp_cov_accumulate": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -154,6 +154,13 @@ int irp_conv1x1_chain_ds(const void* d_t2, const void* d_x, const void* d_wcat, 
                          const void* d_w1, const float* d_b1, void* d_t1, int64_t rows, int K1, int K2, int N1, int N2,
                          void* stream);
 
+/* The last bottleneck's conv3 + residual + ReLU + global average pool, the fused form the trunk ends with (the
+ * 2048-channel activation is never written); exposed for parity tests:
+ *   out [batch,Cout] (fp32) = mean over the 49 pixels of relu(t2 [batch*49,K] . w[Cout,K]^T + bias + residual)
+ * t2 / w / residual bf16 row-major, K = 512, Cout % 128 == 0 (torchvision/models/resnet.py:150-159, :278-279). */
+int irp_conv1x1_pool(const void* d_t2, const void* d_w, const float* d_bias, const void* d_residual, float* d_out,
+                     int batch, int K, int Cout, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * N3  duplicate-detection hash  --  replaces compute_image_hash (functions/data_curation.py:283-292; call site
  * :394-399): md5 of the RGB bytes of img.resize((64, 64)).  irp_preprocess_ex(IRP_LAYOUT_U8_HWC,

@@ -229,6 +229,32 @@ def test_conv1x1_chain_with_folded_shortcut_matches_torch(lib, rows, K1, K2, N1,
     assert ((t1.float() - t1_ref).abs().max() / t1_ref.abs().max()).item() < 6e-3
 
 
+@pytest.mark.parametrize("batch,cout", [(1, 128), (3, 256), (7, 2048), (64, 2048), (256, 2048)])
+def test_conv1x1_pool_matches_torch(lib, batch, cout):
+    """The trunk's last kernel: conv3 (512 -> Cout @7x7) + bias + residual + ReLU + global average pool, fp32 out,
+    against fp32 torch; ragged last image triple, several triples per CTA, and bitwise repeatability (the pooled sum
+    is a fixed-order chain inside one thread)."""
+    from irp_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(batch * 7 + cout)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+    t2 = rn(batch * 49, 512).relu().bfloat16()
+    w = (rn(cout, 512) / 22).bfloat16()
+    b = rn(cout) * 0.5
+    res = rn(batch * 49, cout).relu().bfloat16()
+    out = torch.full((batch, cout), float("nan"), device="cuda")
+    call = lambda o: _lib.check(lib.irp_conv1x1_pool(_ptr(t2), _ptr(w), _ptr(b), _ptr(res), _ptr(o), batch, 512, cout,
+                                                     _stream()), "irp_conv1x1_pool")
+    call(out)
+    torch.cuda.synchronize()
+    ref = (t2.float() @ w.float().t() + b + res.float()).relu().view(batch, 49, cout).mean(1)
+    assert not torch.isnan(out).any()
+    assert ((out - ref).abs().max() / ref.abs().max()).item() < 2e-3
+    out2 = torch.empty_like(out)
+    call(out2)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
 def test_conv2d_rejects_unsupported_shapes(lib):
     x = torch.zeros(1, 8, 8, 48, device="cuda", dtype=torch.bfloat16)
     st = lib.irp_conv2d_nhwc(_ptr(x), _ptr(x), _ptr(x), None, _ptr(x), 1, 8, 8, 48, 64, 1, 1, 0, _stream())
