@@ -101,6 +101,11 @@ extern "C" {
 
 int irp_abi_version(void) { return IRP_B200_ABI_VERSION; }
 
+#ifndef IRP_BUILD_ID
+#define IRP_BUILD_ID "unknown"
+#endif
+const char* irp_build_id(void) { return IRP_BUILD_ID; }
+
 const char* irp_last_error(void) { return irp::g_last_error; }
 
 int irp_init(int device) {

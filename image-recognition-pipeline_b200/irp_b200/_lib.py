@@ -39,6 +39,7 @@ _d = C.c_double
 SIGNATURES = {
     "irp_abi_version": (_i, []),
     "irp_last_error": (C.c_char_p, []),
+    "irp_build_id": (C.c_char_p, []),
     "irp_init": (_i, [_i]),
     "irp_preprocess_geometry": (_i, [_i, _i] + [C.POINTER(_i)] * 5),
     "irp_preprocess_workspace_bytes": (_sz, [_i, _i]),
@@ -107,6 +108,31 @@ def load() -> C.CDLL:
             fn.argtypes = args
         _lib = lib
         return lib
+
+
+def source_build_id() -> str:
+    """The id `make` would stamp into the library for the sources currently on disk (see csrc/Makefile)."""
+    import glob
+    import hashlib
+    csrc = os.path.normpath(os.path.join(_HERE, "..", "csrc"))
+    files = sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh")) +
+                   glob.glob(os.path.join(csrc, "*.h")), key=os.path.basename)
+    files.append(os.path.normpath(os.path.join(_HERE, "..", "..", "include", "irp_b200.h")))
+    h = hashlib.sha256()
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def assert_fresh() -> str:
+    """Raise if the loaded library was not built from the sources beside it; returns the build id."""
+    built = load().irp_build_id().decode()
+    want = source_build_id()
+    if built != want:
+        raise ImportError(f"{LIB_PATH} is stale: built from sources {built}, sources on disk are {want}; rebuild with "
+                          "`python -c 'import __graft_entry__ as g; g.build()'`")
+    return built
 
 
 def check(status: int, what: str = "") -> None:

@@ -39,6 +39,9 @@ typedef enum irp_status {
 
 /* ABI version of the loaded library (IRP_B200_ABI_VERSION at build time). */
 int irp_abi_version(void);
+/* First 16 hex digits of the sha256 over the library's sources (csrc/*.cu, *.cuh, *.h and this header, in sorted
+ * order) at build time: lets a caller check that the .so it loaded was built from the sources beside it. */
+const char* irp_build_id(void);
 /* Message of the last failure on this thread ("" if none). The pointer stays valid until the next failure. */
 const char* irp_last_error(void);
 /* Checks that `device` is a compute-capability 10.x GPU and resolves the driver entry points. */

@@ -47,4 +47,5 @@ def lib():
     import torch
     from irp_b200 import _lib
     assert torch.cuda.is_available()
+    _lib.assert_fresh()  # the prebuilt .so that travelled to the GPU box was built from the sources beside it
     return _lib.init(0)

@@ -60,3 +60,10 @@ def test_conv_index_order_matches_torchvision():
         cout, cin, kh, kw, stride = (v.value for v in vals)
         assert tuple(conv.weight.shape) == (cout, cin, kh, kw)
         assert conv.stride == (stride, stride)
+
+
+def test_library_build_id_matches_the_sources_on_disk():
+    """irp_build_id() is the hash `make` stamped at build time; _lib.source_build_id() recomputes it from csrc/ and
+    include/ -- a stale .so (sources edited, library not rebuilt) must not pass silently."""
+    lib = _lib.load()
+    assert lib.irp_build_id().decode() == _lib.source_build_id() == _lib.assert_fresh()
