@@ -136,7 +136,10 @@ def _conv_ref(x, w, bias, res, stride, relu):
     (8, 56, 64, 256, 1, 1, True, True),       # layer1 conv3 + residual
     (4, 14, 1024, 256, 1, 1, True, False),    # long K
     (2, 56, 64, 64, 3, 1, True, False),       # layer1 3x3
-    (8, 28, 128, 128, 3, 1, True, False),
+    (8, 28, 128, 128, 3, 1, True, False),     # layer2 3x3: patch-resident CTA-pair kernel, ragged 4 x 2 tiles
+    (1, 28, 128, 128, 3, 1, False, False),    # one image: 8 tiles, no ReLU
+    (3, 20, 128, 128, 3, 1, True, False),     # odd tile count (phantom tile in the last pair), ragged both ways
+    (67, 28, 128, 128, 3, 1, True, False),    # several tiles per CTA pair (ring / accumulator recycling)
     (32, 14, 256, 256, 3, 1, True, False),
     (128, 7, 512, 512, 3, 1, True, False),    # (1,1,128) boxes
     (6, 7, 512, 512, 3, 1, True, False),      # (7,7,2) boxes, 98 of 128 rows
