@@ -44,6 +44,7 @@ class ResNet50Trunk:
     """ResNet-50 minus fc on the library's tcgen05 kernels (functions/data_curation.py:654-659, :677)."""
 
     def __init__(self, torch_model: torch.nn.Module, device: torch.device, max_batch: int = 256):
+        self._model = torch_model  # kept so that lane() can build a second handle from the same weights
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("ResNet50Trunk needs a CUDA (sm_100) device; there is no CPU path")
@@ -69,6 +70,10 @@ class ResNet50Trunk:
                                                            *[C.c_void_p(p.data_ptr()) for p in t],
                                                            C.c_float(bn.eps), stream), f"load_conv[{i}]")
             torch.cuda.synchronize(idx)
+
+    def lane(self) -> "ResNet50Trunk":
+        """A second handle (own activation arena and tensor maps) built from the same weights, for a second lane."""
+        return ResNet50Trunk(self._model, self.device, self.max_batch)
 
     @property
     def handle(self) -> int:
@@ -203,13 +208,27 @@ class StageResult:
 class CudaBackend:
     """The product backend: every step is a libirp_b200 kernel (through the irp_b200 custom ops)."""
 
-    def __init__(self, trunk: ResNet50Trunk):
+    def __init__(self, trunk: ResNet50Trunk, lanes: int = 1):
+        """lanes > 1: batches alternate between `lanes` trunk handles, each fed on its own stream, so that the tail of
+        one lane's kernel (the last, partly filled wave of a persistent grid; the pipeline fill of the next one) is
+        covered by the other lane's launches: + 3 % on the embed phase with two lanes, nothing more with three
+        (tools/lane_probe.py; limiting each lane to half of the SMs instead was measured SLOWER than one lane)."""
         self.trunk = trunk
         self.device = trunk.device
+        self.n_lanes = max(1, int(lanes))
+        self.lane_trunks: List[ResNet50Trunk] = [trunk]
+        self.lane_streams: List[torch.cuda.Stream] = []
 
-    def embed(self, part: PackedImages, max_taps: int) -> torch.Tensor:
+    def ensure_lanes(self):
+        """The extra handles (activation arenas) and streams are created at the first multi-batch pass."""
+        if self.n_lanes > 1 and not self.lane_streams:
+            self.lane_trunks = [self.trunk] + [self.trunk.lane() for _ in range(self.n_lanes - 1)]
+            self.lane_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_lanes)]
+
+    def embed(self, part: PackedImages, max_taps: int, lane: Optional[int] = None) -> torch.Tensor:
         x = ops.preprocess(part.pixels, part.offsets, part.hw, max_taps, _lib.LAYOUT_NHWC4P)
-        return self.trunk.embed(x)
+        trunk = self.trunk if lane is None else self.lane_trunks[lane]
+        return trunk.embed(x)
 
     cov_accumulate = staticmethod(ops.cov_accumulate)
     pca_fit = staticmethod(ops.pca_fit)
@@ -228,9 +247,9 @@ class OutlierStage:
     def __init__(self, backend, batch_size: int = 256, pca_components: int = 50, class_n_neighbors: int = 30,
                  class_contamination: float = 0.05, global_n_neighbors: int = 75,
                  global_contamination: float = 0.03, process_group=None, embed_dim: int = _lib.EMBED_DIM,
-                 class_scoring: bool = True, trace: bool = False):
+                 class_scoring: bool = True, trace: bool = False, lanes: int = 2):
         if isinstance(backend, ResNet50Trunk):
-            backend = CudaBackend(backend)
+            backend = CudaBackend(backend, lanes=lanes)  # the second lane's arena is allocated at its first use
         self.backend = backend
         self.device = torch.device(backend.device)
         self.batch_size = int(batch_size)
@@ -279,39 +298,108 @@ class OutlierStage:
     def embed_packed(self, packed: PackedImages, from_host: bool = False) -> torch.Tensor:
         """Preprocess + embed every image of `packed`; fp32 [n,2048] on the device.
 
-        With from_host=True the packed tensors live in (pinned) host memory and every batch's bytes are copied
-        on a side stream while the previous batch computes."""
+        Batch j runs on lane j % lanes (CudaBackend(lanes=...): one trunk handle and one stream per lane; one lane =
+        the caller's stream); the caller's stream waits for every lane at the end.  With from_host=True the packed
+        tensors live in (pinned) host memory: every batch is copied on the copy stream into one slot of a small ring
+        of device staging buffers that is reused across batches and calls (no allocation inside the loop), the copy
+        of a batch overlapping the compute of the batches before it."""
         n = len(packed)
         feats = torch.empty((n, self.embed_dim), dtype=torch.float32, device=self.device)
         if n == 0:
             return feats
         bs = self.batch_size
-        overlap = from_host and self.copy_stream is not None
-        cur = torch.cuda.current_stream(self.device) if overlap else None
+        bounds = list(range(0, n, bs)) + [n]
+        nb = len(bounds) - 1
+        if self.device.type != "cuda":  # oracle-backed test backend
+            for j in range(nb):
+                part = packed.slice(bounds[j], bounds[j + 1])
+                feats[bounds[j]:bounds[j + 1]] = self.backend.embed(part, packed.max_taps)
+            return feats
 
-        def stage(lo):
-            part = packed.slice(lo, min(n, lo + bs))
-            if not from_host:
-                return part, None
-            if not overlap:
-                return part.to(self.device, non_blocking=False), None
-            with torch.cuda.stream(self.copy_stream):
-                dev = part.to(self.device, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.copy_stream)
-            return dev, ev
+        lanes = getattr(self.backend, "n_lanes", 1) if nb > 1 else 1
+        main = torch.cuda.current_stream(self.device)
+        if lanes > 1:
+            self.backend.ensure_lanes()
+            streams = self.backend.lane_streams
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for s in streams:
+                s.wait_event(fork)
+        else:
+            streams = [main]
+        ring = self._h2d_ring(packed, bounds, lanes + 1) if from_host else None
+        if ring is not None and lanes == 1:
+            fork = torch.cuda.Event()
+            fork.record(main)
+        if ring is not None:
+            self.copy_stream.wait_event(fork)  # staging slots last used by an earlier call on this stream
 
-        nxt = stage(0)
-        for lo in range(0, n, bs):
-            part, ev = nxt
-            if lo + bs < n:
-                nxt = stage(lo + bs)
-            if ev is not None:
-                cur.wait_event(ev)
-                for t in (part.pixels, part.offsets, part.hw):
-                    t.record_stream(cur)
-            feats[lo:lo + len(part)] = self.backend.embed(part, packed.max_taps)
+        for j in range(nb):
+            lo, hi = bounds[j], bounds[j + 1]
+            lane = j % lanes
+            s = streams[lane]
+            if ring is not None:
+                part, slot = self._stage_h2d(ring, j, packed, lo, hi)
+            with torch.cuda.stream(s):
+                if ring is not None:
+                    s.wait_event(slot["ready"])
+                else:
+                    # device-resident input: the slice's rebased offsets are computed ON the lane's stream
+                    part = packed.slice(lo, hi)
+                out = self.backend.embed(part, packed.max_taps, lane=lane) if lanes > 1 else \
+                    self.backend.embed(part, packed.max_taps)
+                feats[lo:hi] = out
+                if ring is not None:
+                    slot["done"] = torch.cuda.Event()
+                    slot["done"].record(s)
+        if lanes > 1:
+            for s in streams:
+                done = torch.cuda.Event()
+                done.record(s)
+                main.wait_event(done)
         return feats
+
+    def _h2d_ring(self, packed: PackedImages, bounds, slots: int):
+        """Device staging buffers for host-resident input: `slots` x (pixels, offsets, hw), sized for the largest
+        batch; kept across calls and grown on demand."""
+        nbytes = 0
+        for j in range(len(bounds) - 1):
+            lo, hi = bounds[j], bounds[j + 1]
+            h, w = int(packed.hw_np[hi - 1, 0]), int(packed.hw_np[hi - 1, 1])
+            nbytes = max(nbytes, int(packed.offsets_np[hi - 1]) + h * w * 3 - int(packed.offsets_np[lo]))
+        rows = max(bounds[j + 1] - bounds[j] for j in range(len(bounds) - 1))
+        ring = getattr(self, "_ring", None)
+        if ring is None or len(ring) < slots or ring[0]["pixels"].numel() < nbytes or ring[0]["hw"].shape[0] < rows:
+            cap = (max(nbytes, 1) * 9 // 8 + 255) // 256 * 256  # headroom: the next call's batches differ a little
+            ring = [{"pixels": torch.empty(cap, dtype=torch.uint8, device=self.device),
+                     "offsets": torch.empty(rows, dtype=torch.int64, device=self.device),
+                     "hw": torch.empty((rows, 2), dtype=torch.int32, device=self.device),
+                     "ready": None, "done": None} for _ in range(slots)]
+            self._ring = ring
+        return ring
+
+    def _stage_h2d(self, ring, j: int, packed: PackedImages, lo: int, hi: int):
+        """Copy images [lo, hi) of the host-resident `packed` into ring slot j % len(ring) on the copy stream."""
+        slot = ring[j % len(ring)]
+        start = int(packed.offsets_np[lo])
+        h, w = int(packed.hw_np[hi - 1, 0]), int(packed.hw_np[hi - 1, 1])
+        end = int(packed.offsets_np[hi - 1]) + h * w * 3
+        m = hi - lo
+        cs = self.copy_stream
+        with torch.cuda.stream(cs):
+            if slot["done"] is not None:
+                cs.wait_event(slot["done"])  # the batch that used this slot has been consumed
+            px = slot["pixels"][: end - start]
+            off = slot["offsets"][:m]
+            hw = slot["hw"][:m]
+            px.copy_(packed.pixels[start:end], non_blocking=True)
+            off.copy_(packed.offsets[lo:hi], non_blocking=True)
+            off.sub_(start)  # rebased on the device: no pageable temporary, no blocking copy
+            hw.copy_(packed.hw[lo:hi], non_blocking=True)
+            slot["ready"] = torch.cuda.Event()
+            slot["ready"].record(cs)
+        part = PackedImages(px, off, hw, packed.max_taps, packed.offsets_np[lo:hi] - start, packed.hw_np[lo:hi])
+        return part, slot
 
     # ---- PCA ----
     def fit_pca(self, feats: torch.Tensor) -> PCAState:

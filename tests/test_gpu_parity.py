@@ -290,6 +290,28 @@ def test_embeddings_match_reference_golden(trunk):
     assert cos >= COS_MIN and linf <= LINF_REL_MAX, (cos, linf)
 
 
+def test_embed_lanes_match_single_lane_bitwise(trunk):
+    """Batches alternating between two / three trunk handles on their own streams (CudaBackend(lanes=...)) give the
+    same bits as one handle on one stream, from device-resident and from pinned host input."""
+    from irp_b200.stage import CudaBackend, OutlierStage, pack_images
+    from oracle import synth
+    rng = np.random.default_rng(5)
+    sizes = [(224, 224), (300, 400), (180, 150), (260, 233), (500, 310)]
+    images = [synth.smooth_image(rng, *sizes[i % 5], i % 3) for i in range(37)]
+    host = pack_images(images)
+    dev = host.to(trunk.device, non_blocking=False)
+    ref = OutlierStage(CudaBackend(trunk, lanes=1), batch_size=8).embed_packed(dev)
+    torch.cuda.synchronize()
+    for lanes in (2, 3):
+        stage = OutlierStage(CudaBackend(trunk, lanes=lanes), batch_size=8)
+        for src, from_host in ((dev, False), (host, True)):
+            got = stage.embed_packed(src, from_host=from_host)
+            torch.cuda.synchronize()
+            assert torch.equal(got, ref), (lanes, from_host, float((got - ref).abs().max()))
+        for t in stage.backend.lane_trunks[1:]:
+            t.close()
+
+
 def test_trunk_matches_torchvision_per_layer(lib, trunk):
     """Every conv's fused output (bias/ReLU/residual epilogue) against torchvision evaluated in fp32 on the GPU.
     Index 0 is compared after the max pool (the stem kernel fuses it; the unpooled tensor never exists).  With a

@@ -4,6 +4,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "image-recognition-pipeline_b200")); sys.path.insert(0, ROOT)
 from irp_b200 import _lib, ops
+if os.environ.get("IRP_AB_LIB"):  # developer A/B against another build of the library (tools/ab_trunk.sh)
+    _lib.LIB_PATH = os.path.join(ROOT, os.environ["IRP_AB_LIB"])
 from irp_b200.stage import ResNet50Trunk
 from oracle import stage_ref
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
