@@ -955,6 +955,30 @@ static int sort_rows(const int32_t* d_group, long long n, int n_groups, uint8_t*
   return IRP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// N4: UMAP's k-NN arrays from the neighbour lists of the search above.  umap-learn's
+// nearest_neighbors returns, per sample, ITSELF (distance 0) followed by its n_neighbors - 1 nearest other samples,
+// ascending; rows come back in the caller's order and indices refer to the caller's rows.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void knn_graph_emit_kernel(const double* __restrict__ knn_d, const int32_t* __restrict__ knn_i,
+                                      const int32_t* __restrict__ order, long long n, int k_other,
+                                      int32_t* __restrict__ idx, float* __restrict__ dist) {
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int k = k_other + 1;
+  if (t >= n * k) return;
+  const long long p = t / k;  // sorted position
+  const int j = static_cast<int>(t - p * k);
+  const long long r = order[p];
+  if (j == 0) {
+    idx[r * k] = static_cast<int32_t>(r);
+    dist[r * k] = 0.f;
+    return;
+  }
+  const int32_t nb = knn_i[p * k_other + j - 1];
+  idx[r * k + j] = nb < 0 ? -1 : order[nb];
+  dist[r * k + j] = static_cast<float>(knn_d[p * k_other + j - 1]);
+}
+
 }  // namespace irp
 
 using namespace irp;
@@ -1156,6 +1180,29 @@ int irp_lof(const float* d_z, int64_t n_rows, int dim, const int32_t* d_group, i
   IRP_TRY(irp_lof_score_part(n_rows, n_groups, k, 0, 1, w.lrd, w.score_sorted, d_workspace, workspace_bytes, stream));
   return irp_lof_finish(n_rows, n_groups, k, contamination, w.score_sorted, d_scores, d_offsets, d_flags, d_workspace,
                         workspace_bytes, stream);
+}
+
+size_t irp_knn_graph_workspace_bytes(int64_t n_rows, int dim, int k) {
+  if (n_rows <= 0 || dim <= 0 || k < 2) return 0;
+  return irp_lof_workspace_bytes(n_rows, dim, k - 1);
+}
+
+int irp_knn_graph(const float* d_z, int64_t n_rows, int dim, int k, int32_t* d_idx, float* d_dist, void* d_workspace,
+                  size_t workspace_bytes, void* stream) {
+  IRP_REQUIRE(d_z && d_idx && d_dist && d_workspace, "knn_graph: null argument");
+  IRP_REQUIRE(k >= 2 && k - 1 <= kMaxK, "knn_graph: n_neighbors %d not in [2,%d]", k, kMaxK + 1);
+  IRP_REQUIRE(n_rows >= k, "knn_graph: %lld rows < n_neighbors %d", static_cast<long long>(n_rows), k);
+  IRP_REQUIRE(workspace_bytes >= irp_knn_graph_workspace_bytes(n_rows, dim, k), "knn_graph: workspace too small");
+  const int ko = k - 1;
+  LofWs w = lof_layout(d_workspace, static_cast<size_t>(n_rows), ko);
+  // the exact (fp64, ties by index) neighbour search of the LOF scorer, all rows in one group
+  IRP_TRY(irp_lof_knn_part(d_z, n_rows, dim, nullptr, 1, ko, 0, 1, w.kdist, d_workspace, workspace_bytes, stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(n_rows) * k;
+  knn_graph_emit_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w.knn_d, w.knn_i, w.sr.order,
+                                                                                   n_rows, ko, d_idx, d_dist);
+  IRP_CUDA_OK(cudaGetLastError());
+  return IRP_OK;
 }
 
 size_t irp_centroid_workspace_bytes(int64_t n_rows, int dim, int n_groups) {

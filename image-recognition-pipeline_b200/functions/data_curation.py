@@ -217,9 +217,25 @@ def create_embeddings(features, labels, pca_components=50, umap_params=None):
     le = LabelEncoder()
     y_numeric = le.fit_transform(labels)
     features_pca, pca = _fit_pca(features, pca_components)
-    reducer = umap.UMAP(**umap_params)
+    reducer = umap.UMAP(**_with_device_knn(umap_params, features_pca))
     embedding = reducer.fit_transform(features_pca, y=y_numeric)
     return embedding, le, pca, reducer
+
+
+def _with_device_knn(umap_params, features_pca):
+    """UMAP's neighbour search (umap_.py nearest_neighbors) runs on the device -- exactly,
+    where umap-learn switches to approximate NN-descent above 4 096 samples -- and is handed over through UMAP's own
+    `precomputed_knn=(knn_indices, knn_dists)` parameter; everything else of UMAP stays host-side.  Left alone when
+    the caller brings a `precomputed_knn`, a non-Euclidean or precomputed metric, or fewer rows than neighbours."""
+    params = dict(umap_params)
+    k = int(params.get('n_neighbors', 15))
+    if ('precomputed_knn' in params or params.get('metric', 'euclidean') != 'euclidean'
+            or features_pca.shape[0] <= k or k < 2 or k > 129):
+        return params
+    from irp_b200 import umap_graph
+    knn_indices, knn_dists = umap_graph.nearest_neighbors(features_pca, k)
+    params['precomputed_knn'] = (knn_indices, knn_dists)
+    return params
 
 
 def detect_outliers(embedding, labels, class_n_neighbors=30, class_contamination=0.05,

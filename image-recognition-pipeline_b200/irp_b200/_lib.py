@@ -74,6 +74,9 @@ SIGNATURES = {
     "irp_lof_lrd_part": (_i, [_i64, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "irp_lof_score_part": (_i, [_i64, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "irp_lof_finish": (_i, [_i64, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "irp_knn_graph_workspace_bytes": (_sz, [_i64, _i, _i]),
+    "irp_knn_graph": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "irp_umap_fuzzy_weights": (_i, [_vp, _vp, _i64, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "irp_centroid_workspace_bytes": (_sz, [_i64, _i, _i]),
     "irp_centroid_zscore": (_i, [_vp, _i64, _i, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -375,3 +375,55 @@ def cross_entropy_stats(logits: torch.Tensor, labels: torch.Tensor,
     _lib.check(lib.irp_cross_entropy_stats(_ptr(logits), _ptr(labels.contiguous()), logits.shape[0], logits.shape[1],
                                            _ptr(w), _ptr(stats), _stream(logits)), "irp_cross_entropy_stats")
     return stats
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N4 UMAP graph construction: exact k-NN arrays + fuzzy simplicial set weights
+# ---------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("irp_b200::knn_graph", mutates_args=())
+@_on_device_of(0)
+def knn_graph(z: torch.Tensor, n_neighbors: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """umap_.py nearest_neighbors, exact: -> (knn_indices int32 [n,k], knn_dists float32 [n,k]); column 0 is the
+    row itself at distance 0, then its k-1 nearest other rows in ascending (distance, index) order."""
+    lib = _lib_for(z)
+    assert z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 2
+    n, d = z.shape
+    idx = torch.empty((n, n_neighbors), dtype=torch.int32, device=z.device)
+    dist = torch.empty((n, n_neighbors), dtype=torch.float32, device=z.device)
+    ws_bytes = lib.irp_knn_graph_workspace_bytes(n, d, n_neighbors)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=z.device)
+    _lib.check(lib.irp_knn_graph(_ptr(z), n, d, n_neighbors, _ptr(idx), _ptr(dist), _ptr(ws), ws_bytes, _stream(z)),
+               "irp_knn_graph")
+    return idx, dist
+
+
+@knn_graph.register_fake
+def _(z, n_neighbors):
+    n = z.shape[0]
+    return z.new_empty((n, n_neighbors), dtype=torch.int32), z.new_empty((n, n_neighbors), dtype=torch.float32)
+
+
+@torch.library.custom_op("irp_b200::umap_fuzzy_weights", mutates_args=())
+@_on_device_of(0)
+def umap_fuzzy_weights(knn_indices: torch.Tensor, knn_dists: torch.Tensor, local_connectivity: float = 1.0,
+                       bandwidth: float = 1.0, n_iter: int = 64) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """umap_.py smooth_knn_dist + compute_membership_strengths: -> (sigmas f32 [n], rhos f32 [n], vals f32 [n,k]);
+    vals[i, j] is the weight of the directed edge i -> knn_indices[i, j]."""
+    lib = _lib_for(knn_dists)
+    assert knn_indices.dtype == torch.int32 and knn_dists.dtype == torch.float32
+    assert knn_indices.is_contiguous() and knn_dists.is_contiguous() and knn_indices.shape == knn_dists.shape
+    n, k = knn_dists.shape
+    sig = torch.empty(n, dtype=torch.float32, device=knn_dists.device)
+    rho = torch.empty(n, dtype=torch.float32, device=knn_dists.device)
+    vals = torch.empty((n, k), dtype=torch.float32, device=knn_dists.device)
+    ws = torch.empty(8, dtype=torch.uint8, device=knn_dists.device)
+    _lib.check(lib.irp_umap_fuzzy_weights(_ptr(knn_indices), _ptr(knn_dists), n, k, C.c_float(local_connectivity),
+                                          C.c_float(bandwidth), int(n_iter), _ptr(sig), _ptr(rho), _ptr(vals),
+                                          _ptr(ws), 8, _stream(knn_dists)), "irp_umap_fuzzy_weights")
+    return sig, rho, vals
+
+
+@umap_fuzzy_weights.register_fake
+def _(knn_indices, knn_dists, local_connectivity=1.0, bandwidth=1.0, n_iter=64):
+    n, k = knn_dists.shape
+    return (knn_dists.new_empty(n), knn_dists.new_empty(n), knn_dists.new_empty((n, k)))

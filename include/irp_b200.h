@@ -278,6 +278,32 @@ int irp_classifier_head(const float* d_features, int batch, int in_dim, const fl
 int irp_cross_entropy_stats(const float* d_logits, const int64_t* d_labels, int batch, int num_classes,
                             const float* d_class_weights, double* d_stats, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * N4  UMAP graph construction (last "next" row)  --  the part of
+ * `umap.UMAP(**umap_params).fit_transform(features_pca, y=y_numeric)` (functions/data_curation.py:704-705) that turns
+ * the PCA output into UMAP's weighted k-NN graph; umap-learn 0.5.7 (requirements.txt:175; not vendored):
+ *
+ *   irp_knn_graph          : umap_.py nearest_neighbors, EXACT (Euclidean, fp64 distances, ties by index -- the
+ *                            neighbour search of the LOF scorer).  Row i of d_idx / d_dist [n_rows, k] = i itself
+ *                            (distance 0) followed by its k-1 nearest other rows, ascending; k = UMAP's n_neighbors.
+ *                            umap-learn searches exactly below 4 096 samples and with NN-descent above; the arrays
+ *                            are what UMAP(precomputed_knn=(idx, dist)) takes.
+ *   irp_umap_fuzzy_weights : umap_.py smooth_knn_dist (rho, sigma by binary search; n_iter 64, bandwidth 1 and
+ *                            local_connectivity 1 are UMAP's defaults) + compute_membership_strengths: d_vals
+ *                            [n_rows, k] = weight of the directed edge i -> d_idx[i, j] (0 for i itself), float32
+ *                            arithmetic like umap-learn's numba kernels.  The symmetrisation A + A^T - A.A^T, the
+ *                            categorical intersection with the labels and the layout stay host-side with UMAP.
+ *                            Workspace: 8 bytes.
+ * parity unpinned: umap-learn cannot be installed in the build container; oracle/umap_graph_ref.py restates the
+ * published functions and is pinned to sklearn's brute-force neighbours and to the defining equations only.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t irp_knn_graph_workspace_bytes(int64_t n_rows, int dim, int k);
+int irp_knn_graph(const float* d_z, int64_t n_rows, int dim, int k, int32_t* d_idx, float* d_dist, void* d_workspace,
+                  size_t workspace_bytes, void* stream);
+int irp_umap_fuzzy_weights(const int32_t* d_idx, const float* d_dist, int64_t n_rows, int k, float local_connectivity,
+                           float bandwidth, int n_iter, float* d_sigma, float* d_rho, float* d_vals, void* d_workspace,
+                           size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

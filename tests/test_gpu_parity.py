@@ -728,6 +728,58 @@ def test_create_pca_embeddings_returns_a_working_sklearn_pca(lib):
         dc.create_embeddings(x, labels)  # umap-learn is absent here; the reference fails at import time
 
 
+# ------------------------------------------------------------------ N4 UMAP graph construction (parity unpinned)
+@pytest.mark.parametrize("n,d,k", [(600, 20, 15), (3000, 50, 15), (257, 8, 30), (40, 3, 5)])
+def test_knn_graph_and_fuzzy_weights_match_oracle(lib, n, d, k):
+    """irp_knn_graph / irp_umap_fuzzy_weights against oracle/umap_graph_ref.py (umap-learn 0.5.7 restated; parity
+    unpinned).  Neighbours: distances within 1e-6 relative, index rows equal wherever a row's distances are all
+    distinct.  sigma within 1e-3 relative (the bisection stops on |psum - log2 k| < 1e-5, reached a step earlier or
+    later depending on the last bits of expf), rho exact, edge weights within 1e-4."""
+    from irp_b200 import ops
+    from oracle import umap_graph_ref as ug
+    rng = np.random.default_rng(n + d)
+    x = rng.normal(size=(n, d)).astype(np.float32) * (1.0 + 3.0 * rng.random((n, 1)).astype(np.float32))
+    x[3] = x[4]  # exact duplicates: zero distances next to the row itself
+    idx_r, dist_r = ug.nearest_neighbors(x, k)
+    xt = torch.from_numpy(x).cuda()
+    idx_t, dist_t = ops.knn_graph(xt, k)
+    idx, dist = idx_t.cpu().numpy(), dist_t.cpu().numpy()
+    assert np.array_equal(idx[:, 0], np.arange(n)) and np.all(dist[:, 0] == 0)
+    assert np.abs(dist - dist_r).max() <= 1e-6 * max(1.0, dist_r.max())
+    # rows 3 and 4 are the same point: as neighbours they are interchangeable (when only one of them fits below the
+    # k-th distance, which one is kept is a tie) -> compare with 4 renamed to 3
+    canon = lambda a: np.where(a == 4, 3, a)  # noqa: E731
+    distinct = np.array([np.unique(r).size == k for r in dist_r])
+    assert np.array_equal(canon(idx[distinct]), canon(idx_r[distinct]))
+    for i in np.flatnonzero(~distinct):
+        assert set(canon(idx[i]).tolist()) == set(canon(idx_r[i]).tolist())
+    assert np.all(np.diff(dist, axis=1) >= 0)
+    # weights on the ORACLE's arrays (stage-wise parity)
+    sig_r, rho_r = ug.smooth_knn_dist(dist_r, float(k))
+    _, _, vals_r = ug.compute_membership_strengths(idx_r, dist_r, sig_r, rho_r)
+    sig, rho, vals = ops.umap_fuzzy_weights(torch.from_numpy(idx_r).cuda(), torch.from_numpy(dist_r).cuda())
+    assert np.array_equal(rho.cpu().numpy(), rho_r)
+    assert np.abs(sig.cpu().numpy() - sig_r).max() <= 1e-3 * sig_r.max()
+    assert np.abs(vals.cpu().numpy().reshape(-1) - vals_r).max() <= 1e-4
+    # the defining equation on the device result itself
+    s = sig.cpu().numpy().astype(np.float64)
+    psum = np.exp(-np.maximum(dist_r[:, 1:].astype(np.float64) - rho_r[:, None], 0) / s[:, None]).sum(1)
+    assert np.abs(psum - np.log2(k)).max() < 1e-3
+
+
+def test_fuzzy_simplicial_set_mirror_matches_oracle_graph(lib):
+    from irp_b200 import umap_graph
+    from oracle import umap_graph_ref as ug
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=(900, 16)).astype(np.float32)
+    g, sig, rho = umap_graph.fuzzy_simplicial_set(x, 15)
+    gr, sig_r, rho_r = ug.fuzzy_simplicial_set(x, 15)
+    assert abs(g.tocsr() - g.tocsr().T).max() == 0
+    assert abs(g.tocsr() - gr.tocsr()).max() <= 2e-4 and np.array_equal(rho, rho_r)
+    idx, dist = umap_graph.nearest_neighbors(x, 15)
+    assert idx.dtype == np.int32 and dist.dtype == np.float32 and idx.shape == (900, 15)
+
+
 def test_whole_stage_against_reference_route(trunk):
     """Config-1-shaped run (reduced to 160 images): every stage fed the oracle's previous-stage output."""
     from irp_b200.stage import OutlierStage, pack_images

@@ -256,3 +256,55 @@ def test_image_hash_restatement_matches_reference_golden_and_pillow_in_process()
 def _lib_geometry_taps(h, w):
     from irp_b200 import _lib
     return _lib.geometry(h, w, _lib.TRANSFORM_HASH_64)[4]
+
+
+# ------------------------------------------------------------------ N4 UMAP graph construction (parity unpinned)
+def test_umap_graph_ref_neighbours_match_sklearn_bruteforce_and_the_defining_equations():
+    """umap-learn is absent: the restatement is pinned to scikit-learn's exact neighbours and to the equations of
+    umap_.py smooth_knn_dist / compute_membership_strengths / fuzzy_simplicial_set."""
+    from sklearn.neighbors import NearestNeighbors
+    from oracle import umap_graph_ref as ug
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(600, 20)).astype(np.float32)
+    x[5] = x[6]  # an exact duplicate: rho must skip the zero distance
+    k = 15
+    idx, d = ug.nearest_neighbors(x, k)
+    dd, ii = NearestNeighbors(n_neighbors=k, algorithm="brute").fit(x.astype(np.float64)).kneighbors(
+        x.astype(np.float64))
+    assert np.abs(d - dd).max() <= 1e-6
+    for i in range(600):  # equal up to the order of exactly tied distances
+        assert set(idx[i].tolist()) == set(ii[i].tolist()) or np.unique(dd[i]).size < k
+    sig, rho = ug.smooth_knn_dist(d, float(k))
+    first_pos = np.array([row[row > 0][0] for row in d])
+    assert np.array_equal(rho, first_pos)
+    psum = np.exp(-np.maximum(d[:, 1:] - rho[:, None], 0) / sig[:, None]).sum(1)
+    assert np.abs(psum - np.log2(k)).max() < 1e-4
+    rows, cols, vals = ug.compute_membership_strengths(idx, d, sig, rho)
+    v = vals.reshape(600, k)
+    assert np.all(v[idx == np.arange(600)[:, None]] == 0) and np.all((v >= 0) & (v <= 1))
+    nearest = np.array([np.flatnonzero(row > 0)[0] for row in d])
+    assert np.all(v[np.arange(600), nearest] == 1.0)  # local_connectivity = 1: the nearest neighbour has weight 1
+    g, _, _ = ug.fuzzy_simplicial_set(x, k)
+    g = g.tocsr()
+    assert abs(g - g.T).max() == 0 and g.data.min() > 0 and g.data.max() <= 1.0
+    a = np.zeros((600, 600), np.float64)
+    keep = cols != rows
+    a[rows[keep], cols[keep]] = vals[keep]
+    assert np.abs(g.toarray() - (a + a.T - a * a.T)).max() <= 1e-6
+
+
+def test_create_embeddings_hands_device_knn_to_umap(monkeypatch):
+    """The drop-in passes UMAP's own precomputed_knn parameter (host logic only: the device call is stubbed)."""
+    import sys
+    import types
+    from functions import data_curation as dc
+    from irp_b200 import umap_graph
+    calls = {}
+    monkeypatch.setattr(umap_graph, "nearest_neighbors",
+                        lambda x, k, device=None: calls.setdefault("knn", (x.shape, k)) and ("IDX", "DIST"))
+    z = np.zeros((40, 5), np.float32)
+    p = dc._with_device_knn({"n_components": 2, "random_state": 42}, z)
+    assert p["precomputed_knn"] == ("IDX", "DIST") and calls["knn"] == ((40, 5), 15)
+    assert "precomputed_knn" not in dc._with_device_knn({"metric": "cosine"}, z)
+    assert dc._with_device_knn({"precomputed_knn": (1, 2)}, z)["precomputed_knn"] == (1, 2)
+    assert "precomputed_knn" not in dc._with_device_knn({"n_neighbors": 50}, z)  # fewer rows than neighbours
