@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3x3_c64_kernel(const __gri
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    {  // whole warp, converged; the tcgen05 instructions are issued by the elected lane (elect_one(), ptx.cuh)
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       const uint32_t w_addr = smem_u32(smem_w);
       int slot = 0;
@@ -130,19 +130,22 @@ __global__ void __launch_bounds__(kC64Threads, 1) conv3x3_c64_kernel(const __gri
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 64;
         const uint32_t patch = smem_u32(smem_patch + slot * kC64PatchStride);
+        if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const uint32_t a0 = patch + ((t / 3) * kC64PatchW + (t % 3)) * 128;
-          const uint32_t b0 = w_addr + t * 8192;
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t a0 = patch + ((t / 3) * kC64PatchW + (t % 3)) * 128;
+            const uint32_t b0 = w_addr + t * 8192;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc_sw128(a0 + k * 32, kC64PatchW * 128);
-            const uint64_t db = umma_smem_desc_sw128(b0 + k * 32, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (t | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = umma_smem_desc_sw128(a0 + k * 32, kC64PatchW * 128);
+              const uint64_t db = umma_smem_desc_sw128(b0 + k * 32, 1024);
+              umma_bf16(tmem_d, da, db, idesc, (t | k) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&empty_bar[slot]);
+          umma_commit(&tfull_bar[acc]);
         }
-        umma_commit(&empty_bar[slot]);
-        umma_commit(&tfull_bar[acc]);
+        __syncwarp();
         if (++slot == kC64Slots) {
           slot = 0;
           phase ^= 1;

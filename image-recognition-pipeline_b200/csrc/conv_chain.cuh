@@ -224,43 +224,54 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     }
   } else if (warp == 1) {
     // ============================ MMA issuer (leader CTA only) ============================
-    if (rank == 0 && lane == 0) {
+    // The whole warp runs the loop converged; the tcgen05 instructions are issued by the elected lane (elect_one()):
+    // issued from an `if (lane == 0)` region, each MMA cost ~100 cycles of ELECT / R2UR waterfall and this thread's
+    // 540 instructions per pass -- not the epilogue, the tensor pipe (21 %) or HBM -- set the pass time.
+    if (rank == 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(2 * kTileM, kChainBN1);
       constexpr uint32_t idesc2 = umma_idesc_bf16(2 * kTileM, N2);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a));
+      const uint32_t b1_lo0 = umma_desc_lo(smem_u32(smem_b1));
+      const uint32_t ring_lo0 = umma_desc_lo(smem_u32(smem_ring));
+      const uint32_t b2_lo0 = umma_desc_lo(smem_u32(smem_b2));
       int stage = 0;
       uint32_t phase = 0;
       int my_tiles = 0;
       for (int mt = pair; mt < pair_tiles; mt += num_pairs) ++my_tiles;
       const int total_passes = my_tiles * P;
       const int kt = p.k1_blocks + p.k2_blocks;
-      // GEMM2 of global pass h (tile h / P, pass h % P)
-      auto gemm2 = [&](int h) {
-        const int i = h / P, ps = h - i * P;
-        if (ps == 0) {
-          mbar_wait(acc2_empty, (i & 1) ^ 1);
+      int i2 = 0, ps2 = 0, b2n = 0;  // GEMM2 runs one pass behind GEMM1: its (tile, pass) and W1' k-block counters
+      // GEMM2 of the next pending pass (tile i2, pass ps2)
+      auto gemm2 = [&]() {
+        if (ps2 == 0) {
+          mbar_wait(acc2_empty, (i2 & 1) ^ 1);
           tc_fence_after();
         }
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const int q = q_pass(i, ps, c);
+        for (int c = 0; c < 2; ++c, ++b2n) {
+          const int q = q_pass(i2, ps2, c);
           const int b = q % R;
-          const int b2n = 2 * h + c;
           const int s2 = b2n % kB2;
           mbar_wait(&ychunk_full[b], (q / R) & 1);
           mbar_wait(&b2full[s2], (b2n / kB2) & 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_ring + b * kStgChunkBytes);
-          const uint32_t b_addr = smem_u32(smem_b2 + s2 * S::kB2Bytes);
+          const uint32_t a_lo = ring_lo0 + b * (kStgChunkBytes >> 4);
+          const uint32_t b_lo = b2_lo0 + s2 * (S::kB2Bytes >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc<128>(a_addr + k * 32);
-            const uint64_t db = umma_smem_desc<128>(b_addr + k * 32);
-            umma_bf16_cg2(tmem_base + kAcc2Col, da, db, idesc2, (ps | c | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_cg2_lohi(tmem_base + kAcc2Col, a_lo + 2 * k, b_lo + 2 * k, kUmmaDescHiSw128, idesc2,
+                                 (ps2 | c | k) != 0 ? 1u : 0u);
+            umma_commit_cg2(&b2empty[s2], 3);
+            umma_commit_cg2(&stg_empty[b], 3);  // second arrival on the ring buffer (the first is its TMA store)
+            if (c == 1 && ps2 == P - 1) umma_commit_cg2(acc2_full, 3);
           }
-          umma_commit_cg2(&b2empty[s2], 3);
-          umma_commit_cg2(&stg_empty[b], 3);  // second arrival on the ring buffer (the first is its TMA store)
+          __syncwarp();
         }
-        if (ps == P - 1) umma_commit_cg2(acc2_full, 3);
+        if (++ps2 == P) {
+          ps2 = 0;
+          ++i2;
+        }
       };
       for (int g = 0; g < total_passes; ++g) {
         const int a1 = g & 1;
@@ -270,24 +281,24 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         for (int kb = 0; kb < kt; ++kb) {
           mbar_wait(&full1[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
-          const uint32_t b_addr = smem_u32(smem_b1 + stage * S::kB1Bytes);
+          const uint32_t a_lo = a_lo0 + stage * (S::kABytes >> 4);
+          const uint32_t b_lo = b1_lo0 + stage * (S::kB1Bytes >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc<128>(a_addr + k * 32);
-            const uint64_t db = umma_smem_desc<128>(b_addr + k * 32);
-            umma_bf16_cg2(tmem_d, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_cg2_lohi(tmem_d, a_lo + 2 * k, b_lo + 2 * k, kUmmaDescHiSw128, idesc1, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_cg2(&empty1[stage], 3);
+            if (kb == kt - 1) umma_commit_cg2(&acc1_full[a1], 3);
           }
-          umma_commit_cg2(&empty1[stage], 3);
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_cg2(&acc1_full[a1], 3);
-        if (g >= 1) gemm2(g - 1);
+        if (g >= 1) gemm2();
       }
-      if (total_passes > 0) gemm2(total_passes - 1);
+      if (total_passes > 0) gemm2();
     }
   } else {
     // ============================ epilogue (warps 2..9, both CTAs) ============================

@@ -212,8 +212,12 @@ __global__ void __launch_bounds__(kConv2Threads, 1) conv_gemm2_kernel(const __gr
     }
   } else if (warp == 1) {
     // ============================ MMA issuer (leader CTA only) ============================
-    if (rank == 0 && lane == 0) {
+    // The WHOLE warp runs the loop (converged: barrier waits, stage / phase counters and descriptor words are uniform);
+    // the tcgen05 instructions are issued by the elected lane (see elect_one()).
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * kTileM, BN);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a));
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem_b));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -225,21 +229,21 @@ __global__ void __launch_bounds__(kConv2Threads, 1) conv_gemm2_kernel(const __gr
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * S::kBBytes);
+          const uint32_t a_lo = a_lo0 + stage * (S::kABytes >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (S::kBBytes >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_smem_desc<128>(a_addr + k * 32);
-            const uint64_t db = umma_smem_desc<128>(b_addr + k * 32);
-            umma_bf16_cg2(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)  // 32 bytes of K per MMA = 2 descriptor address units
+              umma_bf16_cg2_lohi(tmem_d, a_lo + 2 * k, b_lo + 2 * k, kUmmaDescHiSw128, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_cg2(&empty_bar[stage], 3);  // frees the slot in both CTAs once these MMAs have read it
+            if (kb == k_blocks - 1) umma_commit_cg2(&tfull_bar[acc], 3);  // accumulator complete -> both epilogues
           }
-          umma_commit_cg2(&empty_bar[stage], 3);  // frees the slot in both CTAs once these MMAs have read it
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_cg2(&tfull_bar[acc], 3);  // accumulator complete -> both CTAs' epilogues
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

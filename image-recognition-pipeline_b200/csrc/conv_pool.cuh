@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kCpThreads, 1) conv_pool_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp, converged; the tcgen05 instructions are issued by the elected lane (elect_one(), ptx.cuh)
       constexpr uint32_t idesc = umma_idesc_bf16(128, kCpN);
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
@@ -149,17 +149,20 @@ __global__ void __launch_bounds__(kCpThreads, 1) conv_pool_kernel(const __grid_c
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_w + kb * kCpABytes);
           const uint32_t b_addr = smem_u32(smem_x + slot * kCpBBytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_d, umma_smem_desc<128>(a_addr + k * 32), umma_smem_desc<128>(b_addr + k * 32), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[slot]);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_d, umma_smem_desc<128>(a_addr + k * 32), umma_smem_desc<128>(b_addr + k * 32), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[slot]);
+            if (kb == kCpKBlocks - 1) umma_commit(&tfull_bar[acc]);
+          }
+          __syncwarp();
           if (++slot == kCpSlots) {
             slot = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

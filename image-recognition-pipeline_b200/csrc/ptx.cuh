@@ -253,6 +253,43 @@ __device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t desc_a, 
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a CONVERGED warp (elect.sync): the MMA warp runs its issue loop with all 32 lanes, so that addresses,
+// descriptors and loop counters stay in uniform registers, and only the tcgen05 instructions are predicated on the
+// elected lane.  (Issued from inside an `if (lane == 0)` region instead, every tcgen05.mma costs a waterfall of
+// ELECT + five R2UR.BROADCAST + BRA.U.ANY around it, ~100 cycles per MMA: the N <= 128 convolutions, 64 tensor cycles
+// per MMA, were bound by that issue rate, not by the tensor pipe.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// high word of a K-major SWIZZLE_128B descriptor with 1024-byte 8-row groups (SBO = 64, version 1, layout 2) and the
+// low word for a shared-memory address (start address >> 4 in bits [0,14), LBO = 1 in bits [16,30))
+constexpr uint32_t kUmmaDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+// tcgen05.mma.cta_group::2 with the descriptors given as (low, high) words; `desc_hi` is shared by A and B
+__device__ __forceinline__ void umma_bf16_cg2_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                   uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrives (once the pair's previously issued MMAs have completed) on the barrier at this offset in every CTA of mask
 __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t mask) {
   asm volatile(

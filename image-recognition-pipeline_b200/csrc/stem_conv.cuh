@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_pool_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp, converged; the tcgen05 instructions are issued by the elected lane (elect_one(), ptx.cuh)
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       const uint32_t w_addr = smem_u32(smem_w);
       int slot = 0;
@@ -149,21 +149,24 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_pool_kernel(const __grid_c
         mbar_wait(&full_bar[slot], phase);
         tc_fence_after();
         const uint32_t patch = smem_u32(smem_patch + slot * kSpPatchStride);
+        if (elect_one()) {
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const uint32_t tmem_d = tmem_base + acc * 128 + sub * 64;
+          for (int sub = 0; sub < 2; ++sub) {
+            const uint32_t tmem_d = tmem_base + acc * 128 + sub * 64;
 #pragma unroll
-          for (int r = 0; r < 7; ++r) {
+            for (int r = 0; r < 7; ++r) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint64_t da = umma_desc_noswz(patch + r * kSpPitch + h * 32 + sub * 128, 16, 2 * kSpPitch);
-              const uint64_t db = umma_desc_noswz(w_addr + (r * 2 + h) * 2048, 128, 256);
-              umma_bf16(tmem_d, da, db, idesc, (r | h) != 0 ? 1u : 0u);
+              for (int h = 0; h < 2; ++h) {
+                const uint64_t da = umma_desc_noswz(patch + r * kSpPitch + h * 32 + sub * 128, 16, 2 * kSpPitch);
+                const uint64_t db = umma_desc_noswz(w_addr + (r * 2 + h) * 2048, 128, 256);
+                umma_bf16(tmem_d, da, db, idesc, (r | h) != 0 ? 1u : 0u);
+              }
             }
           }
+          umma_commit(&empty_bar[slot]);
+          umma_commit(&tfull_bar[acc]);
         }
-        umma_commit(&empty_bar[slot]);
-        umma_commit(&tfull_bar[acc]);
+        __syncwarp();
         if (++slot == kSpSlots) {
           slot = 0;
           phase ^= 1;
