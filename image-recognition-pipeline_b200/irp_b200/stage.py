@@ -471,6 +471,26 @@ class OutlierStage:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
 
             res = self.backend.lof_sharded_multi(z_all, problems, rank, ws, all_reduce)
+        elif len(problems) == 2 and self.device.type == "cuda":
+            # one rank: the per-class and the global problem are independent -> the per-class one runs on a side
+            # stream beside the global one (its grid leaves SMs idle in the last wave, and its group-id validation
+            # synchronises only the side stream)
+            main = torch.cuda.current_stream(self.device)
+            if getattr(self, "_lof_stream", None) is None:
+                self._lof_stream = torch.cuda.Stream(device=self.device)
+            side = self._lof_stream
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            g_res = self.backend.lof(z_all, *problems[1][:1], *problems[1][1:])
+            with torch.cuda.stream(side):
+                c_res = self.backend.lof(z_all, *problems[0][:1], *problems[0][1:])
+                done = torch.cuda.Event()
+                done.record(side)
+            main.wait_event(done)
+            for t in c_res:
+                t.record_stream(main)
+            res = [c_res, g_res]
         else:
             res = [self.backend.lof(z_all, g, ng, k, c) for (g, ng, k, c) in problems]
         gs, _, gf = res[-1]

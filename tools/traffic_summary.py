@@ -15,9 +15,9 @@ def load(path):
 out = {}
 t = load(os.path.join(ROOT, "profiles", "r02_ncu_trunk_traffic.csv"))
 s = next(i for i, d in enumerate(t) if 'stem_pool' in d['name'])
-t = (t[s:] + t[:s])[:46]
+t = (t[s:] + t[:s])[:45]
 out["trunk_call_batch256"] = {"bytes": sum(d['dram__bytes_read.sum'] + d['dram__bytes_write.sum'] for d in t),
-                              "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the 46 kernels of one trunk "
+                              "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the 45 kernels of one trunk "
                                         "call at batch 256, profiles/r02_ncu_trunk_traffic.csv"}
 p = load(os.path.join(ROOT, "profiles", "r02_ncu_pre_launches.csv"))
 calls = [d for d in p if 'resample_fused' in d['name']]
