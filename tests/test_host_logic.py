@@ -136,3 +136,12 @@ def test_classifier_drop_ins_refuse_to_run_without_the_cuda_path():
         B200Classifier(model, "cpu")
     with pytest.raises(ValueError):
         B200Classifier(torch.nn.Linear(4, 4), "cpu")
+
+
+def test_bench_union_of_intervals():
+    """bench.py times the trunk as the union of the lanes' call intervals (overlapping calls must not add up)."""
+    import bench
+    assert bench.union_ms([]) == 0.0
+    assert bench.union_ms([(0.0, 1.0), (2.0, 3.5)]) == 2.5
+    assert bench.union_ms([(0.0, 2.0), (1.0, 3.0), (2.5, 2.75)]) == 3.0      # overlapping / nested
+    assert bench.union_ms([(5.0, 6.0), (0.0, 1.0), (0.5, 5.5)]) == 6.0       # unsorted input
