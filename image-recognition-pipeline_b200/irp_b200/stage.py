@@ -71,9 +71,13 @@ class ResNet50Trunk:
                                                            C.c_float(bn.eps), stream), f"load_conv[{i}]")
             torch.cuda.synchronize(idx)
 
-    def lane(self) -> "ResNet50Trunk":
-        """A second handle (own activation arena and tensor maps) built from the same weights, for a second lane."""
-        return ResNet50Trunk(self._model, self.device, self.max_batch)
+    def lanes(self, n: int) -> List["ResNet50Trunk"]:
+        """[self] + (n - 1) further handles (own activation arenas and tensor maps) built from the same weights, for
+        CudaBackend(lanes=n); created once and shared by every stage that runs on this trunk, closed with it."""
+        extra = self.__dict__.setdefault("_lane_handles", [])
+        while len(extra) < n - 1:
+            extra.append(ResNet50Trunk(self._model, self.device, self.max_batch))
+        return [self] + extra[: n - 1]
 
     @property
     def handle(self) -> int:
@@ -96,6 +100,8 @@ class ResNet50Trunk:
         return torch.cat(out, 0)
 
     def close(self):
+        for t in self.__dict__.pop("_lane_handles", []):
+            t.close()
         if self._handle:
             self.lib.irp_resnet50_destroy(self._handle)
             self._handle = C.c_void_p()
@@ -222,7 +228,7 @@ class CudaBackend:
     def ensure_lanes(self):
         """The extra handles (activation arenas) and streams are created at the first multi-batch pass."""
         if self.n_lanes > 1 and not self.lane_streams:
-            self.lane_trunks = [self.trunk] + [self.trunk.lane() for _ in range(self.n_lanes - 1)]
+            self.lane_trunks = self.trunk.lanes(self.n_lanes)
             self.lane_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_lanes)]
 
     def embed(self, part: PackedImages, max_taps: int, lane: Optional[int] = None) -> torch.Tensor:

@@ -46,8 +46,6 @@ for lanes in (1, 2, 3, 1, 2):
     print(f"embed_packed lanes {lanes}: {ms:.2f} ms for {n_img} images ({n_img / ms:.1f} k img/s), "
           f"max|diff| vs one lane {diff:.3g}", flush=True)
     results.append({"lanes": lanes, "ms": ms, "images": n_img, "max_abs_diff": diff})
-    for t in stage.backend.lane_trunks[1:]:
-        t.close()
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", "lane_probe.jsonl"), "w") as fh:
     for r in results:
