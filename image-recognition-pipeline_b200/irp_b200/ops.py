@@ -255,6 +255,17 @@ def _(z, group, n_groups, n_neighbors, contamination):
             z.new_empty(n, dtype=torch.uint8))
 
 
+_side_streams = {}
+
+
+def _side_stream(device: torch.device) -> torch.cuda.Stream:
+    """One extra stream per device for work that runs beside the caller's stream (created on first use)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 @_on_device_of(0)
 def lof_sharded_multi(z: torch.Tensor, problems, part: int, n_parts: int, all_reduce):
     """Several irp_lof problems over the SAME rows (e.g. per-class and global scoring) with the O(n^2) neighbour
@@ -275,9 +286,24 @@ def lof_sharded_multi(z: torch.Tensor, problems, part: int, n_parts: int, all_re
     buf = lambda: torch.empty((np_, n), dtype=torch.float64, device=z.device)
     kdist, lrd, score = buf(), buf(), buf()
     st = _stream(z)
+    # The neighbour searches (the O(n^2) phase) of the problems are independent: all but the last run on a side stream
+    # beside the last one, and the caller's stream joins them before the first exchange.
+    main = torch.cuda.current_stream(z.device)
+    side = _side_stream(z.device) if np_ > 1 else None
+    if side is not None:
+        fork = torch.cuda.Event()
+        fork.record(main)  # after every allocation above
+        side.wait_event(fork)
     for i, (group, n_groups, k, _) in enumerate(problems):
-        _lib.check(lib.irp_lof_knn_part(_ptr(z), n, d, _ptr(group), n_groups, int(k), part, n_parts, _ptr(kdist[i]),
-                                        _ptr(ws[i][0]), ws[i][1], st), "irp_lof_knn_part")
+        s_i = side if (side is not None and i < np_ - 1) else main
+        with torch.cuda.stream(s_i):
+            _lib.check(lib.irp_lof_knn_part(_ptr(z), n, d, _ptr(group), n_groups, int(k), part, n_parts,
+                                            _ptr(kdist[i]), _ptr(ws[i][0]), ws[i][1], C.c_void_p(s_i.cuda_stream)),
+                       "irp_lof_knn_part")
+    if side is not None:
+        joined = torch.cuda.Event()
+        joined.record(side)
+        main.wait_event(joined)
     all_reduce(kdist)
     for i, (_, n_groups, k, _) in enumerate(problems):
         _lib.check(lib.irp_lof_lrd_part(n, n_groups, int(k), part, n_parts, _ptr(kdist[i]), _ptr(lrd[i]),

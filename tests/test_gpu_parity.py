@@ -598,6 +598,21 @@ def test_lof_duplicates_and_unsorted_groups(ops_mod):
     assert torch.isfinite(scores).all()
 
 
+def test_lof_sharded_multi_two_problems_equal_the_single_calls(ops_mod):
+    """ops.lof_sharded_multi (per-class + global problem in lockstep, their neighbour searches side by side on two
+    streams) on one part with an identity all-reduce: bit-equal to two irp_lof calls, run twice for stream hazards."""
+    z, y = synth.clustered_points(4000, 20, 5, seed=3)
+    zt = torch.from_numpy(z).cuda()
+    ids = torch.from_numpy(y.astype(np.int32)).cuda()
+    problems = [(ids, 5, 30, 0.05), (None, 1, 75, 0.03)]
+    refs = [ops_mod.lof(zt, g, ng, k, c) for (g, ng, k, c) in problems]
+    for _ in range(2):
+        res = ops_mod.lof_sharded_multi(zt, problems, 0, 1, lambda t: None)
+        torch.cuda.synchronize()
+        for (s, o, f), (rs, ro, rf) in zip(res, refs):
+            assert torch.equal(s, rs) and torch.equal(o, ro) and torch.equal(f, rf)
+
+
 @pytest.mark.parametrize("n_parts", [2, 3, 8])
 def test_lof_sharded_over_parts_is_bitwise_the_single_call(lib, ops_mod, n_parts):
     """Multi-GPU form of irp_lof on ONE GPU: the parts (ranks) are run one after the other, their three fp64
